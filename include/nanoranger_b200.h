@@ -1,0 +1,142 @@
+/*
+ * nanoranger_b200.h -- C ABI of the B200 barcode matcher / UMI collapser.
+ *
+ * The reference (mehdiborji/nanoranger) has no FFI: the hot path is two bash scripts that
+ * exec STAR between two Python functions.  Each entry point below names the reference
+ * interface it replaces.  INTEGRATION.md shows the ctypes binding a maintainer would add to
+ * utils.py / pipeline.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes; no torch / C++ types cross this boundary
+ *   - "_device" entry points take device pointers, enqueue on `stream` (a cudaStream_t passed
+ *     as void*) and never synchronise; "_host" entry points take host pointers, do their own
+ *     H2D/D2H copies and return after the results are in the host buffers
+ *   - every function returns 0 on success or a negative NR_E* code; nr_last_error() gives the
+ *     message of the calling thread's last failure
+ *   - a handle is immutable after creation and may be used from several streams
+ */
+#ifndef NANORANGER_B200_H
+#define NANORANGER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NR_MAX_QUERY 64       /* longest candidate (nt) a packed record holds               */
+#define NR_MAX_CORE 32        /* longest scored core: 16 (10x) or 8+18+6 = 32 (slide-seq)   */
+
+/* error codes */
+#define NR_OK 0
+#define NR_EINVAL (-1)
+#define NR_ECUDA (-2)
+#define NR_ENOMEM (-3)
+#define NR_EUNSUPPORTED (-4)
+
+/* per-candidate flag bits (uint8) */
+#define NR_FLAG_TIE 0x01        /* more than one (entry, strand) pair attains the best score  */
+#define NR_FLAG_RC 0x02         /* the reported pair is on the reverse-complement strand      */
+#define NR_FLAG_BELOW 0x04      /* best score < min_score (filtered mode: score not resolved)  */
+#define NR_FLAG_NO_UMI 0x08     /* no optimal alignment reaches reference column padL+L        */
+#define NR_FLAG_TOO_LONG 0x10   /* candidate longer than NR_MAX_QUERY: not scored               */
+#define NR_FLAG_EXHAUSTIVE 0x20 /* resolved by the exhaustive kernel (informational)            */
+
+#define NR_SCORE_BELOW (-128)   /* score value reported together with NR_FLAG_BELOW            */
+#define NR_UMI_NONE 255
+
+/* matcher modes */
+#define NR_MODE_AUTO 0        /* filtered when the whitelist geometry allows it, else exhaustive */
+#define NR_MODE_EXHAUSTIVE 1  /* score every (entry, strand) pair; exact at every score          */
+#define NR_MODE_FILTERED 2    /* lossless seed filter + exact verification; exact for
+                                 score >= min_score, requires L == 16, N-free whitelist and
+                                 min_score >= L - 2                                              */
+
+typedef struct nr_whitelist nr_whitelist_t;
+
+const char *nr_last_error(void);
+const char *nr_version(void);
+
+/* ---- whitelist ("genome") -----------------------------------------------------------------
+ * Replaces scripts/barcode_ref.sh:11-18 (STAR --runMode genomeGenerate over the padded FASTA
+ * written by utils.write_bc_*, utils.py:584-622, 1116-1132, 1412-1458).
+ * cores: n * core_len ASCII bytes (ACGTN, row-major, no separators) -- the FASTA sequences
+ * without their N pads; pad_l / pad_r are the pad lengths.  Builds the packed whitelist and,
+ * when core_len == 16 and no entry contains N, the quarter-key seed index on `device`. */
+int nr_whitelist_create(const char *cores, uint64_t n, uint32_t core_len, uint32_t pad_l,
+                        uint32_t pad_r, int device, nr_whitelist_t **out);
+void nr_whitelist_destroy(nr_whitelist_t *wl);
+uint64_t nr_whitelist_size(const nr_whitelist_t *wl);
+int nr_whitelist_has_index(const nr_whitelist_t *wl);
+uint64_t nr_whitelist_device_bytes(const nr_whitelist_t *wl);
+
+/* ---- candidate packing ---------------------------------------------------------------------
+ * Replaces STAR's read loading (--readFilesIn/--readFilesCommand zcat,
+ * scripts/barcode_align.sh:16,35).  seqs: concatenated ASCII candidate sequences;
+ * offsets[i]..offsets[i+1] delimit candidate i (n + 1 offsets).  Outputs, all device:
+ *   bases  n x 16 bytes   2 bit/base, base k at bit 2k of the little-endian 128-bit record
+ *   meta   n bytes        length (0..64) | 0x80 if the candidate contains a non-ACGT byte;
+ *                         0xFF = longer than NR_MAX_QUERY
+ *   nmask  n x 8 bytes    bit k set where base k is not ACGT */
+int nr_pack_device(const uint8_t *d_seqs, const uint64_t *d_offsets, uint64_t n,
+                   void *d_bases, uint8_t *d_meta, uint64_t *d_nmask, void *stream);
+
+/* ---- matcher --------------------------------------------------------------------------------
+ * Replaces scripts/barcode_align.sh:14-41 (STAR EndToEnd alignment of every candidate against
+ * the N-padded whitelist, unique mappers only) plus the per-record geometry that
+ * utils.process_matching_* derives from the SAM (AS tag, flag, RNAME, query index aligned to
+ * reference column padL+L: utils.py:697-708, 843-856, 1148-1159, 1477-1497, 636-649).
+ * Per candidate i:
+ *   idx[i]    entry index of the best pair (smallest index among ties), -1 if none
+ *   score[i]  best AS over all entries and both strands (NR_SCORE_BELOW with NR_FLAG_BELOW)
+ *   nbest[i]  number of (entry, strand) pairs attaining it, saturated at 255
+ *   flags[i]  NR_FLAG_* bits
+ *   umi_q[i]  query index aligned to reference column padL+L, NR_UMI_NONE if undefined
+ * A candidate is "assigned" (would appear in STAR's SAM with flag 0 and pass the reference's
+ * threshold) iff nbest == 1 && !(flags & (NR_FLAG_RC|NR_FLAG_BELOW|NR_FLAG_TOO_LONG)) &&
+ * score >= min_score. */
+int nr_match_device(const nr_whitelist_t *wl, const void *d_bases, const uint8_t *d_meta,
+                    const uint64_t *d_nmask, uint64_t n, int min_score, int mode,
+                    int32_t *d_idx, int8_t *d_score, uint8_t *d_nbest, uint8_t *d_flags,
+                    uint8_t *d_umi_q, void *d_workspace, size_t workspace_bytes, void *stream);
+size_t nr_match_workspace_bytes(const nr_whitelist_t *wl, uint64_t n, int mode);
+
+/* Host-buffer form of the same call: H2D of the ASCII batch, pack, match, D2H of the five
+ * result arrays, all on an internal stream with pinned staging; returns when the host
+ * arrays are filled.  This is the call the reference-side stub binds. */
+int nr_match_host(const nr_whitelist_t *wl, const char *seqs, const uint64_t *offsets,
+                  uint64_t n, int min_score, int mode, int32_t *idx, int8_t *score,
+                  uint8_t *nbest, uint8_t *flags, uint8_t *umi_q);
+
+/* ---- UMI collapse ---------------------------------------------------------------------------
+ * Replaces the per-barcode exact UMI dedup of utils.py:759-777 (= 910-928, 1212-1230) and
+ * finishes what utils.make_count_mtx_3p10XGEX (utils.py:1523-1548) starts: records
+ * (barcode idx, gene id, 2-bit packed UMI) are sorted by (barcode, gene, umi); identical
+ * records collapse (max_dist = 0: the reference's np.unique), and with max_dist = 1 distinct
+ * UMIs of a (barcode, gene) group are merged by the directional one-hop rule.
+ * Outputs (device, caller-allocated, n entries each unless noted):
+ *   rep_umi[i]     representative UMI of the cluster record i belongs to
+ *   n_groups[0]    number of (barcode, gene, cluster) groups
+ *   g_bc/g_gene/g_umi/g_reads  the groups in sorted order with their read counts (>= n slots) */
+int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_gene, const uint32_t *d_umi,
+                           uint64_t n, int umi_len, int max_dist, uint32_t *d_rep_umi,
+                           uint64_t *d_n_groups, uint32_t *d_g_bc, uint32_t *d_g_gene,
+                           uint32_t *d_g_umi, uint32_t *d_g_reads, void *d_workspace,
+                           size_t workspace_bytes, void *stream);
+size_t nr_umi_workspace_bytes(uint64_t n);
+
+/* ---- measurement support -------------------------------------------------------------------
+ * INT-pipe roofline denominator: runs a dependent LOP3/IADD3 chain on
+ * every SM for `iters` iterations and returns executed integer thread-ops per second. */
+int nr_int_peak(int device, int iters, double *ops_per_s, double *ms);
+
+/* Counters of the last filtered launch on this stream-ordered workspace (debug/bench):
+ * c[0] probes, c[1] bitmap hits, c[2] NFA evaluations, c[3] full-DP verifications,
+ * c[4] candidates sent to the exhaustive kernel. */
+int nr_match_counters(const void *d_workspace, uint64_t *c5, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NANORANGER_B200_H */

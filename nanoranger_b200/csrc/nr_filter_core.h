@@ -1,0 +1,217 @@
+// nr_filter_core.h -- the arithmetic of the filtered matcher, written once for both the
+// sm_100a kernel (nr_match_filtered.cu) and the host-side emulation that tests/ compiles with
+// g++ to check the filter's losslessness against the oracle without a GPU
+// (tests/emul/filter_emul.cpp).  No CUDA runtime calls in here.
+//
+// Problem (scripts/barcode_align.sh:18-33 of the reference): a candidate Q
+// scores AS = 16 - cost against a 16-column N-free core, where cost is the cheapest way to
+// place the core inside Q with
+//     substitution 2, core column missing from Q (deletion) 2, extra Q base inside the core
+//     (insertion) 1, core column hanging over either end of Q 1 per column,
+//     Q prefix longer than padL / suffix longer than padR 1 per excess base.
+// The reference keeps AS >= 14 (utils.py:699, 845, 1150, 1479), i.e. cost <= 2.
+//
+// Filter.  Cut the core into four 4-column quarters.  Any placement of cost <= 2 damages at
+// most two quarters, and two only when both damages are cost-1 events (an insertion strictly
+// inside a quarter, or a one-column overhang).  Every placement is therefore found by at
+// least one of the probes in NR_PROBES: three quarters are read from Q at the stated offsets
+// (one of them possibly as a 5-mer with one interior base removed) and looked up in the
+// 24-bit "three of four quarters" index of the whitelist (nr_whitelist.cu).  A probe can
+// only nominate entries; every nominated (entry, strand) is scored exactly by nr_nfa16().
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define NR_HD __host__ __device__ __forceinline__
+#else
+#define NR_HD static inline
+#endif
+
+// ---- padded packed reads -------------------------------------------------------------------
+// rdp[0] = 0, rdp[1..4] = bases 0..63 (2 bit/base, base k at bit 2k), rdp[5..7] = 0.
+#define NR_RDP_WORDS 8
+
+NR_HD uint32_t nr_funnel_r(uint32_t lo, uint32_t hi, uint32_t s)  // 0 <= s < 32
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, s);
+#else
+    return s ? ((lo >> s) | (hi << (32u - s))) : lo;
+#endif
+}
+
+NR_HD int nr_popc32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+
+// 32 bases (64 bit) starting at base position p, -16 <= p <= 64.
+NR_HD uint64_t nr_window64(const uint32_t *rdp, int p)
+{
+    int q = p + 16;
+    int w = q >> 4;
+    uint32_t s = (uint32_t)(q & 15) * 2u;
+    uint32_t a = rdp[w], b = rdp[w + 1], c = (w + 2 < NR_RDP_WORDS) ? rdp[w + 2] : 0u;
+    uint32_t lo = nr_funnel_r(a, b, s);
+    uint32_t hi = nr_funnel_r(b, c, s);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+NR_HD int nr_read_base(const uint32_t *rdp, int i)  // 0 <= i < 64
+{
+    return (int)((rdp[1 + (i >> 4)] >> ((i & 15) * 2)) & 3u);
+}
+
+// forward words (bases >= m must be zero) -> reverse complement words
+NR_HD void nr_revcomp4(const uint32_t in[4], int m, uint32_t out[4])
+{
+    uint32_t r[6];
+    for (int k = 0; k < 4; k++) {
+        uint32_t x = ~in[3 - k];
+#if defined(__CUDA_ARCH__)
+        x = __brev(x);
+#else
+        x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+        x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+        x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+        x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+        x = (x >> 16) | (x << 16);
+#endif
+        // bit reversal also swapped the two bits of every base: swap them back
+        r[k] = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
+    }
+    r[4] = 0; r[5] = 0;
+    int sh = 64 - m;  // leading garbage bases to drop
+    int ws = sh >> 4;
+    uint32_t bs = (uint32_t)(sh & 15) * 2u;
+    for (int k = 0; k < 4; k++) {
+        uint32_t a = (k + ws < 6) ? r[k + ws] : 0u;
+        uint32_t b = (k + ws + 1 < 6) ? r[k + ws + 1] : 0u;
+        uint32_t v = nr_funnel_r(a, b, bs);
+        int lo = k * 16;
+        if (m <= lo) v = 0;
+        else if (m < lo + 16) v &= (1u << ((m - lo) * 2)) - 1u;
+        out[k] = v;
+    }
+}
+
+// ---- probes ----------------------------------------------------------------------------------
+// A probe reads the three kept quarters at offsets o[0..2] (bases, relative to the slot
+// position p) and drops quarter `drop`.  var = index (0..2) of the kept quarter that is read
+// as a 5-mer with interior base `del` (1..3) removed, or -1.
+struct nr_probe_t {
+    int8_t drop, o0, o1, o2, var, del;
+};
+
+#define NR_PROBES_MAIN 34   // run at every slot position
+#define NR_PROBES_EDGE 9    // run at p = -1 only (one-column start overhang + interior insertion)
+#define NR_PROBES_ALL (NR_PROBES_MAIN + NR_PROBES_EDGE)
+
+#define NR_V3(d, a, b, c, v) {d, a, b, c, v, 1}, {d, a, b, c, v, 2}, {d, a, b, c, v, 3}
+
+static constexpr nr_probe_t NR_PROBES[NR_PROBES_ALL] = {
+    // one damaged quarter (or none) plus boundary insertions
+    {0, 4, 8, 12, -1, 0}, {0, 4, 9, 13, -1, 0}, {0, 4, 8, 13, -1, 0},
+    {3, 0, 4, 8, -1, 0},  {3, 0, 5, 9, -1, 0},  {3, 0, 4, 9, -1, 0},
+    {1, 0, 7, 11, -1, 0}, {1, 0, 8, 12, -1, 0}, {1, 0, 9, 13, -1, 0}, {1, 0, 10, 14, -1, 0},
+    {1, 0, 9, 14, -1, 0},
+    {2, 0, 4, 11, -1, 0}, {2, 0, 4, 12, -1, 0}, {2, 0, 4, 13, -1, 0}, {2, 0, 4, 14, -1, 0},
+    {2, 0, 5, 14, -1, 0},
+    // interior insertions in two different quarters v < d: drop d, read v as 5-mer minus one
+    NR_V3(1, 0, 10, 14, 0), NR_V3(2, 0, 5, 14, 0), NR_V3(3, 0, 5, 9, 0),
+    NR_V3(2, 0, 4, 14, 1),  NR_V3(3, 0, 4, 9, 1),  NR_V3(3, 0, 4, 8, 2),
+    // p = -1 only: quarter 0 loses its first column to the read start, insertion inside v >= 1
+    NR_V3(0, 4, 9, 13, 0),  NR_V3(0, 4, 8, 13, 1), NR_V3(0, 4, 8, 12, 2),
+};
+
+// one kept quarter out of the 64-bit window W (base 0 of W = slot position p)
+NR_HD uint32_t nr_quarter(uint64_t W, int off, int del)
+{
+    uint32_t v = (uint32_t)(W >> (2 * off));
+    if (del == 0) return v & 0xFFu;
+    uint32_t low = v & ((1u << (2 * del)) - 1u);
+    uint32_t high = (v >> (2 * del + 2)) << (2 * del);
+    return (low | high) & 0xFFu;
+}
+
+// extent of the probe in Q: first base used and one past the last base used (relative to p)
+NR_HD int nr_probe_first(const nr_probe_t &t) { return t.o0; }
+NR_HD int nr_probe_end(const nr_probe_t &t) { return t.o2 + (t.var == 2 ? 5 : 4); }
+
+NR_HD uint32_t nr_probe_key(uint64_t W, const nr_probe_t &t)
+{
+    uint32_t a = nr_quarter(W, t.o0, t.var == 0 ? t.del : 0);
+    uint32_t b = nr_quarter(W, t.o1, t.var == 1 ? t.del : 0);
+    uint32_t c = nr_quarter(W, t.o2, t.var == 2 ? t.del : 0);
+    return a | (b << 8) | (c << 16);
+}
+
+// key of a whitelist core with quarter j removed (must agree with nr_probe_key)
+NR_HD uint32_t nr_core_key(uint32_t core, int j)
+{
+    switch (j) {
+    case 0: return core >> 8;
+    case 1: return (core & 0xFFu) | ((core >> 8) & 0xFFFF00u);
+    case 2: return (core & 0xFFFFu) | ((core >> 8) & 0xFF0000u);
+    default: return core & 0xFFFFFFu;
+    }
+}
+
+// slot positions worth probing for a read of length m: first..last inclusive
+NR_HD int nr_slot_first(int m, int padR) { int a = m - padR - 22; return a > -2 ? a : -2; }
+NR_HD int nr_slot_last(int m, int padL) { int a = m - 10, b = padL + 3; return a < b ? a : b; }
+
+// rows of Q the exact scorer must cover for a hit at slot position p
+NR_HD int nr_rows_first(int p) { return p - 3 > 0 ? p - 3 : 0; }
+NR_HD int nr_rows_last(int p, int m) { return p + 24 < m ? p + 24 : m; }
+
+// ---- exact scorer for cost <= 2 -----------------------------------------------------------------
+// Three-level shift-and automaton over the core columns, state j (1..16 columns consumed) at
+// bit 2(j-1); level k holds the states reachable with cost <= k.  State 0 (still in the left
+// pad) is implicit with cost z(i) = max(0, i - padL).  Rows r0..r1 of Q are consumed (r0 = 0
+// applies the start-overhang rule, r1 = m the end-overhang rule).  Returns the cost (0..2) of
+// the best placement inside those rows, 3 if none; *umi = smallest row at which a best
+// placement leaves the core (the query index aligned to reference column padL+16,
+// utils.py:705-708), -1 if the best placement ends inside the core.
+NR_HD int nr_nfa16(const uint32_t *rdp, int m, uint32_t core, int padL, int padR, int r0, int r1,
+                   int *umi)
+{
+    const uint32_t KEEP = 0x15555555u;   // states 1..15
+    const uint32_t FIN = 0x40000000u;    // state 16
+    uint32_t R0 = 0, R1, R2;
+    if (r0 == 0) { R1 = 1u; R2 = 5u; }
+    else { R1 = 0u; R2 = (r0 <= padL) ? 1u : 0u; }
+    int best = 3, arg = -1;
+    for (int i = r0; i < r1; i++) {
+        uint32_t c = (uint32_t)nr_read_base(rdp, i);
+        uint32_t x = core ^ (c * 0x55555555u);
+        uint32_t M = ~(x | (x >> 1)) & 0x55555555u;
+        int z = i - padL;                                   // cost of state 0 at row i (if > 0)
+        uint32_t S0 = (R0 << 2) | (z <= 0 ? 1u : 0u);
+        uint32_t S1 = (R1 << 2) | (z <= 1 ? 1u : 0u);
+        uint32_t S2 = (R2 << 2) | (z <= 2 ? 1u : 0u);
+        uint32_t A0 = S0 & M;
+        uint32_t A1 = (S1 & M) | (R0 & KEEP) | A0;
+        uint32_t A2 = (S2 & M) | (R1 & KEEP) | S0 | A1;
+        A2 |= (A0 << 2) | (z + 1 <= 0 ? 1u : 0u);           // one deleted column, cost 2
+        R0 = A0; R1 = A1; R2 = A2;
+        if (R2 & FIN) {
+            int k = (R0 & FIN) ? 0 : ((R1 & FIN) ? 1 : 2);
+            int t = m - (i + 1) - padR;
+            int tot = k + (t > 0 ? t : 0);
+            if (tot < best) { best = tot; arg = i + 1; }
+        }
+    }
+    if (r1 == m) {
+        int tot = 3;
+        if (R0 & 0x10000000u) tot = 1;                                   // state 15, cost 0
+        else if ((R1 & 0x10000000u) | (R0 & 0x04000000u)) tot = 2;      // 15 @1 or 14 @0
+        if (tot < best) { best = tot; arg = -1; }
+    }
+    *umi = arg;
+    return best;
+}

@@ -1,0 +1,338 @@
+// nr_match_exhaustive.cu -- score every (entry, strand) pair of a candidate: exact at every
+// score, any core length <= 32, N on either side.  This is the kernel that defines parity
+// with the oracle; the filtered kernel falls back to it for the candidates it cannot take.
+//
+// Replaces scripts/barcode_align.sh:14-41 (STAR EndToEnd, unique mappers only).
+//
+// DP on the core columns with closed-form pad boundaries, in the
+// gap-free form  H'[i][j] = S[i][j] + i + j:
+//     H'[i][j] = max(H'[i-1][j-1] + s + 2, H'[i-1][j], H'[i][j-1]),  s+2 in {3 match, 1 mismatch, 2 N}
+// so one cell is one VIMNMX + one VIADDMNMX.  The L = 16 / N-free-whitelist kernel keeps two
+// entries per thread in the s16x2 halves of every register (DPX), the 4 x 16 score profile
+// of the entry pair in registers, and walks the query rows with a warp-uniform base switch.
+#include "nr_common.cuh"
+
+namespace {
+
+struct Best {
+    int score;       // best AS
+    uint32_t cnt;    // pairs attaining it
+    uint32_t key;    // smallest (idx << 1 | strand) among them
+};
+
+__device__ __forceinline__ void best_add(Best &b, int score, uint32_t key)
+{
+    if (score > b.score) { b.score = score; b.cnt = 1; b.key = key; }
+    else if (score == b.score) { b.cnt++; b.key = min(b.key, key); }
+}
+
+__device__ __forceinline__ void best_merge(Best &a, int score, uint32_t cnt, uint32_t key)
+{
+    if (score > a.score) { a.score = score; a.cnt = cnt; a.key = key; }
+    else if (score == a.score) { a.cnt += cnt; a.key = min(a.key, key); }
+}
+
+__device__ __forceinline__ Best block_reduce_best(Best b, Best *sh /* >= 32 */)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        int s = __shfl_xor_sync(0xffffffffu, b.score, o);
+        uint32_t c = __shfl_xor_sync(0xffffffffu, b.cnt, o);
+        uint32_t k = __shfl_xor_sync(0xffffffffu, b.key, o);
+        // symmetric merge (both lanes end with the same value)
+        if (s > b.score) { b.score = s; b.cnt = c; b.key = k; }
+        else if (s == b.score) { b.cnt += c; b.key = min(b.key, k); }
+    }
+    int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (nr_lane() == 0) sh[warp] = b;
+    __syncthreads();
+    Best r = sh[0];
+    for (int w = 1; w < nw; w++) best_merge(r, sh[w].score, sh[w].cnt, sh[w].key);
+    __syncthreads();
+    return r;
+}
+
+// byte codes of the candidate (forward and reverse complement), 4 = N
+__device__ __forceinline__ void load_codes(const uint4 *bases, const uint64_t *nmask,
+                                           uint64_t cand, int m, uint8_t *cf, uint8_t *cr)
+{
+    const uint32_t *bw = reinterpret_cast<const uint32_t *>(bases + cand);
+    uint64_t nm = nmask ? nmask[cand] : 0ull;
+    for (int p = threadIdx.x; p < NR_MAX_QUERY; p += blockDim.x) {
+        int c = 4;
+        if (p < m) {
+            c = (int)((bw[p >> 4] >> ((p & 15) * 2)) & 3u);
+            if ((nm >> p) & 1ull) c = 4;
+        }
+        cf[p] = (uint8_t)c;
+        if (p < m) cr[m - 1 - p] = (uint8_t)(c > 3 ? 4 : 3 - c);
+        else cr[p] = 4;
+    }
+}
+
+// generic scalar pair DP on byte codes (any L <= 32, N aware): AS and UMI column.
+__device__ int pair_dp_codes(const uint8_t *q, int m, uint32_t lo, uint32_t hi, uint32_t nm,
+                             int L, int padL, int padR, int *iend)
+{
+    int C[NR_MAX_CORE + 1];
+    for (int j = 0; j <= L; j++) C[j] = 0;
+    int a_r = -max(0, m - padR), arg = 0;
+    for (int i = 1; i <= m; i++) {
+        int qq = q[i - 1];
+        int diag = C[0];
+        C[0] = -max(0, i - padL);
+        for (int j = 1; j <= L; j++) {
+            int col = j - 1;
+            int x = (int)(((col < 16 ? lo >> (2 * col) : hi >> (2 * (col - 16)))) & 3u);
+            int s = (qq > 3 || ((nm >> col) & 1u)) ? 0 : (x == qq ? 1 : -1);
+            int v = max(diag + s, max(C[j], C[j - 1]) - 1);
+            diag = C[j];
+            C[j] = v;
+        }
+        int v = C[L] - max(0, m - i - padR);
+        if (v > a_r) { a_r = v; arg = i; }
+    }
+    int a_in = -1000;
+    for (int j = 1; j < L; j++) a_in = max(a_in, C[j]);
+    int as = max(-max(0, m - padL), max(a_in, a_r));
+    *iend = (a_r == as) ? arg : -1;
+    return as;
+}
+
+__device__ __forceinline__ void write_result(const Best &r, uint64_t cand, int m,
+                                             const uint8_t *cf, const uint32_t *lo,
+                                             const uint32_t *hi, const uint32_t *nmw, int L,
+                                             int padL, int padR, int min_score, int32_t *o_idx,
+                                             int8_t *o_score, uint8_t *o_nbest, uint8_t *o_flags,
+                                             uint8_t *o_umi)
+{
+    int32_t idx = (int32_t)(r.key >> 1);
+    int strand = (int)(r.key & 1u);
+    uint8_t fl = NR_FLAG_EXHAUSTIVE;
+    if (r.cnt > 1) fl |= NR_FLAG_TIE;
+    if (strand) fl |= NR_FLAG_RC;
+    if (r.score < min_score) fl |= NR_FLAG_BELOW;
+    int u = -1;
+    if (!strand) {
+        int as = pair_dp_codes(cf, m, lo[idx], hi ? hi[idx] : 0u, nmw ? nmw[idx] : 0u, L, padL,
+                               padR, &u);
+        (void)as;
+    }
+    if (u < 0) fl |= NR_FLAG_NO_UMI;
+    o_idx[cand] = idx;
+    o_score[cand] = (int8_t)r.score;
+    o_nbest[cand] = (uint8_t)min(r.cnt, 255u);
+    o_flags[cand] = fl;
+    o_umi[cand] = (uint8_t)(u < 0 ? NR_UMI_NONE : u);
+}
+
+#define P2(x) ((uint32_t)((x) & 0xFFFF) * 0x10001u)
+
+// ---- L = 16, N-free whitelist: DPX s16x2, two entries per thread ---------------------------
+__global__ void __launch_bounds__(256, 2)
+nr_match_exhaustive16_kernel(const uint32_t *__restrict__ wl, uint32_t n, int padL, int padR,
+                             const uint4 *__restrict__ bases, const uint8_t *__restrict__ meta,
+                             const uint64_t *__restrict__ nmask,
+                             const uint32_t *__restrict__ list,
+                             const uint32_t *__restrict__ list_count, uint64_t n_cand,
+                             int min_score, int32_t *__restrict__ o_idx,
+                             int8_t *__restrict__ o_score, uint8_t *__restrict__ o_nbest,
+                             uint8_t *__restrict__ o_flags, uint8_t *__restrict__ o_umi)
+{
+    __shared__ uint8_t cf[NR_MAX_QUERY], cr[NR_MAX_QUERY];
+    __shared__ Best shb[32];
+    uint64_t total = list ? (uint64_t)*list_count : n_cand;
+    uint32_t npairs = (n + 1) >> 1;
+    for (uint64_t it = blockIdx.x; it < total; it += gridDim.x) {
+        uint64_t cand = list ? (uint64_t)list[it] : it;
+        uint8_t mt = meta[cand];
+        if (mt == 0xFF) {
+            if (threadIdx.x == 0) {
+                o_idx[cand] = -1; o_score[cand] = NR_SCORE_BELOW; o_nbest[cand] = 0;
+                o_flags[cand] = NR_FLAG_TOO_LONG | NR_FLAG_BELOW | NR_FLAG_NO_UMI;
+                o_umi[cand] = NR_UMI_NONE;
+            }
+            continue;
+        }
+        int m = mt & 0x7F;
+        __syncthreads();
+        load_codes(bases, (mt & 0x80) ? nmask : nullptr, cand, m, cf, cr);
+        __syncthreads();
+        Best b; b.score = -1000; b.cnt = 0; b.key = 0xFFFFFFFFu;
+        const uint32_t aleft = P2(-max(0, m - padL));
+        for (uint32_t p = threadIdx.x; p < npairs; p += blockDim.x) {
+            uint32_t ea = wl[2 * p];
+            bool vb = 2 * p + 1 < n;
+            uint32_t eb = vb ? wl[2 * p + 1] : ea;
+            // score profile: P[q][j] = s16x2 of (s + 2) = 1 + 2 * match
+            uint32_t P0[16], P1[16], P2_[16], P3[16];
+            {
+                uint32_t la = ea & 0x55555555u, ha = (ea >> 1) & 0x55555555u;
+                uint32_t lb = eb & 0x55555555u, hb = (eb >> 1) & 0x55555555u;
+                uint32_t w0 = ((~la & ~ha) & 0x55555555u) | (((~lb & ~hb) & 0x55555555u) << 1);
+                uint32_t w1 = ((la & ~ha)) | ((lb & ~hb) << 1);
+                uint32_t w2 = ((~la & ha)) | ((~lb & hb) << 1);
+                uint32_t w3 = ((la & ha)) | ((lb & hb) << 1);
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    P0[j] = 0x00010001u + (((((w0 >> (2 * j)) & 3u) * 0x8001u) & 0x00010001u) << 1);
+                    P1[j] = 0x00010001u + (((((w1 >> (2 * j)) & 3u) * 0x8001u) & 0x00010001u) << 1);
+                    P2_[j] = 0x00010001u + (((((w2 >> (2 * j)) & 3u) * 0x8001u) & 0x00010001u) << 1);
+                    P3[j] = 0x00010001u + (((((w3 >> (2 * j)) & 3u) * 0x8001u) & 0x00010001u) << 1);
+                }
+            }
+#pragma unroll 1
+            for (int strand = 0; strand < 2; strand++) {
+                const uint8_t *q = strand ? cr : cf;
+                uint32_t C[17];
+#pragma unroll
+                for (int j = 0; j <= 16; j++) C[j] = P2(j);
+                uint32_t ar = P2(-max(0, m - padR));
+#pragma unroll 1
+                for (int i = 1; i <= m; i++) {
+                    int qq = q[i - 1];
+                    uint32_t diag = C[0];
+                    C[0] = P2(min(i, padL));
+#define NR_ROW(PX)                                                              \
+    _Pragma("unroll") for (int j = 1; j <= 16; j++) {                           \
+        uint32_t t = C[j];                                                      \
+        C[j] = __viaddmax_s16x2(diag, PX, __vmaxs2(C[j], C[j - 1]));            \
+        diag = t;                                                               \
+    }
+                    if (qq == 0) { NR_ROW(P0[j - 1]) }
+                    else if (qq == 1) { NR_ROW(P1[j - 1]) }
+                    else if (qq == 2) { NR_ROW(P2_[j - 1]) }
+                    else if (qq == 3) { NR_ROW(P3[j - 1]) }
+                    else { NR_ROW(0x00020002u) }
+#undef NR_ROW
+                    uint32_t off = P2(i + 16 + max(0, m - i - padR));
+                    ar = __vmaxs2(ar, __vsub2(C[16], off));
+                }
+                uint32_t ain = P2(-1000);
+#pragma unroll
+                for (int j = 1; j < 16; j++) ain = __vmaxs2(ain, __vsub2(C[j], P2(m + j)));
+                uint32_t as2 = __vmaxs2(aleft, __vmaxs2(ain, ar));
+                int sa = (int)(int16_t)(as2 & 0xFFFFu);
+                int sb = (int)(int16_t)(as2 >> 16);
+                best_add(b, sa, ((2 * p) << 1) | (uint32_t)strand);
+                if (vb) best_add(b, sb, ((2 * p + 1) << 1) | (uint32_t)strand);
+            }
+        }
+        Best r = block_reduce_best(b, shb);
+        if (threadIdx.x == 0)
+            write_result(r, cand, m, cf, wl, nullptr, nullptr, 16, padL, padR, min_score, o_idx,
+                         o_score, o_nbest, o_flags, o_umi);
+    }
+}
+
+// ---- generic: any L <= 32, N columns in the whitelist; one entry per thread ----------------
+__global__ void __launch_bounds__(256)
+nr_match_exhaustive_generic_kernel(const uint32_t *__restrict__ wlo,
+                                   const uint32_t *__restrict__ whi,
+                                   const uint32_t *__restrict__ wnm, uint32_t n, int L, int padL,
+                                   int padR, const uint4 *__restrict__ bases,
+                                   const uint8_t *__restrict__ meta,
+                                   const uint64_t *__restrict__ nmask,
+                                   const uint32_t *__restrict__ list,
+                                   const uint32_t *__restrict__ list_count, uint64_t n_cand,
+                                   int min_score, int32_t *__restrict__ o_idx,
+                                   int8_t *__restrict__ o_score, uint8_t *__restrict__ o_nbest,
+                                   uint8_t *__restrict__ o_flags, uint8_t *__restrict__ o_umi)
+{
+    __shared__ uint8_t cf[NR_MAX_QUERY], cr[NR_MAX_QUERY];
+    __shared__ Best shb[32];
+    uint64_t total = list ? (uint64_t)*list_count : n_cand;
+    for (uint64_t it = blockIdx.x; it < total; it += gridDim.x) {
+        uint64_t cand = list ? (uint64_t)list[it] : it;
+        uint8_t mt = meta[cand];
+        if (mt == 0xFF) {
+            if (threadIdx.x == 0) {
+                o_idx[cand] = -1; o_score[cand] = NR_SCORE_BELOW; o_nbest[cand] = 0;
+                o_flags[cand] = NR_FLAG_TOO_LONG | NR_FLAG_BELOW | NR_FLAG_NO_UMI;
+                o_umi[cand] = NR_UMI_NONE;
+            }
+            continue;
+        }
+        int m = mt & 0x7F;
+        __syncthreads();
+        load_codes(bases, (mt & 0x80) ? nmask : nullptr, cand, m, cf, cr);
+        __syncthreads();
+        Best b; b.score = -1000; b.cnt = 0; b.key = 0xFFFFFFFFu;
+        const int aleft = -max(0, m - padL);
+        for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+            uint32_t lo = wlo[e], hi = whi ? whi[e] : 0u, nm = wnm ? wnm[e] : 0u;
+#pragma unroll 1
+            for (int strand = 0; strand < 2; strand++) {
+                const uint8_t *q = strand ? cr : cf;
+                int C[NR_MAX_CORE + 1];
+#pragma unroll
+                for (int j = 0; j <= NR_MAX_CORE; j++) C[j] = j;
+                int ar = -max(0, m - padR);
+#pragma unroll 1
+                for (int i = 1; i <= m; i++) {
+                    int qq = q[i - 1];
+                    int diag = C[0];
+                    C[0] = min(i, padL);
+                    // per-column s+2: match 3, mismatch 1, N 2
+                    uint32_t xl = lo ^ (uint32_t)(qq & 3) * 0x55555555u;
+                    uint32_t xh = hi ^ (uint32_t)(qq & 3) * 0x55555555u;
+                    uint32_t ml = ~(xl | (xl >> 1)) & 0x55555555u;   // bit 2c: column c matches
+                    uint32_t mh = ~(xh | (xh >> 1)) & 0x55555555u;
+                    bool qn = qq > 3;
+#pragma unroll
+                    for (int j = 1; j <= NR_MAX_CORE; j++) {
+                        int col = j - 1;
+                        uint32_t mb = col < 16 ? (ml >> (2 * col)) & 1u : (mh >> (2 * (col - 16))) & 1u;
+                        int sp = (qn || ((nm >> col) & 1u)) ? 2 : 1 + 2 * (int)mb;
+                        int t = C[j];
+                        int v = max(diag + sp, max(C[j], C[j - 1]));
+                        C[j] = (j <= L) ? v : C[j];
+                        diag = t;
+                    }
+                    int cl = C[0];
+#pragma unroll
+                    for (int j = 1; j <= NR_MAX_CORE; j++) if (j == L) cl = C[j];
+                    ar = max(ar, cl - (i + L + max(0, m - i - padR)));
+                }
+                int ain = -1000;
+#pragma unroll
+                for (int j = 1; j < NR_MAX_CORE; j++) if (j < L) ain = max(ain, C[j] - (m + j));
+                int as = max(aleft, max(ain, ar));
+                best_add(b, as, (e << 1) | (uint32_t)strand);
+            }
+        }
+        Best r = block_reduce_best(b, shb);
+        if (threadIdx.x == 0)
+            write_result(r, cand, m, cf, wlo, whi, wnm, L, padL, padR, min_score, o_idx, o_score,
+                         o_nbest, o_flags, o_umi);
+    }
+}
+
+}  // namespace
+
+// host launcher shared with the C API: either all n_cand candidates, or the device-resident
+// list (d_list, d_list_count) written by the filtered kernel.
+int nr_launch_exhaustive(const nr_whitelist *wl, const void *d_bases, const uint8_t *d_meta,
+                         const uint64_t *d_nmask, const uint32_t *d_list,
+                         const uint32_t *d_list_count, uint64_t n_cand, int min_score,
+                         int32_t *d_idx, int8_t *d_score, uint8_t *d_nbest, uint8_t *d_flags,
+                         uint8_t *d_umi, int grid_cap, cudaStream_t stream)
+{
+    if (!d_list && n_cand == 0) return NR_OK;
+    uint64_t want = d_list ? (uint64_t)grid_cap : n_cand;
+    unsigned grid = (unsigned)(want < 65535ull * 8 ? want : 65535ull * 8);
+    if (grid == 0) grid = 1;
+    if (wl->L == 16 && !wl->has_n) {
+        nr_match_exhaustive16_kernel<<<grid, 256, 0, stream>>>(
+            wl->d_lo, (uint32_t)wl->n, (int)wl->pad_l, (int)wl->pad_r, (const uint4 *)d_bases,
+            d_meta, d_nmask, d_list, d_list_count, n_cand, min_score, d_idx, d_score, d_nbest,
+            d_flags, d_umi);
+    } else {
+        nr_match_exhaustive_generic_kernel<<<grid, 256, 0, stream>>>(
+            wl->d_lo, wl->d_hi, wl->d_nm, (uint32_t)wl->n, (int)wl->L, (int)wl->pad_l,
+            (int)wl->pad_r, (const uint4 *)d_bases, d_meta, d_nmask, d_list, d_list_count,
+            n_cand, min_score, d_idx, d_score, d_nbest, d_flags, d_umi);
+    }
+    NR_CHECK_CUDA(cudaGetLastError());
+    return NR_OK;
+}

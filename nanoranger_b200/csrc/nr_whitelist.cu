@@ -1,0 +1,185 @@
+// nr_whitelist.cu -- whitelist handle: 2-bit packing, N mask and the quarter-key seed index.
+// Replaces scripts/barcode_ref.sh:11-18 (STAR genomeGenerate) for the matcher kernels.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include <thrust/device_ptr.h>
+#include <thrust/execution_policy.h>
+#include <thrust/sort.h>
+
+#include "nr_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void nr_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *nr_last_error(void) { return g_err; }
+extern "C" const char *nr_version(void) { return "nanoranger_b200 0.1 (sm_100a)"; }
+
+// ---------------------------------------------------------------------------------------
+
+__global__ void nr_index_keys_kernel(const uint32_t *__restrict__ lo, uint32_t n, int j,
+                                     uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        keys[i] = nr_key_drop(lo[i], j);
+        vals[i] = i;
+    }
+}
+
+// after the (key, idx) rows are sorted by key: bitmap bits + {idx, core} rows
+__global__ void nr_index_fill_kernel(const uint32_t *__restrict__ lo, uint32_t n,
+                                     const uint32_t *__restrict__ keys,
+                                     const uint32_t *__restrict__ vals, uint2 *__restrict__ bm,
+                                     uint2 *__restrict__ ents)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        uint32_t k = keys[i];
+        atomicOr(&bm[k >> 5].x, 1u << (k & 31u));
+        uint32_t e = vals[i];
+        ents[i] = make_uint2(e, lo[e]);
+    }
+}
+
+// bm[w].y = number of rows with key < 32 w  (w in 0..2^19 inclusive)
+__global__ void nr_index_rank_kernel(const uint32_t *__restrict__ keys, uint32_t n,
+                                     uint2 *__restrict__ bm)
+{
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w > NR_BM_WORDS) return;
+    uint64_t target = (uint64_t)w << 5;
+    uint32_t a = 0, b = n;
+    while (a < b) {
+        uint32_t mid = (a + b) >> 1;
+        if ((uint64_t)keys[mid] < target) a = mid + 1; else b = mid;
+    }
+    bm[w].y = a;
+}
+
+static int code_of(char c)
+{
+    switch (c) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return 3;
+    default: return 4;
+    }
+}
+
+extern "C" int nr_whitelist_create(const char *cores, uint64_t n, uint32_t core_len,
+                                   uint32_t pad_l, uint32_t pad_r, int device,
+                                   nr_whitelist_t **out)
+{
+    if (!cores || !out || n == 0 || n >= (1ull << 31) || core_len == 0 ||
+        core_len > NR_MAX_CORE || pad_l > 127 || pad_r > 127) {
+        nr_set_error("nr_whitelist_create: bad arguments (n=%llu core_len=%u pads=%u/%u)",
+                     (unsigned long long)n, core_len, pad_l, pad_r);
+        return NR_EINVAL;
+    }
+    NR_CHECK_CUDA(cudaSetDevice(device));
+    std::vector<uint32_t> lo(n), hi, nm;
+    if (core_len > 16) hi.assign(n, 0);
+    bool has_n = false;
+    std::vector<uint32_t> nmv(n, 0);
+    for (uint64_t e = 0; e < n; e++) {
+        uint32_t l = 0, h = 0, m = 0;
+        for (uint32_t j = 0; j < core_len; j++) {
+            int c = code_of(cores[e * core_len + j]);
+            if (c > 3) { m |= 1u << j; c = 0; }
+            if (j < 16) l |= (uint32_t)c << (2 * j);
+            else h |= (uint32_t)c << (2 * (j - 16));
+        }
+        lo[e] = l;
+        if (core_len > 16) hi[e] = h;
+        nmv[e] = m;
+        has_n |= (m != 0);
+    }
+    nr_whitelist *w = new (std::nothrow) nr_whitelist();
+    if (!w) { nr_set_error("out of host memory"); return NR_ENOMEM; }
+    memset(w, 0, sizeof(*w));
+    w->device = device; w->n = n; w->L = core_len; w->pad_l = pad_l; w->pad_r = pad_r;
+    w->has_n = has_n ? 1 : 0;
+    size_t nb = n * sizeof(uint32_t);
+    auto fail = [&](int rc) { nr_whitelist_destroy(w); return rc; };
+    if (cudaMalloc(&w->d_lo, nb) != cudaSuccess) { nr_set_error("cudaMalloc whitelist"); return fail(NR_ENOMEM); }
+    w->bytes += nb;
+    cudaMemcpy(w->d_lo, lo.data(), nb, cudaMemcpyHostToDevice);
+    if (core_len > 16) {
+        if (cudaMalloc(&w->d_hi, nb) != cudaSuccess) { nr_set_error("cudaMalloc whitelist"); return fail(NR_ENOMEM); }
+        w->bytes += nb;
+        cudaMemcpy(w->d_hi, hi.data(), nb, cudaMemcpyHostToDevice);
+    }
+    if (has_n) {
+        if (cudaMalloc(&w->d_nm, nb) != cudaSuccess) { nr_set_error("cudaMalloc whitelist"); return fail(NR_ENOMEM); }
+        w->bytes += nb;
+        cudaMemcpy(w->d_nm, nmv.data(), nb, cudaMemcpyHostToDevice);
+    }
+    if (core_len == 16 && !has_n) {
+        uint32_t *d_keys = nullptr, *d_vals = nullptr;
+        if (cudaMalloc(&d_keys, nb) != cudaSuccess || cudaMalloc(&d_vals, nb) != cudaSuccess) {
+            cudaFree(d_keys);
+            nr_set_error("cudaMalloc index scratch");
+            return fail(NR_ENOMEM);
+        }
+        size_t bmb = (size_t)(NR_BM_WORDS + 1) * sizeof(uint2);
+        uint32_t nn = (uint32_t)n;
+        uint32_t blocks = (nn + 255) / 256;
+        for (int j = 0; j < 4; j++) {
+            if (cudaMalloc(&w->d_bm[j], bmb) != cudaSuccess ||
+                cudaMalloc(&w->d_ents[j], n * sizeof(uint2)) != cudaSuccess) {
+                cudaFree(d_keys); cudaFree(d_vals);
+                nr_set_error("cudaMalloc seed index");
+                return fail(NR_ENOMEM);
+            }
+            w->bytes += bmb + n * sizeof(uint2);
+            cudaMemset(w->d_bm[j], 0, bmb);
+            nr_index_keys_kernel<<<blocks, 256>>>(w->d_lo, nn, j, d_keys, d_vals);
+            thrust::stable_sort_by_key(thrust::device, thrust::device_pointer_cast(d_keys),
+                                       thrust::device_pointer_cast(d_keys) + n,
+                                       thrust::device_pointer_cast(d_vals));
+            nr_index_fill_kernel<<<blocks, 256>>>(w->d_lo, nn, d_keys, d_vals, w->d_bm[j],
+                                                  w->d_ents[j]);
+            nr_index_rank_kernel<<<(NR_BM_WORDS + 1 + 255) / 256, 256>>>(d_keys, nn, w->d_bm[j]);
+        }
+        cudaError_t e = cudaDeviceSynchronize();
+        cudaFree(d_keys); cudaFree(d_vals);
+        if (e != cudaSuccess) {
+            nr_set_error("seed index build failed: %s", cudaGetErrorString(e));
+            return fail(NR_ECUDA);
+        }
+        w->has_index = 1;
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        nr_set_error("whitelist upload failed: %s", cudaGetErrorString(e));
+        return fail(NR_ECUDA);
+    }
+    *out = w;
+    return NR_OK;
+}
+
+extern "C" void nr_whitelist_destroy(nr_whitelist_t *w)
+{
+    if (!w) return;
+    cudaSetDevice(w->device);
+    cudaFree(w->d_lo); cudaFree(w->d_hi); cudaFree(w->d_nm);
+    for (int j = 0; j < 4; j++) { cudaFree(w->d_bm[j]); cudaFree(w->d_ents[j]); }
+    delete w;
+}
+
+extern "C" uint64_t nr_whitelist_size(const nr_whitelist_t *w) { return w ? w->n : 0; }
+extern "C" int nr_whitelist_has_index(const nr_whitelist_t *w) { return w ? w->has_index : 0; }
+extern "C" uint64_t nr_whitelist_device_bytes(const nr_whitelist_t *w) { return w ? w->bytes : 0; }

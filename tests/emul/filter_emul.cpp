@@ -1,0 +1,136 @@
+// filter_emul.cpp -- host-side emulation of the filtered matcher (TEST INFRASTRUCTURE).
+// Compiled by tests/ with g++ from the same nr_filter_core.h the sm_100a kernel includes, so
+// that the probe set and the exact scorer can be checked against the oracle without a GPU.
+// It is serial and slow on purpose; nothing in nanoranger_b200/ links or calls it.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <utility>
+#include <vector>
+
+#include "../../nanoranger_b200/csrc/nr_filter_core.h"
+
+namespace {
+
+struct Index {
+    std::vector<std::pair<uint32_t, uint32_t>> rows[4];  // (key, entry) sorted
+};
+
+void pack_read(const uint8_t *codes, int m, uint32_t w[4])
+{
+    w[0] = w[1] = w[2] = w[3] = 0;
+    for (int i = 0; i < m; i++) w[i >> 4] |= (uint32_t)(codes[i] & 3) << ((i & 15) * 2);
+}
+
+void pad_read(const uint32_t w[4], uint32_t rdp[NR_RDP_WORDS])
+{
+    memset(rdp, 0, sizeof(uint32_t) * NR_RDP_WORDS);
+    for (int k = 0; k < 4; k++) rdp[1 + k] = w[k];
+}
+
+}  // namespace
+
+extern "C" {
+
+// whole-read exact scorer on one pair: returns cost (0..2, 3 = more), *umi as nr_nfa16
+int nr_emul_nfa(const uint8_t *q, int m, const uint8_t *core, int padL, int padR, int *umi)
+{
+    uint32_t w[4], rdp[NR_RDP_WORDS];
+    pack_read(q, m, w);
+    pad_read(w, rdp);
+    uint32_t c = 0;
+    for (int j = 0; j < 16; j++) c |= (uint32_t)(core[j] & 3) << (2 * j);
+    return nr_nfa16(rdp, m, c, padL, padR, 0, m, umi);
+}
+
+// revcomp helper check
+void nr_emul_revcomp(const uint8_t *q, int m, uint8_t *out)
+{
+    uint32_t w[4], r[4];
+    pack_read(q, m, w);
+    nr_revcomp4(w, m, r);
+    for (int i = 0; i < 64; i++) out[i] = (uint8_t)((r[i >> 4] >> ((i & 15) * 2)) & 3u);
+}
+
+// the filtered matcher, serial.  wl: n packed cores.  cand: N x 64 codes (4 = N), clen: N.
+// took[i] = 0 when the candidate is left to the exhaustive kernel (contains N, too short).
+// score[i] = -128 / idx -1 / nbest 0 when no pair reaches cost <= 2.
+// windowed != 0: score hits on the row window of their slot (as the kernel does).
+int nr_emul_filtered(const uint32_t *wl, int64_t n, int padL, int padR, const uint8_t *cand,
+                     const uint8_t *clen, int64_t N, int windowed, int min_len, int32_t *idx,
+                     int8_t *score, int32_t *nbest, uint8_t *strand, int16_t *umi, uint8_t *took,
+                     int64_t *counters /* probes, hits, verifies */)
+{
+    Index ix;
+    for (int j = 0; j < 4; j++) {
+        ix.rows[j].resize((size_t)n);
+        for (int64_t e = 0; e < n; e++) ix.rows[j][(size_t)e] = {nr_core_key(wl[e], j), (uint32_t)e};
+        std::sort(ix.rows[j].begin(), ix.rows[j].end());
+    }
+    counters[0] = counters[1] = counters[2] = 0;
+    for (int64_t c = 0; c < N; c++) {
+        int m = clen[c];
+        const uint8_t *q = cand + (size_t)c * 64;
+        bool has_n = false;
+        for (int i = 0; i < m && i < 64; i++) has_n |= q[i] > 3;
+        idx[c] = -1; score[c] = -128; nbest[c] = 0; strand[c] = 0; umi[c] = -1;
+        if (m > 64 || has_n || m < min_len) { took[c] = 0; continue; }
+        took[c] = 1;
+        uint32_t w[2][4], rdp[2][NR_RDP_WORDS];
+        pack_read(q, m, w[0]);
+        nr_revcomp4(w[0], m, w[1]);
+        pad_read(w[0], rdp[0]);
+        pad_read(w[1], rdp[1]);
+        // (entry << 1 | strand) -> (cost, umi)
+        std::map<uint32_t, std::pair<int, int>> found;
+        int p0 = nr_slot_first(m, padR), p1 = nr_slot_last(m, padL);
+        for (int s = 0; s < 2; s++)
+            for (int p = p0; p <= p1; p++) {
+                uint64_t W = nr_window64(rdp[s], p);
+                int nt = (p == -1) ? NR_PROBES_ALL : NR_PROBES_MAIN;
+                for (int t = 0; t < nt; t++) {
+                    const nr_probe_t &pr = NR_PROBES[t];
+                    if (p + nr_probe_first(pr) < 0 || p + nr_probe_end(pr) > m) continue;
+                    uint32_t key = nr_probe_key(W, pr);
+                    counters[0]++;
+                    auto &rows = ix.rows[pr.drop];
+                    auto it = std::lower_bound(rows.begin(), rows.end(),
+                                               std::make_pair(key, (uint32_t)0));
+                    for (; it != rows.end() && it->first == key; ++it) {
+                        counters[1]++;
+                        int r0 = windowed ? nr_rows_first(p) : 0;
+                        int r1 = windowed ? nr_rows_last(p, m) : m;
+                        int u;
+                        int cost = nr_nfa16(rdp[s], m, wl[it->second], padL, padR, r0, r1, &u);
+                        counters[2]++;
+                        if (cost > 2) continue;
+                        uint32_t k = (it->second << 1) | (uint32_t)s;
+                        auto f = found.find(k);
+                        if (f == found.end()) found[k] = {cost, u};
+                        else if (cost < f->second.first) f->second = {cost, u};
+                        else if (cost == f->second.first) {
+                            int a = f->second.second, b = u;
+                            // smallest row; -1 (ends inside the core) only if no window saw a row
+                            f->second.second = (a < 0) ? b : (b < 0 ? a : std::min(a, b));
+                        }
+                    }
+                }
+            }
+        int best = 3;
+        for (auto &kv : found) best = std::min(best, kv.second.first);
+        if (best > 2) continue;
+        int cnt = 0; uint32_t bk = 0xFFFFFFFFu; int bu = -1;
+        for (auto &kv : found)
+            if (kv.second.first == best) {
+                cnt++;
+                if (kv.first < bk) { bk = kv.first; bu = kv.second.second; }
+            }
+        idx[c] = (int32_t)(bk >> 1); strand[c] = (uint8_t)(bk & 1u);
+        score[c] = (int8_t)(16 - best); nbest[c] = cnt;
+        umi[c] = (int16_t)((bk & 1u) ? -1 : bu);
+    }
+    return 0;
+}
+
+}  // extern "C"
