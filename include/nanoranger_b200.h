@@ -109,6 +109,11 @@ int nr_match_host(const nr_whitelist_t *wl, const char *seqs, const uint64_t *of
                   uint64_t n, int min_score, int mode, int32_t *idx, int8_t *score,
                   uint8_t *nbest, uint8_t *flags, uint8_t *umi_q);
 
+/* Pinned host memory for callers that want nr_match_host's staging copies to be the only
+ * copies (optional; any host pointer works). */
+void *nr_host_alloc(size_t bytes);
+void nr_host_free(void *p);
+
 /* ---- UMI collapse ---------------------------------------------------------------------------
  * Replaces the per-barcode exact UMI dedup of utils.py:759-777 (= 910-928, 1212-1230) and
  * finishes what utils.make_count_mtx_3p10XGEX (utils.py:1523-1548) starts: records
@@ -130,10 +135,20 @@ size_t nr_umi_workspace_bytes(uint64_t n);
  * INT-pipe roofline denominator: runs a dependent LOP3/IADD3 chain on
  * every SM for `iters` iterations and returns executed integer thread-ops per second. */
 int nr_int_peak(int device, int iters, double *ops_per_s, double *ms);
+/* same chains with the add half placed on the FMA pipe (LOP3 + IMAD.IADD): integer issue rate
+ * with both pipes busy */
+int nr_int_peak_dual(int device, int iters, double *ops_per_s, double *ms);
 
-/* Counters of the last filtered launch on this stream-ordered workspace (debug/bench):
- * c[0] probes, c[1] bitmap hits, c[2] NFA evaluations, c[3] full-DP verifications,
- * c[4] candidates sent to the exhaustive kernel. */
+/* NR_MODE_FILTERED with the counting build of the kernel: fills the counters below. */
+int nr_match_device_counted(const nr_whitelist_t *wl, const void *d_bases, const uint8_t *d_meta,
+                            const uint64_t *d_nmask, uint64_t n, int min_score, int32_t *d_idx,
+                            int8_t *d_score, uint8_t *d_nbest, uint8_t *d_flags,
+                            uint8_t *d_umi_q, void *d_workspace, size_t workspace_bytes,
+                            void *stream);
+
+/* Counters of the last nr_match_device_counted launch on this workspace:
+ * c[0] index probes, c[1] bitmap hits, c[2] exact verifications, c[3] verifications that found
+ * cost <= 2, c[4] candidates sent to the exhaustive kernel. */
 int nr_match_counters(const void *d_workspace, uint64_t *c5, void *stream);
 
 #ifdef __cplusplus

@@ -177,41 +177,57 @@ NR_HD int nr_rows_last(int p, int m) { return p + 24 < m ? p + 24 : m; }
 // the best placement inside those rows, 3 if none; *umi = smallest row at which a best
 // placement leaves the core (the query index aligned to reference column padL+16,
 // utils.py:705-708), -1 if the best placement ends inside the core.
+// NR_NFA16_BODY(BASE_AT) is the body; BASE_AT(i) yields base i of Q.
+#define NR_NFA16_BODY(BASE_AT)                                                                \
+    const uint32_t KEEP = 0x15555555u; /* states 1..15 */                                     \
+    const uint32_t FIN = 0x40000000u;  /* state 16 */                                         \
+    uint32_t R0 = 0, R1, R2;                                                                  \
+    if (r0 == 0) { R1 = 1u; R2 = 5u; }                                                        \
+    else { R1 = 0u; R2 = (r0 <= padL) ? 1u : 0u; }                                            \
+    int best = 3, arg = -1;                                                                   \
+    for (int i = r0; i < r1; i++) {                                                           \
+        uint32_t c = (uint32_t)(BASE_AT(i));                                                  \
+        uint32_t x = core ^ (c * 0x55555555u);                                                \
+        uint32_t M = ~(x | (x >> 1)) & 0x55555555u;                                           \
+        int z = i - padL; /* cost of state 0 at row i when positive */                        \
+        uint32_t S0 = (R0 << 2) | (z <= 0 ? 1u : 0u);                                         \
+        uint32_t S1 = (R1 << 2) | (z <= 1 ? 1u : 0u);                                         \
+        uint32_t S2 = (R2 << 2) | (z <= 2 ? 1u : 0u);                                         \
+        uint32_t A0 = S0 & M;                                                                 \
+        uint32_t A1 = (S1 & M) | (R0 & KEEP) | A0;                                            \
+        uint32_t A2 = (S2 & M) | (R1 & KEEP) | S0 | A1;                                       \
+        A2 |= (A0 << 2) | (z + 1 <= 0 ? 1u : 0u); /* one deleted column, cost 2 */            \
+        R0 = A0; R1 = A1; R2 = A2;                                                            \
+        if (R2 & FIN) {                                                                       \
+            int k = (R0 & FIN) ? 0 : ((R1 & FIN) ? 1 : 2);                                    \
+            int t = m - (i + 1) - padR;                                                       \
+            int tot = k + (t > 0 ? t : 0);                                                    \
+            if (tot < best) { best = tot; arg = i + 1; }                                      \
+        }                                                                                     \
+    }                                                                                         \
+    if (r1 == m) {                                                                            \
+        int tot = 3;                                                                          \
+        if (R0 & 0x10000000u) tot = 1; /* state 15 at cost 0 */                               \
+        else if ((R1 & 0x10000000u) | (R0 & 0x04000000u)) tot = 2; /* 15 @1 or 14 @0 */       \
+        if (tot < best) { best = tot; arg = -1; }                                             \
+    }                                                                                         \
+    *umi = arg;                                                                               \
+    return best;
+
+// any rows, bases fetched from the padded read
 NR_HD int nr_nfa16(const uint32_t *rdp, int m, uint32_t core, int padL, int padR, int r0, int r1,
                    int *umi)
 {
-    const uint32_t KEEP = 0x15555555u;   // states 1..15
-    const uint32_t FIN = 0x40000000u;    // state 16
-    uint32_t R0 = 0, R1, R2;
-    if (r0 == 0) { R1 = 1u; R2 = 5u; }
-    else { R1 = 0u; R2 = (r0 <= padL) ? 1u : 0u; }
-    int best = 3, arg = -1;
-    for (int i = r0; i < r1; i++) {
-        uint32_t c = (uint32_t)nr_read_base(rdp, i);
-        uint32_t x = core ^ (c * 0x55555555u);
-        uint32_t M = ~(x | (x >> 1)) & 0x55555555u;
-        int z = i - padL;                                   // cost of state 0 at row i (if > 0)
-        uint32_t S0 = (R0 << 2) | (z <= 0 ? 1u : 0u);
-        uint32_t S1 = (R1 << 2) | (z <= 1 ? 1u : 0u);
-        uint32_t S2 = (R2 << 2) | (z <= 2 ? 1u : 0u);
-        uint32_t A0 = S0 & M;
-        uint32_t A1 = (S1 & M) | (R0 & KEEP) | A0;
-        uint32_t A2 = (S2 & M) | (R1 & KEEP) | S0 | A1;
-        A2 |= (A0 << 2) | (z + 1 <= 0 ? 1u : 0u);           // one deleted column, cost 2
-        R0 = A0; R1 = A1; R2 = A2;
-        if (R2 & FIN) {
-            int k = (R0 & FIN) ? 0 : ((R1 & FIN) ? 1 : 2);
-            int t = m - (i + 1) - padR;
-            int tot = k + (t > 0 ? t : 0);
-            if (tot < best) { best = tot; arg = i + 1; }
-        }
-    }
-    if (r1 == m) {
-        int tot = 3;
-        if (R0 & 0x10000000u) tot = 1;                                   // state 15, cost 0
-        else if ((R1 & 0x10000000u) | (R0 & 0x04000000u)) tot = 2;      // 15 @1 or 14 @0
-        if (tot < best) { best = tot; arg = -1; }
-    }
-    *umi = arg;
-    return best;
+#define NR_BASE_AT(i) nr_read_base(rdp, (i))
+    NR_NFA16_BODY(NR_BASE_AT)
+#undef NR_BASE_AT
+}
+
+// at most 32 rows, bases r0.. held in Wn = nr_window64(rdp, r0)
+NR_HD int nr_nfa16_w(uint64_t Wn, int m, uint32_t core, int padL, int padR, int r0, int r1,
+                     int *umi)
+{
+#define NR_BASE_AT(i) ((uint32_t)(Wn >> (2 * ((i) - r0))) & 3u)
+    NR_NFA16_BODY(NR_BASE_AT)
+#undef NR_BASE_AT
 }

@@ -1,0 +1,337 @@
+// nr_match_api.cu -- C ABI of the matcher: device-pointer entry point, host-buffer entry point
+// (chunked, double-buffered H2D -> pack -> match -> D2H) and the workspace/counter helpers.
+// Replaces scripts/barcode_align.sh:14-41 of the reference (see include/nanoranger_b200.h).
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "nr_common.cuh"
+
+int nr_launch_exhaustive(const nr_whitelist *wl, const void *d_bases, const uint8_t *d_meta,
+                         const uint64_t *d_nmask, const uint32_t *d_list,
+                         const uint32_t *d_list_count, uint64_t n_cand, int min_score,
+                         int32_t *d_idx, int8_t *d_score, uint8_t *d_nbest, uint8_t *d_flags,
+                         uint8_t *d_umi, int grid_cap, cudaStream_t stream);
+int nr_launch_filtered(const nr_whitelist *wl, const void *d_bases, const uint8_t *d_meta,
+                       uint64_t n_cand, int min_score, int resolve_below, int32_t *d_idx,
+                       int8_t *d_score, uint8_t *d_nbest, uint8_t *d_flags, uint8_t *d_umi,
+                       uint32_t *d_list, uint32_t *d_list_count, unsigned long long *d_counters,
+                       int *grid_out, cudaStream_t stream);
+
+// workspace layout: [0,64) eight u64 counters, [64,68) list count, [128, 128 + 4n) list
+#define NR_WS_HEADER 128
+
+namespace {
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+            cudaSetDevice(dev);
+            switched = true;
+        }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+}  // namespace
+
+extern "C" size_t nr_match_workspace_bytes(const nr_whitelist_t *wl, uint64_t n, int mode)
+{
+    (void)wl; (void)mode;
+    return NR_WS_HEADER + (size_t)n * sizeof(uint32_t);
+}
+
+static int resolve_mode(const nr_whitelist *wl, int min_score, int mode)
+{
+    bool can_filter = wl->has_index && min_score >= (int)wl->L - 2;
+    if (mode == NR_MODE_AUTO) return can_filter ? NR_MODE_AUTO : NR_MODE_EXHAUSTIVE;
+    if (mode == NR_MODE_FILTERED && !can_filter) return -1;
+    return mode;
+}
+
+extern "C" int nr_match_device(const nr_whitelist_t *wl, const void *d_bases,
+                               const uint8_t *d_meta, const uint64_t *d_nmask, uint64_t n,
+                               int min_score, int mode, int32_t *d_idx, int8_t *d_score,
+                               uint8_t *d_nbest, uint8_t *d_flags, uint8_t *d_umi_q,
+                               void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    if (!wl) { nr_set_error("nr_match_device: null whitelist"); return NR_EINVAL; }
+    if (n == 0) return NR_OK;
+    if (!d_bases || !d_meta || !d_nmask || !d_idx || !d_score || !d_nbest || !d_flags || !d_umi_q) {
+        nr_set_error("nr_match_device: null pointer");
+        return NR_EINVAL;
+    }
+    if (n >= (1ull << 32)) { nr_set_error("nr_match_device: n must be < 2^32 per call"); return NR_EINVAL; }
+    if (mode != NR_MODE_AUTO && mode != NR_MODE_EXHAUSTIVE && mode != NR_MODE_FILTERED) {
+        nr_set_error("nr_match_device: unknown mode %d", mode);
+        return NR_EINVAL;
+    }
+    int eff = resolve_mode(wl, min_score, mode);
+    if (eff < 0) {
+        nr_set_error("NR_MODE_FILTERED needs a 16-column N-free whitelist and min_score >= %d",
+                     (int)wl->L - 2);
+        return NR_EUNSUPPORTED;
+    }
+    DeviceGuard guard(wl->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (eff == NR_MODE_EXHAUSTIVE)
+        return nr_launch_exhaustive(wl, d_bases, d_meta, d_nmask, nullptr, nullptr, n, min_score,
+                                    d_idx, d_score, d_nbest, d_flags, d_umi_q, 0, st);
+    if (!d_workspace || workspace_bytes < nr_match_workspace_bytes(wl, n, mode)) {
+        nr_set_error("nr_match_device: workspace too small (%zu < %zu)", workspace_bytes,
+                     nr_match_workspace_bytes(wl, n, mode));
+        return NR_EINVAL;
+    }
+    uint8_t *ws = (uint8_t *)d_workspace;
+    uint32_t *d_count = (uint32_t *)(ws + 64);
+    uint32_t *d_list = (uint32_t *)(ws + NR_WS_HEADER);
+    NR_CHECK_CUDA(cudaMemsetAsync(ws, 0, NR_WS_HEADER, st));
+    int grid = 0;
+    int rc = nr_launch_filtered(wl, d_bases, d_meta, n, min_score, eff == NR_MODE_AUTO ? 1 : 0,
+                                d_idx, d_score, d_nbest, d_flags, d_umi_q, d_list, d_count,
+                                nullptr, &grid, st);
+    if (rc != NR_OK) return rc;
+    // candidates the filter left (N, short, > 32 co-optimal pairs; in AUTO also everything below
+    // cost 2) are resolved exactly, count read on the device
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
+    return nr_launch_exhaustive(wl, d_bases, d_meta, d_nmask, d_list, d_count, n, min_score, d_idx,
+                                d_score, d_nbest, d_flags, d_umi_q, sms * 2, st);
+}
+
+// Debug/bench variant: same as NR_MODE_FILTERED but with the counting kernel; fills the five
+// counters at the head of the workspace.
+extern "C" int nr_match_device_counted(const nr_whitelist_t *wl, const void *d_bases,
+                                       const uint8_t *d_meta, const uint64_t *d_nmask, uint64_t n,
+                                       int min_score, int32_t *d_idx, int8_t *d_score,
+                                       uint8_t *d_nbest, uint8_t *d_flags, uint8_t *d_umi_q,
+                                       void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    if (!wl || n == 0 || !d_workspace || workspace_bytes < nr_match_workspace_bytes(wl, n, 0) ||
+        resolve_mode(wl, min_score, NR_MODE_FILTERED) < 0) {
+        nr_set_error("nr_match_device_counted: bad arguments");
+        return NR_EINVAL;
+    }
+    DeviceGuard guard(wl->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *ws = (uint8_t *)d_workspace;
+    NR_CHECK_CUDA(cudaMemsetAsync(ws, 0, NR_WS_HEADER, st));
+    int rc = nr_launch_filtered(wl, d_bases, d_meta, n, min_score, 0, d_idx, d_score, d_nbest,
+                                d_flags, d_umi_q, (uint32_t *)(ws + NR_WS_HEADER),
+                                (uint32_t *)(ws + 64), (unsigned long long *)ws, nullptr, st);
+    if (rc != NR_OK) return rc;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
+    return nr_launch_exhaustive(wl, d_bases, d_meta, d_nmask, (uint32_t *)(ws + NR_WS_HEADER),
+                                (uint32_t *)(ws + 64), n, min_score, d_idx, d_score, d_nbest,
+                                d_flags, d_umi_q, sms * 2, st);
+}
+
+extern "C" int nr_match_counters(const void *d_workspace, uint64_t *c5, void *stream)
+{
+    if (!d_workspace || !c5) { nr_set_error("nr_match_counters: null pointer"); return NR_EINVAL; }
+    uint64_t h[9];
+    NR_CHECK_CUDA(cudaMemcpyAsync(h, d_workspace, sizeof(h), cudaMemcpyDeviceToHost,
+                                  (cudaStream_t)stream));
+    NR_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int i = 0; i < 4; i++) c5[i] = h[i];
+    c5[4] = (uint32_t)(h[8] & 0xFFFFFFFFu);   // list count (candidates sent to the exhaustive kernel)
+    return NR_OK;
+}
+
+// ---- pinned host memory for callers that want truly asynchronous copies ----------------------
+extern "C" void *nr_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        nr_set_error("cudaHostAlloc(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void nr_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---- host-buffer entry point ---------------------------------------------------------------------
+namespace {
+
+constexpr uint64_t CHUNK_CAND = 1ull << 21;               // candidates per chunk
+constexpr uint64_t CHUNK_BYTES = CHUNK_CAND * 64;         // sequence bytes per chunk
+
+struct Slot {
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    uint8_t *h_in = nullptr;        // pinned: sequence bytes, then offsets
+    uint8_t *h_out = nullptr;       // pinned: idx | score | nbest | flags | umi
+    uint8_t *d_seqs = nullptr;
+    uint64_t *d_off = nullptr;
+    uint8_t *d_bases = nullptr, *d_meta = nullptr;
+    uint64_t *d_nmask = nullptr;
+    int32_t *d_idx = nullptr;
+    int8_t *d_score = nullptr;
+    uint8_t *d_nbest = nullptr, *d_flags = nullptr, *d_umi = nullptr;
+    uint8_t *d_ws = nullptr;
+    size_t ws_bytes = 0;
+    uint64_t c0 = 0, cn = 0;        // chunk in flight
+    bool busy = false;
+};
+
+struct HostCtx {
+    std::mutex mu;
+    Slot slot[2];
+    bool ready = false;
+};
+
+int slot_init(Slot &s, const nr_whitelist *wl)
+{
+    NR_CHECK_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    NR_CHECK_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    size_t in_bytes = CHUNK_BYTES + (CHUNK_CAND + 1) * sizeof(uint64_t);
+    NR_CHECK_CUDA(cudaHostAlloc((void **)&s.h_in, in_bytes, cudaHostAllocDefault));
+    NR_CHECK_CUDA(cudaHostAlloc((void **)&s.h_out, CHUNK_CAND * 8, cudaHostAllocDefault));
+    NR_CHECK_CUDA(cudaMalloc((void **)&s.d_seqs, CHUNK_BYTES));
+    NR_CHECK_CUDA(cudaMalloc((void **)&s.d_off, (CHUNK_CAND + 1) * sizeof(uint64_t)));
+    NR_CHECK_CUDA(cudaMalloc((void **)&s.d_bases, CHUNK_CAND * 16));
+    NR_CHECK_CUDA(cudaMalloc((void **)&s.d_meta, CHUNK_CAND));
+    NR_CHECK_CUDA(cudaMalloc((void **)&s.d_nmask, CHUNK_CAND * 8));
+    NR_CHECK_CUDA(cudaMalloc((void **)&s.d_idx, CHUNK_CAND * 8));   // idx|score|nbest|flags|umi
+    s.d_score = (int8_t *)(s.d_idx + CHUNK_CAND);
+    s.d_nbest = (uint8_t *)s.d_score + CHUNK_CAND;
+    s.d_flags = s.d_nbest + CHUNK_CAND;
+    s.d_umi = s.d_flags + CHUNK_CAND;
+    s.ws_bytes = nr_match_workspace_bytes(wl, CHUNK_CAND, NR_MODE_AUTO);
+    NR_CHECK_CUDA(cudaMalloc((void **)&s.d_ws, s.ws_bytes));
+    return NR_OK;
+}
+
+void slot_free(Slot &s)
+{
+    if (s.st) cudaStreamDestroy(s.st);
+    if (s.done) cudaEventDestroy(s.done);
+    cudaFreeHost(s.h_in); cudaFreeHost(s.h_out);
+    cudaFree(s.d_seqs); cudaFree(s.d_off); cudaFree(s.d_bases); cudaFree(s.d_meta);
+    cudaFree(s.d_nmask); cudaFree(s.d_idx); cudaFree(s.d_ws);
+    s = Slot();
+}
+
+// copy the finished chunk of a slot into the caller's arrays
+int slot_collect(Slot &s, int32_t *idx, int8_t *score, uint8_t *nbest, uint8_t *flags,
+                 uint8_t *umi_q)
+{
+    if (!s.busy) return NR_OK;
+    NR_CHECK_CUDA(cudaEventSynchronize(s.done));
+    const uint8_t *o = s.h_out;
+    memcpy(idx + s.c0, o, s.cn * 4); o += s.cn * 4;
+    memcpy(score + s.c0, o, s.cn); o += s.cn;
+    memcpy(nbest + s.c0, o, s.cn); o += s.cn;
+    memcpy(flags + s.c0, o, s.cn); o += s.cn;
+    memcpy(umi_q + s.c0, o, s.cn);
+    s.busy = false;
+    return NR_OK;
+}
+
+}  // namespace
+
+void nr_host_ctx_destroy(void *p)
+{
+    HostCtx *c = (HostCtx *)p;
+    if (!c) return;
+    slot_free(c->slot[0]);
+    slot_free(c->slot[1]);
+    delete c;
+}
+
+extern "C" int nr_match_host(const nr_whitelist_t *wlc, const char *seqs, const uint64_t *offsets,
+                             uint64_t n, int min_score, int mode, int32_t *idx, int8_t *score,
+                             uint8_t *nbest, uint8_t *flags, uint8_t *umi_q)
+{
+    nr_whitelist *wl = const_cast<nr_whitelist *>(wlc);
+    if (!wl) { nr_set_error("nr_match_host: null whitelist"); return NR_EINVAL; }
+    if (n == 0) return NR_OK;
+    if (!seqs || !offsets || !idx || !score || !nbest || !flags || !umi_q) {
+        nr_set_error("nr_match_host: null pointer");
+        return NR_EINVAL;
+    }
+    if (resolve_mode(wl, min_score, mode) < 0 ||
+        (mode != NR_MODE_AUTO && mode != NR_MODE_EXHAUSTIVE && mode != NR_MODE_FILTERED)) {
+        nr_set_error("nr_match_host: mode %d not usable with this whitelist / min_score", mode);
+        return NR_EUNSUPPORTED;
+    }
+    DeviceGuard guard(wl->device);
+    static std::mutex create_mu;
+    {
+        std::lock_guard<std::mutex> g(create_mu);
+        if (!wl->host_ctx) {
+            HostCtx *c = new (std::nothrow) HostCtx();
+            if (!c) { nr_set_error("out of host memory"); return NR_ENOMEM; }
+            wl->host_ctx = c;
+        }
+    }
+    HostCtx *ctx = (HostCtx *)wl->host_ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (!ctx->ready) {
+        for (int k = 0; k < 2; k++) {
+            int rc = slot_init(ctx->slot[k], wl);
+            if (rc != NR_OK) { slot_free(ctx->slot[0]); slot_free(ctx->slot[1]); return rc; }
+        }
+        ctx->ready = true;
+    }
+    uint64_t c0 = 0;
+    int k = 0;
+    int rc = NR_OK;
+    while (c0 < n) {
+        // chunk = as many candidates as fit both limits
+        uint64_t c1 = std::min(n, c0 + CHUNK_CAND);
+        if (offsets[c1] - offsets[c0] > CHUNK_BYTES) {
+            const uint64_t *hi = std::upper_bound(offsets + c0, offsets + c1 + 1,
+                                                  offsets[c0] + CHUNK_BYTES);
+            c1 = (uint64_t)(hi - offsets) - 1;
+            if (c1 <= c0) {
+                nr_set_error("nr_match_host: candidate %llu is longer than %llu bytes",
+                             (unsigned long long)c0, (unsigned long long)CHUNK_BYTES);
+                rc = NR_EINVAL;
+                break;
+            }
+        }
+        Slot &s = ctx->slot[k];
+        if ((rc = slot_collect(s, idx, score, nbest, flags, umi_q)) != NR_OK) break;
+        uint64_t cn = c1 - c0, b0 = offsets[c0], nb = offsets[c1] - b0;
+        memcpy(s.h_in, seqs + b0, nb);
+        uint64_t *h_off = (uint64_t *)(s.h_in + CHUNK_BYTES);
+        memcpy(h_off, offsets + c0, (cn + 1) * sizeof(uint64_t));
+        cudaError_t e;
+        e = cudaMemcpyAsync(s.d_seqs, s.h_in, nb, cudaMemcpyHostToDevice, s.st);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(s.d_off, h_off, (cn + 1) * sizeof(uint64_t),
+                                cudaMemcpyHostToDevice, s.st);
+        if (e != cudaSuccess) { nr_set_error("H2D failed: %s", cudaGetErrorString(e)); rc = NR_ECUDA; break; }
+        // offsets are absolute: bias the sequence pointer instead of rewriting them
+        rc = nr_pack_device(s.d_seqs - b0, s.d_off, cn, s.d_bases, s.d_meta, s.d_nmask, s.st);
+        if (rc != NR_OK) break;
+        rc = nr_match_device(wl, s.d_bases, s.d_meta, s.d_nmask, cn, min_score, mode, s.d_idx,
+                             s.d_score, s.d_nbest, s.d_flags, s.d_umi, s.d_ws, s.ws_bytes, s.st);
+        if (rc != NR_OK) break;
+        // results are contiguous on the device when cn == CHUNK_CAND; otherwise five copies
+        uint8_t *o = s.h_out;
+        e = cudaMemcpyAsync(o, s.d_idx, cn * 4, cudaMemcpyDeviceToHost, s.st); o += cn * 4;
+        if (e == cudaSuccess) { e = cudaMemcpyAsync(o, s.d_score, cn, cudaMemcpyDeviceToHost, s.st); o += cn; }
+        if (e == cudaSuccess) { e = cudaMemcpyAsync(o, s.d_nbest, cn, cudaMemcpyDeviceToHost, s.st); o += cn; }
+        if (e == cudaSuccess) { e = cudaMemcpyAsync(o, s.d_flags, cn, cudaMemcpyDeviceToHost, s.st); o += cn; }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(o, s.d_umi, cn, cudaMemcpyDeviceToHost, s.st);
+        if (e == cudaSuccess) e = cudaEventRecord(s.done, s.st);
+        if (e != cudaSuccess) { nr_set_error("D2H failed: %s", cudaGetErrorString(e)); rc = NR_ECUDA; break; }
+        s.c0 = c0; s.cn = cn; s.busy = true;
+        c0 = c1;
+        k ^= 1;
+    }
+    for (int j = 0; j < 2; j++) {
+        int r2 = slot_collect(ctx->slot[j], idx, score, nbest, flags, umi_q);
+        if (rc == NR_OK) rc = r2;
+    }
+    if (rc != NR_OK) {
+        cudaDeviceSynchronize();
+        ctx->slot[0].busy = ctx->slot[1].busy = false;
+    }
+    return rc;
+}

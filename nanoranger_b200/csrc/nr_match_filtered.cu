@@ -1,0 +1,393 @@
+// nr_match_filtered.cu -- lossless seed filter + exact verification for cost <= 2 (AS >= 14).
+//
+// Replaces scripts/barcode_align.sh:14-41 (STAR EndToEnd against the N-padded whitelist, unique
+// mappers only) for the score range the reference keeps (AS >= 14: utils.py:699, 845, 1150,
+// 1479).  The arithmetic (probe set, exact automaton) is in nr_filter_core.h and is the same
+// code the CPU emulation in tests/emul/ checks against the oracle.
+//
+// Mapping.  One warp owns a tile of 32 consecutive candidates: lane l loads candidate l's
+// 128-bit packed record (one coalesced 512 B request per warp) and stores its 8 B of results;
+// the candidates of the tile are then resolved one after another by the whole warp:
+//   probe    lane = (strand, slot position); the 34 probes of a slot are unrolled with
+//            compile-time offsets; each is one 8 B read of the L2-resident 24-bit key bitmap
+//   queue    bitmap hits are compacted with ballot/popc into a per-warp shared-memory queue
+//   verify   lane = one queued hit: reads its index row(s) and runs the 3-level shift-and
+//            automaton over the <= 27 rows around the slot (registers only)
+//   merge    best cost, the distinct (entry, strand) pairs attaining it (kept one per lane),
+//            smallest UMI row per pair
+// Candidates the filter cannot take (contain N, shorter than NR_FILTER_MIN_LEN, more than 32
+// co-optimal pairs) are appended to a device list that the exhaustive kernel resolves.
+#include <utility>
+
+#include "nr_common.cuh"
+#include "nr_filter_core.h"
+
+#define NR_FILTER_MIN_LEN 24
+#define NR_FWARPS 8                        // warps per block
+#define NR_PBATCH 6                        // probes issued back to back before their hits are queued
+#define NR_NBATCH 6                        // main probe batches per slot chunk (34 = 5 * 6 + 4)
+#define NR_QCAP 480                        // queue slots per warp
+#define NR_QROOM (32 * NR_PBATCH)          // free slots a batch may need
+
+struct nr_filter_params {
+    const uint2 *bm[4];
+    const uint2 *ents[4];
+    uint32_t n;
+    int padL, padR;
+    const uint4 *bases;
+    const uint8_t *meta;
+    uint64_t n_cand;
+    int min_score;
+    int resolve_below;      // 1: candidates without a pair at cost <= 2 go to the list as well
+    int32_t *o_idx;
+    int8_t *o_score;
+    uint8_t *o_nbest;
+    uint8_t *o_flags;
+    uint8_t *o_umi;
+    uint32_t *list;         // candidates left to the exhaustive kernel
+    uint32_t *list_count;
+    unsigned long long *counters;   // nullable: probes, hits, verifications, passes, listed
+};
+
+namespace {
+
+struct WarpSmem {
+    uint4 tile[32];                  // packed records of the warp's 32 candidates
+    uint32_t rdp[2][NR_RDP_WORDS];   // candidate in flight: forward / reverse complement, padded
+    uint2 queue[NR_QCAP];            // bitmap hits waiting for verification
+};
+
+struct Acc {                 // running answer of the candidate in flight (warp-uniform unless noted)
+    int best;                // best cost so far (3 = none)
+    int nb;                  // distinct pairs at `best`
+    uint32_t key;            // per lane: pair (entry << 1 | strand) held by this lane (lane < nb)
+    int umi;                 // per lane: smallest leaving row of that pair, -1 none
+    int overflow;            // more than 32 pairs at `best`
+    int qn;                  // queued hits
+    unsigned long long c_hits, c_ver, c_pass;   // per lane partial counters
+};
+
+__device__ __forceinline__ int merge_umi(int a, int b) { return a < 0 ? b : (b < 0 ? a : min(a, b)); }
+
+// verify up to 32 queued hits (one per lane) and merge them into acc
+template <bool COUNT>
+__device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, Acc &acc, int m)
+{
+    const uint32_t lane = nr_lane();
+    int cnt = min(32, acc.qn);
+    int base = acc.qn - cnt;
+    acc.qn = base;
+    bool have = (int)lane < cnt;
+    uint2 item = have ? sm.queue[base + lane] : make_uint2(0u, 0u);
+    __syncwarp();
+    uint32_t d = item.x >> 28, r = item.x & 0x0FFFFFFFu;
+    uint32_t key = item.y & 0xFFFFFFu;
+    int strand = (int)((item.y >> 24) & 1u);
+    int p = (int)(item.y >> 25) - 16;
+    int r0 = nr_rows_first(p), r1 = nr_rows_last(p, m);
+    uint64_t Wn = 0;
+    const uint2 *ents = nullptr;
+    if (have) {
+        Wn = nr_window64(sm.rdp[strand], r0);
+        ents = P.ents[d];
+    }
+    bool active = have;
+    while (__any_sync(0xffffffffu, active)) {
+        int cost = 3, u = -1;
+        uint32_t k = 0;
+        if (active) {
+            // rows are sorted by key; `r` starts at a lower bound of the key's first row (one row
+            // counted per smaller key of the bitmap word), so rows of smaller keys are skipped
+            uint2 e = (r < P.n) ? __ldg(ents + r) : make_uint2(0u, 0u);
+            uint32_t ek = (r < P.n) ? nr_core_key(e.y, (int)d) : 0xFFFFFFFFu;
+            if (ek == key) {
+                cost = nr_nfa16_w(Wn, m, e.y, P.padL, P.padR, r0, r1, &u);
+                k = (e.x << 1) | (uint32_t)strand;
+                if (COUNT) { acc.c_ver++; acc.c_pass += cost < 3; }
+            }
+            if (ek <= key) r++;
+            else active = false;
+        }
+        int rb = __reduce_min_sync(0xffffffffu, cost);
+        if (rb < 3 && rb <= acc.best) {
+            if (rb < acc.best) { acc.best = rb; acc.nb = 0; }
+            uint32_t contrib = __ballot_sync(0xffffffffu, cost == rb);
+            while (contrib) {
+                int src = __ffs(contrib) - 1;
+                contrib &= contrib - 1;
+                uint32_t kk = __shfl_sync(0xffffffffu, k, src);
+                int uu = __shfl_sync(0xffffffffu, u, src);
+                uint32_t found = __ballot_sync(0xffffffffu, (int)lane < acc.nb && acc.key == kk);
+                if (found) {
+                    if ((int)lane == __ffs(found) - 1) acc.umi = merge_umi(acc.umi, uu);
+                } else if (acc.nb < 32) {
+                    if ((int)lane == acc.nb) { acc.key = kk; acc.umi = uu; }
+                    acc.nb++;
+                } else {
+                    acc.overflow = 1;
+                }
+            }
+        }
+    }
+}
+
+template <int T>
+__device__ __forceinline__ void probe_issue(const nr_filter_params &P, uint64_t W, int p, int m,
+                                            bool slot_ok, uint32_t &key, uint2 &w)
+{
+    constexpr nr_probe_t t = NR_PROBES[T];
+    constexpr int first = t.o0;
+    constexpr int end = t.o2 + (t.var == 2 ? 5 : 4);
+    key = nr_probe_key(W, t);
+    bool valid = slot_ok && (p + first >= 0) && (p + end <= m);
+    w = valid ? __ldg(P.bm[t.drop] + (key >> 5)) : make_uint2(0u, 0u);
+}
+
+template <int T, bool COUNT>
+__device__ __forceinline__ void probe_commit(WarpSmem &sm, Acc &acc, int p, int strand,
+                                             uint32_t key, uint2 w)
+{
+    constexpr nr_probe_t t = NR_PROBES[T];
+    const uint32_t lane = nr_lane();
+    bool hit = (w.x >> (key & 31u)) & 1u;
+    uint32_t mask = __ballot_sync(0xffffffffu, hit);
+    if (mask) {
+        if (hit) {
+            uint32_t row = w.y + (uint32_t)__popc(w.x & ((1u << (key & 31u)) - 1u));
+            int pos = acc.qn + __popc(mask & ((1u << lane) - 1u));
+            sm.queue[pos] = make_uint2(row | ((uint32_t)t.drop << 28),
+                                       key | ((uint32_t)strand << 24) | ((uint32_t)(p + 16) << 25));
+            if (COUNT) acc.c_hits++;
+        }
+        acc.qn += __popc(mask);
+    }
+}
+
+template <int T0, bool COUNT, int... I>
+__device__ __forceinline__ void probe_batch(const nr_filter_params &P, WarpSmem &sm, Acc &acc,
+                                            uint64_t W, int p, int strand, int m, bool slot_ok,
+                                            std::integer_sequence<int, I...>)
+{
+    uint32_t key[sizeof...(I)];
+    uint2 w[sizeof...(I)];
+    (probe_issue<T0 + I>(P, W, p, m, slot_ok, key[I], w[I]), ...);
+    (probe_commit<T0 + I, COUNT>(sm, acc, p, strand, key[I], w[I]), ...);
+}
+
+// edge probes (table rows NR_PROBES_MAIN..), dynamic row index
+__device__ __constant__ nr_probe_t c_edge_probes[NR_PROBES_EDGE];
+
+template <bool COUNT>
+__global__ void __launch_bounds__(NR_FWARPS * 32, 2)
+nr_match_filtered_kernel(const nr_filter_params P)
+{
+    __shared__ WarpSmem smem[NR_FWARPS];
+    const uint32_t lane = nr_lane();
+    const int warp = threadIdx.x >> 5;
+    WarpSmem &sm = smem[warp];
+    const uint64_t n_tiles = (P.n_cand + 31) >> 5;
+    unsigned long long c_probes = 0, c_listed = 0;
+    Acc acc;
+    acc.c_hits = acc.c_ver = acc.c_pass = 0;
+
+    for (uint64_t tile = (uint64_t)blockIdx.x * NR_FWARPS + warp; tile < n_tiles;
+         tile += (uint64_t)gridDim.x * NR_FWARPS) {
+        // one coalesced 512 B request brings the tile's records; meta bytes stay in registers
+        uint32_t mt = 0x100u;   // no candidate
+        {
+            const uint64_t mine = tile * 32 + lane;
+            uint4 b = make_uint4(0u, 0u, 0u, 0u);
+            if (mine < P.n_cand) { b = __ldg(P.bases + mine); mt = P.meta[mine]; }
+            __syncwarp();
+            sm.tile[lane] = b;
+            __syncwarp();
+        }
+        const int in_tile = (int)min((uint64_t)32, P.n_cand - tile * 32);
+
+#pragma unroll 1
+        for (int c = 0; c < in_tile; c++) {
+            const uint32_t cmt = __shfl_sync(0xffffffffu, mt, c);
+            const uint64_t cand = tile * 32 + c;
+            if (cmt == 0xFFu) {          // longer than NR_MAX_QUERY: not scored
+                if (lane == 0) {
+                    P.o_idx[cand] = -1; P.o_score[cand] = NR_SCORE_BELOW; P.o_nbest[cand] = 0;
+                    P.o_flags[cand] = NR_FLAG_TOO_LONG | NR_FLAG_BELOW | NR_FLAG_NO_UMI;
+                    P.o_umi[cand] = NR_UMI_NONE;
+                }
+                continue;
+            }
+            const int m = (int)(cmt & 0x7Fu);
+            bool to_list = (cmt & 0x80u) || m < NR_FILTER_MIN_LEN;
+            if (!to_list) {
+                // stage both strands, padded, in shared memory
+                {
+                    uint4 t4 = sm.tile[c];
+                    uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w}, rc[4];
+                    nr_revcomp4(w4, m, rc);
+                    uint32_t vf = 0, vr = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if ((int)lane == k + 1) { vf = w4[k]; vr = rc[k]; }
+                    __syncwarp();
+                    if (lane < NR_RDP_WORDS) { sm.rdp[0][lane] = vf; sm.rdp[1][lane] = vr; }
+                    __syncwarp();
+                }
+                acc.best = 3; acc.nb = 0; acc.key = 0; acc.umi = -1; acc.overflow = 0; acc.qn = 0;
+                const int p0 = nr_slot_first(m, P.padR), p1 = nr_slot_last(m, P.padL);
+                const int nP = p1 - p0 + 1;
+                const int nslots = nP > 0 ? 2 * nP : 0;
+                const int nchunks = (nslots + 31) >> 5;
+                // work items: NR_NBATCH main batches per chunk, then one edge batch
+                const int n_items = nchunks * NR_NBATCH + 1;
+                int item = 0;
+                while (true) {
+                    // phase A: probe until everything is issued or the queue may overflow
+#pragma unroll 1
+                    while (item < n_items && acc.qn + NR_QROOM <= NR_QCAP) {
+                        if (item < n_items - 1) {
+                            const int chunk = item / NR_NBATCH, tb = item - chunk * NR_NBATCH;
+                            const int slot = chunk * 32 + (int)lane;
+                            const bool slot_ok = slot < nslots;
+                            const int strand = slot >= nP ? 1 : 0;
+                            const int p = p0 + slot - strand * nP;
+                            uint64_t W = 0;
+                            if (slot_ok) W = nr_window64(sm.rdp[strand], p);
+                            if (COUNT) c_probes += slot_ok ? (tb < 5 ? 6 : 4) : 0;
+                            switch (tb) {
+                            case 0: probe_batch<0, COUNT>(P, sm, acc, W, p, strand, m, slot_ok, std::make_integer_sequence<int, 6>{}); break;
+                            case 1: probe_batch<6, COUNT>(P, sm, acc, W, p, strand, m, slot_ok, std::make_integer_sequence<int, 6>{}); break;
+                            case 2: probe_batch<12, COUNT>(P, sm, acc, W, p, strand, m, slot_ok, std::make_integer_sequence<int, 6>{}); break;
+                            case 3: probe_batch<18, COUNT>(P, sm, acc, W, p, strand, m, slot_ok, std::make_integer_sequence<int, 6>{}); break;
+                            case 4: probe_batch<24, COUNT>(P, sm, acc, W, p, strand, m, slot_ok, std::make_integer_sequence<int, 6>{}); break;
+                            default: probe_batch<30, COUNT>(P, sm, acc, W, p, strand, m, slot_ok, std::make_integer_sequence<int, 4>{}); break;
+                            }
+                        } else if (p0 <= -1 && p1 >= -1) {
+                            // one-column start overhang + interior insertion: slot position -1 only
+                            const bool ok = lane < 2 * NR_PROBES_EDGE;
+                            const int strand = lane >= NR_PROBES_EDGE ? 1 : 0;
+                            const int ti = (int)lane - strand * NR_PROBES_EDGE;
+                            bool hit = false;
+                            uint32_t key = 0;
+                            uint2 w = make_uint2(0u, 0u);
+                            const nr_probe_t t = c_edge_probes[ok ? ti : 0];
+                            if (ok && -1 + nr_probe_end(t) <= m) {
+                                uint64_t W = nr_window64(sm.rdp[strand], -1);
+                                key = nr_probe_key(W, t);
+                                w = __ldg(P.bm[0] + (key >> 5));
+                                hit = (w.x >> (key & 31u)) & 1u;
+                                if (COUNT) c_probes++;
+                            }
+                            const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+                            if (mask) {
+                                if (hit) {
+                                    uint32_t row = w.y + (uint32_t)__popc(w.x & ((1u << (key & 31u)) - 1u));
+                                    int pos = acc.qn + __popc(mask & ((1u << lane) - 1u));
+                                    sm.queue[pos] = make_uint2(row, key | ((uint32_t)strand << 24) |
+                                                                        ((uint32_t)(-1 + 16) << 25));
+                                    if (COUNT) acc.c_hits++;
+                                }
+                                acc.qn += __popc(mask);
+                            }
+                        }
+                        item++;
+                    }
+                    __syncwarp();
+                    // phase B: verify everything queued
+#pragma unroll 1
+                    while (acc.qn > 0) drain<COUNT>(P, sm, acc, m);
+                    if (item >= n_items) break;
+                }
+
+                if (acc.overflow || (acc.best == 3 && P.resolve_below)) {
+                    to_list = true;
+                } else if (acc.best == 3) {
+                    if (lane == 0) {
+                        P.o_idx[cand] = -1; P.o_score[cand] = NR_SCORE_BELOW; P.o_nbest[cand] = 0;
+                        P.o_flags[cand] = NR_FLAG_BELOW | NR_FLAG_NO_UMI; P.o_umi[cand] = NR_UMI_NONE;
+                    }
+                } else {
+                    uint32_t kmine = (int)lane < acc.nb ? acc.key : 0xFFFFFFFFu;
+                    uint32_t kmin = __reduce_min_sync(0xffffffffu, kmine);
+                    uint32_t holder = __ballot_sync(0xffffffffu, kmine == kmin);
+                    int u = __shfl_sync(0xffffffffu, acc.umi, __ffs(holder) - 1);
+                    if (lane == 0) {
+                        int strand = (int)(kmin & 1u);
+                        int score = 16 - acc.best;
+                        uint32_t fl = 0;
+                        if (acc.nb > 1) fl |= NR_FLAG_TIE;
+                        if (strand) { fl |= NR_FLAG_RC; u = -1; }
+                        if (score < P.min_score) fl |= NR_FLAG_BELOW;
+                        if (u < 0) fl |= NR_FLAG_NO_UMI;
+                        P.o_idx[cand] = (int32_t)(kmin >> 1); P.o_score[cand] = (int8_t)score;
+                        P.o_nbest[cand] = (uint8_t)acc.nb; P.o_flags[cand] = (uint8_t)fl;
+                        P.o_umi[cand] = (uint8_t)(u < 0 ? NR_UMI_NONE : u);
+                    }
+                }
+            }
+            if (to_list) {
+                if (lane == 0) {
+                    uint32_t at = atomicAdd(P.list_count, 1u);
+                    P.list[at] = (uint32_t)cand;
+                }
+                if (COUNT) c_listed += lane == 0;
+            }
+        }
+    }
+    if (COUNT && P.counters) {
+        atomicAdd(P.counters + 0, c_probes);
+        atomicAdd(P.counters + 1, acc.c_hits);
+        atomicAdd(P.counters + 2, acc.c_ver);
+        atomicAdd(P.counters + 3, acc.c_pass);
+        atomicAdd(P.counters + 4, c_listed);
+    }
+}
+
+}  // namespace
+
+static int g_edge_uploaded_device = -1;
+
+// Enqueue the filtered matcher on `stream`.  list_count must have been zeroed on the stream.
+int nr_launch_filtered(const nr_whitelist *wl, const void *d_bases, const uint8_t *d_meta,
+                       uint64_t n_cand, int min_score, int resolve_below, int32_t *d_idx,
+                       int8_t *d_score, uint8_t *d_nbest, uint8_t *d_flags, uint8_t *d_umi,
+                       uint32_t *d_list, uint32_t *d_list_count, unsigned long long *d_counters,
+                       int *grid_out, cudaStream_t stream)
+{
+    if (n_cand == 0) return NR_OK;
+    if (!wl->has_index) {
+        nr_set_error("filtered matcher needs a 16-column N-free whitelist");
+        return NR_EUNSUPPORTED;
+    }
+    if (g_edge_uploaded_device != wl->device) {
+        NR_CHECK_CUDA(cudaMemcpyToSymbol(c_edge_probes, &NR_PROBES[NR_PROBES_MAIN],
+                                         sizeof(nr_probe_t) * NR_PROBES_EDGE));
+        g_edge_uploaded_device = wl->device;
+    }
+    nr_filter_params P;
+    for (int j = 0; j < 4; j++) { P.bm[j] = wl->d_bm[j]; P.ents[j] = wl->d_ents[j]; }
+    P.n = (uint32_t)wl->n; P.padL = (int)wl->pad_l; P.padR = (int)wl->pad_r;
+    P.bases = (const uint4 *)d_bases; P.meta = d_meta; P.n_cand = n_cand;
+    P.min_score = min_score; P.resolve_below = resolve_below;
+    P.o_idx = d_idx; P.o_score = d_score; P.o_nbest = d_nbest; P.o_flags = d_flags; P.o_umi = d_umi;
+    P.list = d_list; P.list_count = d_list_count; P.counters = d_counters;
+    int sms = 148, per_sm = 1;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
+    if (d_counters)
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nr_match_filtered_kernel<true>,
+                                                      NR_FWARPS * 32, 0);
+    else
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nr_match_filtered_kernel<false>,
+                                                      NR_FWARPS * 32, 0);
+    if (per_sm < 1) per_sm = 1;
+    uint64_t tiles = (n_cand + 31) / 32;
+    uint64_t want = (tiles + NR_FWARPS - 1) / NR_FWARPS;
+    uint64_t cap = (uint64_t)sms * (uint64_t)per_sm;
+    unsigned grid = (unsigned)(want < cap ? want : cap);
+    if (grid_out) *grid_out = (int)grid;
+    if (d_counters)
+        nr_match_filtered_kernel<true><<<grid, NR_FWARPS * 32, 0, stream>>>(P);
+    else
+        nr_match_filtered_kernel<false><<<grid, NR_FWARPS * 32, 0, stream>>>(P);
+    NR_CHECK_CUDA(cudaGetLastError());
+    return NR_OK;
+}

@@ -1,0 +1,305 @@
+// nr_umi.cu -- UMI collapse: segmented sort by (cell barcode, transcript, UMI) + clustering.
+//
+// Replaces the per-barcode exact dedup of the reference (utils.py:759-777 = 910-928 = 1212-1230:
+// np.unique over the UMI strings of each barcode) and finishes what
+// utils.make_count_mtx_3p10XGEX (utils.py:1523-1548) starts.  The reference only ever counts
+// exact-distinct UMIs (max_dist = 0, gene ignored: pass gene = 0).  max_dist = 1 adds the
+// one-hop directional merge defined in DESIGN.md (checked against oracle/nr_oracle.c's twin):
+// inside a (barcode, gene) group the distinct UMIs are walked by (reads desc, umi asc); a UMI
+// joins the earliest representative within Hamming distance 1 whose reads >= 2 * reads - 1,
+// otherwise it becomes a representative itself.
+//
+// Pipeline (all on `stream`, no host synchronisation):
+//   1  LSD radix sort: by umi (2 * umi_len bits), then stable by (barcode << 32 | gene)
+//   2  head flags + scans -> distinct-UMI ids, group ids; run lengths -> reads per distinct UMI
+//   3  one warp per group: rank the distinct UMIs, walk them, pick representatives
+//   4  reads per representative, compaction of the representatives into the group table,
+//      scatter of the representative UMI back to input order
+#include <cub/cub.cuh>
+
+#include "nr_common.cuh"
+
+namespace {
+
+struct UmiWs {
+    // n-sized arrays
+    uint32_t *umi_a, *umi_b, *idx_a, *idx_b;
+    uint64_t *key_a, *key_b;
+    uint32_t *s_bc, *s_gene, *s_umi;       // sorted records
+    uint32_t *head_u, *head_g;             // flags, then exclusive ids after the scan
+    uint32_t *du_id, *grp_id;              // per sorted record
+    uint32_t *du_first;                    // per distinct: first sorted position (+ sentinel)
+    uint32_t *grp_first;                   // per group: first distinct id (+ sentinel)
+    uint32_t *du_rank_order;               // per distinct: distinct ids of its group in walk order
+    uint32_t *du_rep;                      // per distinct: distinct id of its representative
+    uint32_t *rep_reads;                   // per distinct: reads of the cluster it represents
+    uint32_t *rep_flag, *rep_pos;          // per distinct
+    uint32_t *totals;                      // [0] n distinct, [1] n groups, [2] n reps
+    void *cub_tmp;
+    size_t cub_bytes;
+};
+
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t carve(uint8_t *base, uint64_t n, UmiWs *w, size_t cub_bytes)
+{
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return base ? base + o : nullptr; };
+    size_t n4 = (size_t)(n + 1) * 4, n8 = (size_t)(n + 1) * 8;
+    uint32_t **a32[] = {&w->umi_a, &w->umi_b, &w->idx_a, &w->idx_b, &w->s_bc, &w->s_gene, &w->s_umi,
+                        &w->head_u, &w->head_g, &w->du_id, &w->grp_id, &w->du_first,
+                        &w->grp_first, &w->du_rank_order, &w->du_rep, &w->rep_reads,
+                        &w->rep_flag, &w->rep_pos};
+    for (auto p : a32) *p = (uint32_t *)take(n4);
+    w->key_a = (uint64_t *)take(n8);
+    w->key_b = (uint64_t *)take(n8);
+    w->totals = (uint32_t *)take(256);
+    w->cub_tmp = take(cub_bytes);
+    w->cub_bytes = cub_bytes;
+    return off;
+}
+
+size_t cub_temp_bytes(uint64_t n)
+{
+    // radix sort temp is O(#tiles); scans likewise.  A generous closed form keeps this callable
+    // without a device: 16 bytes per 1024 keys per pass-histogram plus fixed slack.
+    return align_up((size_t)(n / 64 + 1) * 64 + (8u << 20));
+}
+
+__global__ void k_init(const uint32_t *umi, uint64_t n, uint32_t *umi_a, uint32_t *idx_a)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { umi_a[i] = umi[i]; idx_a[i] = (uint32_t)i; }
+}
+
+__global__ void k_gather_key(const uint32_t *bc, const uint32_t *gene, const uint32_t *idx,
+                             uint64_t n, uint64_t *key)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { uint32_t s = idx[i]; key[i] = ((uint64_t)bc[s] << 32) | gene[s]; }
+}
+
+__global__ void k_sorted(const uint64_t *key, const uint32_t *umi_in, const uint32_t *idx,
+                         uint64_t n, uint32_t *s_bc, uint32_t *s_gene, uint32_t *s_umi,
+                         uint32_t *head_u, uint32_t *head_g)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = key[i];
+    uint32_t u = umi_in[idx[i]];
+    s_bc[i] = (uint32_t)(k >> 32); s_gene[i] = (uint32_t)k; s_umi[i] = u;
+    bool hg = true, hu = true;
+    if (i > 0) {
+        hg = key[i - 1] != k;
+        hu = hg || umi_in[idx[i - 1]] != u;
+    }
+    head_u[i] = hu; head_g[i] = hg;
+}
+
+// after inclusive scans: ids = scan - 1; record first positions of distinct UMIs and groups
+__global__ void k_ids(const uint32_t *scan_u, const uint32_t *scan_g, uint64_t n, uint32_t *du_id,
+                      uint32_t *grp_id, uint32_t *du_first, uint32_t *grp_first, uint32_t *totals)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t du = scan_u[i] - 1, g = scan_g[i] - 1;
+    bool hu = i == 0 || scan_u[i - 1] != scan_u[i];
+    bool hg = i == 0 || scan_g[i - 1] != scan_g[i];
+    du_id[i] = du; grp_id[i] = g;
+    if (hu) du_first[du] = (uint32_t)i;
+    if (hg) grp_first[g] = du;
+    if (i == n - 1) {
+        totals[0] = du + 1; totals[1] = g + 1;
+        du_first[du + 1] = (uint32_t)n;      // sentinels
+        grp_first[g + 1] = du + 1;
+    }
+}
+
+__device__ __forceinline__ int hamming_2bit(uint32_t a, uint32_t b)
+{
+    uint32_t x = a ^ b;
+    x = (x | (x >> 1)) & 0x55555555u;
+    return __popc(x);
+}
+
+// one warp per (barcode, gene) group
+__global__ void __launch_bounds__(256)
+k_cluster(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ du_first,
+          const uint32_t *__restrict__ grp_first, const uint32_t *__restrict__ totals, int max_dist,
+          uint32_t *__restrict__ order, uint32_t *__restrict__ du_rep)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_groups = totals[1];
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += warps) {
+        const uint32_t d0 = grp_first[g], d1 = grp_first[g + 1];
+        const uint32_t nd = d1 - d0;
+        if (max_dist <= 0 || nd == 1) {
+            for (uint32_t i = d0 + lane; i < d1; i += 32) du_rep[i] = i;
+            continue;
+        }
+        // walk order: rank = number of distinct UMIs that come first by (reads desc, umi asc);
+        // distinct ids are already umi-ascending inside the group
+        for (uint32_t i = d0 + lane; i < d1; i += 32) {
+            uint32_t ci = du_first[i + 1] - du_first[i];
+            uint32_t rank = 0;
+            for (uint32_t j = d0; j < d1; j++) {
+                uint32_t cj = du_first[j + 1] - du_first[j];
+                rank += (cj > ci) || (cj == ci && j < i);
+            }
+            order[d0 + rank] = i;
+        }
+        __syncwarp();
+        // representatives are kept compacted at the front of the walked prefix: order[d0..d0+nrep)
+        // is overwritten in place (a walked position is never read again once passed)
+        uint32_t nrep = 0;
+        for (uint32_t r = 0; r < nd; r++) {
+            const uint32_t d = order[d0 + r];
+            const uint32_t u = s_umi[du_first[d]];
+            const uint32_t cnt = du_first[d + 1] - du_first[d];
+            uint32_t found = 0xFFFFFFFFu;
+            for (uint32_t q0 = 0; q0 < nrep && found == 0xFFFFFFFFu; q0 += 32) {
+                uint32_t q = q0 + lane;
+                bool ok = false;
+                uint32_t e = 0;
+                if (q < nrep) {
+                    e = order[d0 + q];
+                    uint32_t ce = du_first[e + 1] - du_first[e];
+                    ok = hamming_2bit(s_umi[du_first[e]], u) <= max_dist && ce + 1 >= 2 * cnt;
+                }
+                uint32_t mask = __ballot_sync(0xffffffffu, ok);
+                if (mask) found = __shfl_sync(0xffffffffu, e, __ffs(mask) - 1);
+            }
+            __syncwarp();
+            if (found == 0xFFFFFFFFu) {
+                if (lane == 0) { order[d0 + nrep] = d; du_rep[d] = d; }
+                nrep++;
+            } else if (lane == 0) {
+                du_rep[d] = found;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void k_rep_reads(const uint32_t *du_first, const uint32_t *du_rep, const uint32_t *totals,
+                            uint32_t *rep_reads, uint32_t *rep_flag)
+{
+    uint32_t nd = totals[0];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nd; i += gridDim.x * blockDim.x) {
+        uint32_t r = du_rep[i];
+        atomicAdd(&rep_reads[r], du_first[i + 1] - du_first[i]);
+        rep_flag[i] = r == i;
+    }
+}
+
+__global__ void k_emit(const uint32_t *s_bc, const uint32_t *s_gene, const uint32_t *s_umi,
+                       const uint32_t *du_first, const uint32_t *rep_flag, const uint32_t *rep_pos,
+                       const uint32_t *rep_reads, const uint32_t *totals, uint32_t *g_bc,
+                       uint32_t *g_gene, uint32_t *g_umi, uint32_t *g_reads, uint64_t *n_groups)
+{
+    uint32_t nd = totals[0];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nd; i += gridDim.x * blockDim.x) {
+        if (rep_flag[i]) {
+            uint32_t o = rep_pos[i] - 1, s = du_first[i];
+            g_bc[o] = s_bc[s]; g_gene[o] = s_gene[s]; g_umi[o] = s_umi[s]; g_reads[o] = rep_reads[i];
+        }
+        if (i == nd - 1) *n_groups = rep_pos[i];
+    }
+}
+
+__global__ void k_scatter_rep(const uint32_t *idx, const uint32_t *du_id, const uint32_t *du_rep,
+                              const uint32_t *du_first, const uint32_t *s_umi, uint64_t n,
+                              uint32_t *rep_umi)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rep_umi[idx[i]] = s_umi[du_first[du_rep[du_id[i]]]];
+}
+
+}  // namespace
+
+extern "C" size_t nr_umi_workspace_bytes(uint64_t n)
+{
+    UmiWs w;
+    return carve(nullptr, n, &w, cub_temp_bytes(n));
+}
+
+extern "C" int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_gene,
+                                      const uint32_t *d_umi, uint64_t n, int umi_len, int max_dist,
+                                      uint32_t *d_rep_umi, uint64_t *d_n_groups, uint32_t *d_g_bc,
+                                      uint32_t *d_g_gene, uint32_t *d_g_umi, uint32_t *d_g_reads,
+                                      void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!d_n_groups) { nr_set_error("nr_umi_collapse_device: null pointer"); return NR_EINVAL; }
+    if (n == 0) {
+        NR_CHECK_CUDA(cudaMemsetAsync(d_n_groups, 0, sizeof(uint64_t), st));
+        return NR_OK;
+    }
+    if (!d_bc || !d_gene || !d_umi || !d_rep_umi || !d_g_bc || !d_g_gene || !d_g_umi ||
+        !d_g_reads || !d_workspace) {
+        nr_set_error("nr_umi_collapse_device: null pointer");
+        return NR_EINVAL;
+    }
+    if (umi_len < 1 || umi_len > 16 || max_dist < 0 || max_dist > 1 || n >= (1ull << 31)) {
+        nr_set_error("nr_umi_collapse_device: umi_len 1..16, max_dist 0..1, n < 2^31");
+        return NR_EINVAL;
+    }
+    if (workspace_bytes < nr_umi_workspace_bytes(n)) {
+        nr_set_error("nr_umi_collapse_device: workspace too small");
+        return NR_EINVAL;
+    }
+    UmiWs w;
+    carve((uint8_t *)d_workspace, n, &w, cub_temp_bytes(n));
+    const int T = 256;
+    const unsigned nb = (unsigned)((n + T - 1) / T);
+    const int N = (int)n;
+
+    k_init<<<nb, T, 0, st>>>(d_umi, n, w.umi_a, w.idx_a);
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, w.umi_a, w.umi_b, w.idx_a, w.idx_b, N, 0,
+                                    2 * umi_len, st);
+    size_t need2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need2, w.key_a, w.key_b, w.idx_b, w.idx_a, N, 0, 64, st);
+    size_t need3 = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, need3, w.head_u, w.head_u, N, st);
+    if (need > w.cub_bytes || need2 > w.cub_bytes || need3 > w.cub_bytes) {
+        nr_set_error("nr_umi_collapse_device: CUB needs %zu bytes of temporary storage, have %zu",
+                     std::max(need, std::max(need2, need3)), w.cub_bytes);
+        return NR_ENOMEM;
+    }
+    size_t tb = w.cub_bytes;
+    NR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.umi_a, w.umi_b, w.idx_a, w.idx_b,
+                                                  N, 0, 2 * umi_len, st));
+    k_gather_key<<<nb, T, 0, st>>>(d_bc, d_gene, w.idx_b, n, w.key_a);
+    tb = w.cub_bytes;
+    NR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.key_a, w.key_b, w.idx_b, w.idx_a,
+                                                  N, 0, 64, st));
+    // sorted order: key_b (barcode, gene), idx_a (source record)
+    k_sorted<<<nb, T, 0, st>>>(w.key_b, d_umi, w.idx_a, n, w.s_bc, w.s_gene, w.s_umi, w.head_u,
+                               w.head_g);
+    tb = w.cub_bytes;
+    NR_CHECK_CUDA(cub::DeviceScan::InclusiveSum(w.cub_tmp, tb, w.head_u, w.head_u, N, st));
+    tb = w.cub_bytes;
+    NR_CHECK_CUDA(cub::DeviceScan::InclusiveSum(w.cub_tmp, tb, w.head_g, w.head_g, N, st));
+    k_ids<<<nb, T, 0, st>>>(w.head_u, w.head_g, n, w.du_id, w.grp_id, w.du_first, w.grp_first,
+                            w.totals);
+    int sms = 148;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    k_cluster<<<sms * 8, 256, 0, st>>>(w.s_umi, w.du_first, w.grp_first, w.totals, max_dist,
+                                       w.du_rank_order, w.du_rep);
+    NR_CHECK_CUDA(cudaMemsetAsync(w.rep_reads, 0, (size_t)(n + 1) * 4, st));
+    k_rep_reads<<<sms * 8, 256, 0, st>>>(w.du_first, w.du_rep, w.totals, w.rep_reads, w.rep_flag);
+    // rep_flag is defined for the first n_distinct entries only; the scan also runs over the
+    // tail, whose prefix sums are never read back
+    tb = w.cub_bytes;
+    NR_CHECK_CUDA(cub::DeviceScan::InclusiveSum(w.cub_tmp, tb, w.rep_flag, w.rep_pos, N, st));
+    k_emit<<<sms * 8, 256, 0, st>>>(w.s_bc, w.s_gene, w.s_umi, w.du_first, w.rep_flag, w.rep_pos,
+                                    w.rep_reads, w.totals, d_g_bc, d_g_gene, d_g_umi, d_g_reads,
+                                    d_n_groups);
+    k_scatter_rep<<<nb, T, 0, st>>>(w.idx_a, w.du_id, w.du_rep, w.du_first, w.s_umi, n, d_rep_umi);
+    NR_CHECK_CUDA(cudaGetLastError());
+    return NR_OK;
+}

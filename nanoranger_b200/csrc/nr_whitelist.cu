@@ -12,6 +12,7 @@
 #include <thrust/sort.h>
 
 #include "nr_common.cuh"
+#include "nr_filter_core.h"
 
 static thread_local char g_err[512] = "";
 
@@ -33,7 +34,7 @@ __global__ void nr_index_keys_kernel(const uint32_t *__restrict__ lo, uint32_t n
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
-        keys[i] = nr_key_drop(lo[i], j);
+        keys[i] = nr_core_key(lo[i], j);
         vals[i] = i;
     }
 }
@@ -89,7 +90,10 @@ extern "C" int nr_whitelist_create(const char *cores, uint64_t n, uint32_t core_
                      (unsigned long long)n, core_len, pad_l, pad_r);
         return NR_EINVAL;
     }
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
     NR_CHECK_CUDA(cudaSetDevice(device));
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
     std::vector<uint32_t> lo(n), hi, nm;
     if (core_len > 16) hi.assign(n, 0);
     bool has_n = false;
@@ -174,10 +178,14 @@ extern "C" int nr_whitelist_create(const char *cores, uint64_t n, uint32_t core_
 extern "C" void nr_whitelist_destroy(nr_whitelist_t *w)
 {
     if (!w) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
     cudaSetDevice(w->device);
+    nr_host_ctx_destroy(w->host_ctx);
     cudaFree(w->d_lo); cudaFree(w->d_hi); cudaFree(w->d_nm);
     for (int j = 0; j < 4; j++) { cudaFree(w->d_bm[j]); cudaFree(w->d_ents[j]); }
     delete w;
+    if (prev >= 0) cudaSetDevice(prev);
 }
 
 extern "C" uint64_t nr_whitelist_size(const nr_whitelist_t *w) { return w ? w->n : 0; }

@@ -13,8 +13,12 @@
 
 namespace {
 
+// same layout as nr_whitelist.cu builds on the device: per dropped quarter j, rows {entry, core}
+// sorted by key_j and a bitmap of present keys with, per 32-key word, the number of rows whose
+// key is smaller than the word's first key
 struct Index {
     std::vector<std::pair<uint32_t, uint32_t>> rows[4];  // (key, entry) sorted
+    std::vector<uint32_t> bits[4], rank[4];
 };
 
 void pack_read(const uint8_t *codes, int m, uint32_t w[4])
@@ -67,6 +71,14 @@ int nr_emul_filtered(const uint32_t *wl, int64_t n, int padL, int padR, const ui
         ix.rows[j].resize((size_t)n);
         for (int64_t e = 0; e < n; e++) ix.rows[j][(size_t)e] = {nr_core_key(wl[e], j), (uint32_t)e};
         std::sort(ix.rows[j].begin(), ix.rows[j].end());
+        ix.bits[j].assign((1u << 19) + 1, 0u);
+        ix.rank[j].assign((1u << 19) + 1, 0u);
+        for (auto &kv : ix.rows[j]) ix.bits[j][kv.first >> 5] |= 1u << (kv.first & 31u);
+        size_t r = 0;
+        for (uint32_t w = 0; w <= (1u << 19); w++) {
+            while (r < ix.rows[j].size() && (uint64_t)ix.rows[j][r].first < ((uint64_t)w << 5)) r++;
+            ix.rank[j][w] = (uint32_t)r;
+        }
     }
     counters[0] = counters[1] = counters[2] = 0;
     for (int64_t c = 0; c < N; c++) {
@@ -95,14 +107,17 @@ int nr_emul_filtered(const uint32_t *wl, int64_t n, int padL, int padR, const ui
                     uint32_t key = nr_probe_key(W, pr);
                     counters[0]++;
                     auto &rows = ix.rows[pr.drop];
-                    auto it = std::lower_bound(rows.begin(), rows.end(),
-                                               std::make_pair(key, (uint32_t)0));
-                    for (; it != rows.end() && it->first == key; ++it) {
+                    uint32_t bw = ix.bits[pr.drop][key >> 5];
+                    if (!((bw >> (key & 31u)) & 1u)) continue;
+                    size_t r = ix.rank[pr.drop][key >> 5] +
+                               (size_t)nr_popc32(bw & ((1u << (key & 31u)) - 1u));
+                    while (r < rows.size() && rows[r].first < key) r++;   // as the kernel's drain
+                    for (auto it = rows.begin() + (long)r; it != rows.end() && it->first == key; ++it) {
                         counters[1]++;
                         int r0 = windowed ? nr_rows_first(p) : 0;
                         int r1 = windowed ? nr_rows_last(p, m) : m;
                         int u;
-                        int cost = nr_nfa16(rdp[s], m, wl[it->second], padL, padR, r0, r1, &u);
+                        int cost = windowed ? nr_nfa16_w(nr_window64(rdp[s], r0), m, wl[it->second], padL, padR, r0, r1, &u) : nr_nfa16(rdp[s], m, wl[it->second], padL, padR, r0, r1, &u);
                         counters[2]++;
                         if (cost > 2) continue;
                         uint32_t k = (it->second << 1) | (uint32_t)s;

@@ -1,0 +1,136 @@
+"""Parity of the CUDA matcher (through the C ABI) against the CPU oracle.  Bit-exact."""
+import numpy as np
+import pytest
+
+from helpers import compare, mixed_candidates, rs, tie_rich_whitelist
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_device(wl, seqs, min_score, mode, counted=False):
+    import torch
+    from nanoranger_b200 import pack_ascii
+    buf, off = pack_ascii(seqs)
+    dev = torch.device("cuda:0")
+    d_seqs = torch.from_numpy(buf.copy()).to(dev) if len(buf) else torch.zeros(1, dtype=torch.uint8, device=dev)
+    d_off = torch.from_numpy(off.view(np.int64).copy()).to(dev)
+    bases, meta, nmask = wl.pack_device(d_seqs, d_off)
+    ws = wl.workspace(len(seqs), dev)
+    res = wl.match_device(bases, meta, nmask, min_score=min_score, mode=mode, workspace=ws,
+                          counted=counted)
+    torch.cuda.synchronize()
+    from nanoranger_b200 import MatchResult
+    out = MatchResult(*(t.cpu().numpy() for t in (res.idx, res.score, res.nbest, res.flags, res.umi_q)))
+    return out, ws
+
+
+def _oracle(oracle, wl_strs, pad_l, pad_r, seqs):
+    L = len(wl_strs[0])
+    wlc, _ = oracle.encode_many(wl_strs, L)
+    keep = [s if len(s) <= 64 else "" for s in seqs]
+    cc, cl = oracle.encode_many(keep, 64)
+    return oracle.match(wlc, pad_l, pad_r, cc, cl)
+
+
+GEOMS = [(30, 40, 50), (4, 17, 35), (16, 28, 41), (30, 40, 64), (2, 3, 30)]
+
+
+@pytest.mark.parametrize("pad_l,pad_r,qlen", GEOMS)
+def test_exhaustive_vs_oracle(cuda_device, oracle, pad_l, pad_r, qlen):
+    from nanoranger_b200 import Whitelist, NR_MODE_EXHAUSTIVE
+    rng = np.random.default_rng(100 + qlen)
+    wl_strs = tie_rich_whitelist(rng, 2500)
+    seqs = mixed_candidates(rng, wl_strs, 1500, pad_l, qlen)
+    seqs += ["A", "ACGT" * 16, "N" * 20, rs(rng, 1), rs(rng, 2), rs(rng, 15), rs(rng, 16)]
+    wl = Whitelist(wl_strs, pad_l, pad_r)
+    ref = _oracle(oracle, wl_strs, pad_l, pad_r, seqs)
+    res, _ = _run_device(wl, seqs, 14, NR_MODE_EXHAUSTIVE)
+    compare(ref, res, 14, exact_below=True, label="exhaustive")
+
+
+@pytest.mark.parametrize("pad_l,pad_r,qlen", GEOMS)
+def test_filtered_and_auto_vs_oracle(cuda_device, oracle, pad_l, pad_r, qlen):
+    from nanoranger_b200 import Whitelist, NR_MODE_AUTO, NR_MODE_FILTERED
+    rng = np.random.default_rng(200 + qlen)
+    wl_strs = tie_rich_whitelist(rng, 3000)
+    seqs = mixed_candidates(rng, wl_strs, 4000, pad_l, qlen)
+    wl = Whitelist(wl_strs, pad_l, pad_r)
+    assert wl.has_index
+    ref = _oracle(oracle, wl_strs, pad_l, pad_r, seqs)
+    res, ws = _run_device(wl, seqs, 14, NR_MODE_FILTERED, counted=True)
+    nhi = compare(ref, res, 14, exact_below=False, label="filtered")
+    cnt = wl.counters(ws)
+    assert cnt["probes"] > 0 and cnt["verifications"] >= cnt["passes"]
+    res2, _ = _run_device(wl, seqs, 14, NR_MODE_FILTERED)
+    for a, b in zip((res.idx, res.score, res.nbest, res.flags, res.umi_q),
+                    (res2.idx, res2.score, res2.nbest, res2.flags, res2.umi_q)):
+        assert np.array_equal(a, b)
+    res3, _ = _run_device(wl, seqs, 14, NR_MODE_AUTO)
+    compare(ref, res3, 14, exact_below=True, label="auto")
+    assert nhi > 200 or pad_l < 4
+
+
+def test_737k_synthetic_vs_oracle(cuda_device, oracle):
+    """C4-shaped inputs at a size the oracle finishes in seconds: real 737K list, ONT errors."""
+    from nanoranger_b200 import Whitelist, NR_MODE_AUTO, NR_MODE_FILTERED, synth, whitelists
+    wl_a = whitelists.load_737k()
+    d = synth.make_candidates(wl_a, 600, seed=1)
+    seqs = synth.to_strings(d["seqs"], d["offsets"])
+    wl_strs = whitelists.ascii_to_strings(wl_a)
+    wl = Whitelist(wl_a, 30, 40)
+    ref = _oracle(oracle, wl_strs, 30, 40, seqs)
+    res, _ = _run_device(wl, seqs, 14, NR_MODE_FILTERED)
+    compare(ref, res, 14, exact_below=False, label="737K filtered")
+    res, _ = _run_device(wl, seqs[:150], 14, NR_MODE_AUTO)
+    sub = {k: v[:150] for k, v in ref.items()}
+    compare(sub, res, 14, exact_below=True, label="737K auto")
+
+
+def test_slideseq_geometry_generic_kernel(cuda_device, oracle):
+    """32-column cores with N inside (write_bc_slideseq, utils.py:584-601): generic kernel."""
+    from nanoranger_b200 import Whitelist, NR_MODE_AUTO
+    from nanoranger_b200.whitelists import LINKER_SLIDESEQ
+    rng = np.random.default_rng(5)
+    bcs = sorted({rs(rng, 14) for _ in range(1500)})
+    bcs = [b if rng.random() > 0.15 else b[:3] + "N" + b[4:] for b in bcs]
+    cores = [b[:8] + LINKER_SLIDESEQ + b[8:] for b in bcs]
+    seqs = []
+    for _ in range(800):
+        c = cores[rng.integers(0, len(cores))].replace("N", "ACGT"[rng.integers(0, 4)])
+        from helpers import mutate
+        mid = mutate(rng, c, int(rng.integers(0, 3)))
+        a = int(rng.integers(0, 18))
+        seqs.append((rs(rng, a) + mid + rs(rng, 30))[:int(rng.integers(40, 60))])
+    wl = Whitelist(cores, 15, 24)
+    assert not wl.has_index
+    ref = _oracle(oracle, cores, 15, 24, seqs)
+    res, _ = _run_device(wl, seqs, 30, NR_MODE_AUTO)
+    compare(ref, res, 30, exact_below=True, label="slideseq")
+
+
+def test_host_entry_point_matches_device(cuda_device, oracle):
+    from nanoranger_b200 import Whitelist, NR_MODE_AUTO, NR_MODE_FILTERED
+    rng = np.random.default_rng(9)
+    wl_strs = tie_rich_whitelist(rng, 2000)
+    seqs = mixed_candidates(rng, wl_strs, 3000, 30, 50) + ["ACGT" * 20, ""]
+    wl = Whitelist(wl_strs, 30, 40)
+    for mode in (NR_MODE_FILTERED, NR_MODE_AUTO):
+        a, _ = _run_device(wl, seqs, 14, mode)
+        b = wl.match_host(seqs, min_score=14, mode=mode)
+        for x, y in zip((a.idx, a.score, a.nbest, a.flags, a.umi_q),
+                        (b.idx, b.score, b.nbest, b.flags, b.umi_q)):
+            assert np.array_equal(x, y)
+    from nanoranger_b200 import _lib as K
+    assert b.flags[-2] & K.NR_FLAG_TOO_LONG
+    empty = wl.match_host([], min_score=14)
+    assert len(empty.idx) == 0
+
+
+def test_filtered_mode_refused_when_unsupported(cuda_device):
+    from nanoranger_b200 import Whitelist, NR_MODE_FILTERED
+    wl = Whitelist(["ACGTACGTACGTACGTACGT", "ACGTACGTACGTACGTACGA"], 4, 4)
+    with pytest.raises(RuntimeError):
+        wl.match_host(["ACGTACGTACGTACGTACGTAA"], min_score=18, mode=NR_MODE_FILTERED)
+    wl16 = Whitelist(["ACGTACGTACGTACGT", "ACGTACGTACGTACGA"], 4, 4)
+    with pytest.raises(RuntimeError):
+        wl16.match_host(["ACGTACGTACGTACGTACGTAA"], min_score=10, mode=NR_MODE_FILTERED)
