@@ -11,8 +11,9 @@
 //   probe    lane = (strand, slot position); the 34 probes of a slot are unrolled with
 //            compile-time offsets; each is one 8 B read of the L2-resident 24-bit key bitmap
 //   queue    bitmap hits are compacted with ballot/popc into a per-warp shared-memory queue
-//   verify   lane = one queued hit: reads its index row(s) and runs the 3-level shift-and
-//            automaton over the <= 27 rows around the slot (registers only)
+//   verify   32 queued hits are expanded into the index rows sharing their keys (prefix sum over
+//            the row counts); lane = one row: reads {entry, core} and runs the 3-level shift-and
+//            automaton over the <= 27 read rows around the slot (registers only)
 //   merge    best cost, the distinct (entry, strand) pairs attaining it (kept one per lane),
 //            smallest UMI row per pair
 // Candidates the filter cannot take (contain N, shorter than NR_FILTER_MIN_LEN, more than 32
@@ -32,6 +33,7 @@
 struct nr_filter_params {
     const uint2 *bm[4];
     const uint2 *ents[4];
+    const uint32_t *kstart[4];
     uint32_t n;
     int padL, padR;
     const uint4 *bases;
@@ -69,55 +71,72 @@ struct Acc {                 // running answer of the candidate in flight (warp-
 
 __device__ __forceinline__ int merge_umi(int a, int b) { return a < 0 ? b : (b < 0 ? a : min(a, b)); }
 
-// verify up to 32 queued hits (one per lane) and merge them into acc
+// Take up to 32 queued bitmap hits, expand each into the index rows that share its key
+// (kstart gives first row and count), and verify the rows 32 at a time, one row per lane.
 template <bool COUNT>
 __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, Acc &acc, int m)
 {
     const uint32_t lane = nr_lane();
-    int cnt = min(32, acc.qn);
-    int base = acc.qn - cnt;
+    const int cnt = min(32, acc.qn);
+    const int base = acc.qn - cnt;
     acc.qn = base;
-    bool have = (int)lane < cnt;
-    uint2 item = have ? sm.queue[base + lane] : make_uint2(0u, 0u);
+    const bool have = (int)lane < cnt;
+    const uint2 item = have ? sm.queue[base + lane] : make_uint2(0u, 0u);
     __syncwarp();
-    uint32_t d = item.x >> 28, r = item.x & 0x0FFFFFFFu;
-    uint32_t key = item.y & 0xFFFFFFu;
-    int strand = (int)((item.y >> 24) & 1u);
-    int p = (int)(item.y >> 25) - 16;
-    int r0 = nr_rows_first(p), r1 = nr_rows_last(p, m);
-    uint64_t Wn = 0;
-    const uint2 *ents = nullptr;
+    const uint32_t d = item.x >> 28, kr = item.x & 0x0FFFFFFFu;
+    uint32_t start = 0, rows = 0;
     if (have) {
-        Wn = nr_window64(sm.rdp[strand], r0);
-        ents = P.ents[d];
+        const uint32_t *ks = P.kstart[d] + kr;
+        start = __ldg(ks);
+        rows = __ldg(ks + 1) - start;
     }
-    bool active = have;
-    while (__any_sync(0xffffffffu, active)) {
+    // exclusive prefix of the row counts
+    uint32_t incl = rows;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t excl = incl - rows;
+    for (uint32_t b = 0; b < total; b += 32) {
+        const uint32_t g = b + lane;
+        const bool active = g < total;
+        // owner = last lane whose exclusive prefix is <= g (lanes without rows never win: their
+        // prefix equals that of the next lane with rows, which is preferred by the search order)
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            uint32_t v = __shfl_sync(0xffffffffu, excl, (lo + step) & 31);
+            if (lo + step < cnt && v <= g) lo += step;
+        }
+        const uint32_t o_start = __shfl_sync(0xffffffffu, start, lo);
+        const uint32_t o_excl = __shfl_sync(0xffffffffu, excl, lo);
+        const uint32_t o_x = __shfl_sync(0xffffffffu, item.x, lo);
+        const uint32_t o_y = __shfl_sync(0xffffffffu, item.y, lo);
         int cost = 3, u = -1;
         uint32_t k = 0;
         if (active) {
-            // rows are sorted by key; `r` starts at a lower bound of the key's first row (one row
-            // counted per smaller key of the bitmap word), so rows of smaller keys are skipped
-            uint2 e = (r < P.n) ? __ldg(ents + r) : make_uint2(0u, 0u);
-            uint32_t ek = (r < P.n) ? nr_core_key(e.y, (int)d) : 0xFFFFFFFFu;
-            if (ek == key) {
-                cost = nr_nfa16_w(Wn, m, e.y, P.padL, P.padR, r0, r1, &u);
-                k = (e.x << 1) | (uint32_t)strand;
-                if (COUNT) { acc.c_ver++; acc.c_pass += cost < 3; }
-            }
-            if (ek <= key) r++;
-            else active = false;
+            const uint32_t od = o_x >> 28;
+            const int strand = (int)((o_y >> 24) & 1u);
+            const int p = (int)(o_y >> 25) - 16;
+            const int r0 = nr_rows_first(p), r1 = nr_rows_last(p, m);
+            const uint64_t Wn = nr_window64(sm.rdp[strand], r0);
+            const uint2 e = __ldg(P.ents[od] + o_start + (g - o_excl));
+            cost = nr_nfa16_w(Wn, m, e.y, P.padL, P.padR, r0, r1, &u);
+            k = (e.x << 1) | (uint32_t)strand;
+            if (COUNT) { acc.c_ver++; acc.c_pass += cost < 3; }
         }
-        int rb = __reduce_min_sync(0xffffffffu, cost);
+        const int rb = __reduce_min_sync(0xffffffffu, cost);
         if (rb < 3 && rb <= acc.best) {
             if (rb < acc.best) { acc.best = rb; acc.nb = 0; }
             uint32_t contrib = __ballot_sync(0xffffffffu, cost == rb);
             while (contrib) {
-                int src = __ffs(contrib) - 1;
+                const int src = __ffs(contrib) - 1;
                 contrib &= contrib - 1;
-                uint32_t kk = __shfl_sync(0xffffffffu, k, src);
-                int uu = __shfl_sync(0xffffffffu, u, src);
-                uint32_t found = __ballot_sync(0xffffffffu, (int)lane < acc.nb && acc.key == kk);
+                const uint32_t kk = __shfl_sync(0xffffffffu, k, src);
+                const int uu = __shfl_sync(0xffffffffu, u, src);
+                const uint32_t found = __ballot_sync(0xffffffffu, (int)lane < acc.nb && acc.key == kk);
                 if (found) {
                     if ((int)lane == __ffs(found) - 1) acc.umi = merge_umi(acc.umi, uu);
                 } else if (acc.nb < 32) {
@@ -153,10 +172,10 @@ __device__ __forceinline__ void probe_commit(WarpSmem &sm, Acc &acc, int p, int 
     uint32_t mask = __ballot_sync(0xffffffffu, hit);
     if (mask) {
         if (hit) {
-            uint32_t row = w.y + (uint32_t)__popc(w.x & ((1u << (key & 31u)) - 1u));
+            uint32_t kr = w.y + (uint32_t)__popc(w.x & ((1u << (key & 31u)) - 1u));
             int pos = acc.qn + __popc(mask & ((1u << lane) - 1u));
-            sm.queue[pos] = make_uint2(row | ((uint32_t)t.drop << 28),
-                                       key | ((uint32_t)strand << 24) | ((uint32_t)(p + 16) << 25));
+            sm.queue[pos] = make_uint2(kr | ((uint32_t)t.drop << 28),
+                                       ((uint32_t)strand << 24) | ((uint32_t)(p + 16) << 25));
             if (COUNT) acc.c_hits++;
         }
         acc.qn += __popc(mask);
@@ -280,10 +299,10 @@ nr_match_filtered_kernel(const nr_filter_params P)
                             const uint32_t mask = __ballot_sync(0xffffffffu, hit);
                             if (mask) {
                                 if (hit) {
-                                    uint32_t row = w.y + (uint32_t)__popc(w.x & ((1u << (key & 31u)) - 1u));
+                                    uint32_t kr = w.y + (uint32_t)__popc(w.x & ((1u << (key & 31u)) - 1u));
                                     int pos = acc.qn + __popc(mask & ((1u << lane) - 1u));
-                                    sm.queue[pos] = make_uint2(row, key | ((uint32_t)strand << 24) |
-                                                                        ((uint32_t)(-1 + 16) << 25));
+                                    sm.queue[pos] = make_uint2(kr, ((uint32_t)strand << 24) |
+                                                                       ((uint32_t)(-1 + 16) << 25));
                                     if (COUNT) acc.c_hits++;
                                 }
                                 acc.qn += __popc(mask);
@@ -364,7 +383,7 @@ int nr_launch_filtered(const nr_whitelist *wl, const void *d_bases, const uint8_
         g_edge_uploaded_device = wl->device;
     }
     nr_filter_params P;
-    for (int j = 0; j < 4; j++) { P.bm[j] = wl->d_bm[j]; P.ents[j] = wl->d_ents[j]; }
+    for (int j = 0; j < 4; j++) { P.bm[j] = wl->d_bm[j]; P.ents[j] = wl->d_ents[j]; P.kstart[j] = wl->d_kstart[j]; }
     P.n = (uint32_t)wl->n; P.padL = (int)wl->pad_l; P.padR = (int)wl->pad_r;
     P.bases = (const uint4 *)d_bases; P.meta = d_meta; P.n_cand = n_cand;
     P.min_score = min_score; P.resolve_below = resolve_below;

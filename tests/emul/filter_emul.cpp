@@ -14,11 +14,11 @@
 namespace {
 
 // same layout as nr_whitelist.cu builds on the device: per dropped quarter j, rows {entry, core}
-// sorted by key_j and a bitmap of present keys with, per 32-key word, the number of rows whose
-// key is smaller than the word's first key
+// sorted by key_j, a bitmap of present keys with, per 32-key word, the number of distinct keys
+// below the word, and kstart[rank of a key] = its first row (+ sentinel)
 struct Index {
     std::vector<std::pair<uint32_t, uint32_t>> rows[4];  // (key, entry) sorted
-    std::vector<uint32_t> bits[4], rank[4];
+    std::vector<uint32_t> bits[4], rank[4], kstart[4];
 };
 
 void pack_read(const uint8_t *codes, int m, uint32_t w[4])
@@ -74,10 +74,20 @@ int nr_emul_filtered(const uint32_t *wl, int64_t n, int padL, int padR, const ui
         ix.bits[j].assign((1u << 19) + 1, 0u);
         ix.rank[j].assign((1u << 19) + 1, 0u);
         for (auto &kv : ix.rows[j]) ix.bits[j][kv.first >> 5] |= 1u << (kv.first & 31u);
+        std::vector<uint32_t> hs(ix.rows[j].size());
+        uint32_t nd = 0;
+        for (size_t i = 0; i < ix.rows[j].size(); i++) {
+            if (i == 0 || ix.rows[j][i - 1].first != ix.rows[j][i].first) {
+                ix.kstart[j].push_back((uint32_t)i);
+                nd++;
+            }
+            hs[i] = nd;
+        }
+        ix.kstart[j].push_back((uint32_t)ix.rows[j].size());
         size_t r = 0;
         for (uint32_t w = 0; w <= (1u << 19); w++) {
             while (r < ix.rows[j].size() && (uint64_t)ix.rows[j][r].first < ((uint64_t)w << 5)) r++;
-            ix.rank[j][w] = (uint32_t)r;
+            ix.rank[j][w] = r == ix.rows[j].size() ? nd : hs[r] - 1;
         }
     }
     counters[0] = counters[1] = counters[2] = 0;
@@ -109,10 +119,11 @@ int nr_emul_filtered(const uint32_t *wl, int64_t n, int padL, int padR, const ui
                     auto &rows = ix.rows[pr.drop];
                     uint32_t bw = ix.bits[pr.drop][key >> 5];
                     if (!((bw >> (key & 31u)) & 1u)) continue;
-                    size_t r = ix.rank[pr.drop][key >> 5] +
-                               (size_t)nr_popc32(bw & ((1u << (key & 31u)) - 1u));
-                    while (r < rows.size() && rows[r].first < key) r++;   // as the kernel's drain
-                    for (auto it = rows.begin() + (long)r; it != rows.end() && it->first == key; ++it) {
+                    size_t kr = ix.rank[pr.drop][key >> 5] +
+                                (size_t)nr_popc32(bw & ((1u << (key & 31u)) - 1u));
+                    for (size_t r = ix.kstart[pr.drop][kr]; r < ix.kstart[pr.drop][kr + 1]; r++) {
+                        auto it = rows.begin() + (long)r;
+                        if (it->first != key) return -2;   // index inconsistency
                         counters[1]++;
                         int r0 = windowed ? nr_rows_first(p) : 0;
                         int r1 = windowed ? nr_rows_last(p, m) : m;
