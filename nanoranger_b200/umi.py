@@ -1,0 +1,116 @@
+"""UMI collapse on the GPU (nr_umi_collapse_device) and its multi-GPU partitioning.
+
+Replaces the exact per-barcode dedup of utils.py:759-777 of the reference (np.unique over the UMI
+strings of each barcode) and provides the (barcode, transcript, UMI-cluster) table that
+utils.make_count_mtx_3p10XGEX (utils.py:1523-1548) was meant to produce.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+_CODE = np.full(256, 255, dtype=np.uint8)
+for _i, _c in enumerate(b"ACGT"):
+    _CODE[_c] = _i
+_ASCII = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def pack_umis(umis, umi_len: int) -> tuple[np.ndarray, np.ndarray]:
+    """list of equal-length ACGT strings -> (u32 codes, ok mask).  Base k at bits 2k.
+    UMIs containing anything but ACGT are not packable (ok False)."""
+    n = len(umis)
+    if n == 0:
+        return np.zeros(0, np.uint32), np.zeros(0, bool)
+    a = np.frombuffer("".join(umis).encode("ascii"), np.uint8).reshape(n, umi_len)
+    c = _CODE[a]
+    ok = (c < 4).all(axis=1)
+    c = np.where(c < 4, c, 0).astype(np.uint32)
+    out = np.zeros(n, np.uint32)
+    for k in range(umi_len):
+        out |= c[:, k] << np.uint32(2 * k)
+    return out, ok
+
+
+def unpack_umis(codes: np.ndarray, umi_len: int) -> list[str]:
+    a = np.empty((len(codes), umi_len), np.uint8)
+    for k in range(umi_len):
+        a[:, k] = _ASCII[(codes >> np.uint32(2 * k)) & np.uint32(3)]
+    return [bytes(r).decode("ascii") for r in a]
+
+
+def collapse_device(d_bc, d_gene, d_umi, umi_len: int, max_dist: int = 0):
+    """torch uint32-as-int32 tensors on one GPU -> dict of device tensors:
+    rep_umi [n], n_groups (int), g_bc / g_gene / g_umi / g_reads [n_groups] sorted by
+    (bc, gene, umi).  Stream-ordered; the only synchronisation is reading n_groups."""
+    import torch
+    n = d_bc.numel()
+    dev = d_bc.device
+    L = _lib.lib()
+    rep = torch.empty(n, dtype=torch.int32, device=dev)
+    ng = torch.zeros(1, dtype=torch.int64, device=dev)
+    g = [torch.empty(max(n, 1), dtype=torch.int32, device=dev) for _ in range(4)]
+    ws = torch.empty(max(int(L.nr_umi_workspace_bytes(n)), 1), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _lib.check(L.nr_umi_collapse_device(
+            d_bc.data_ptr(), d_gene.data_ptr(), d_umi.data_ptr(), n, umi_len, max_dist,
+            rep.data_ptr(), ng.data_ptr(), g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(),
+            g[3].data_ptr(), ws.data_ptr(), ws.numel(), st), "nr_umi_collapse_device")
+    k = int(ng.item())
+    return {"rep_umi": rep, "n_groups": k, "g_bc": g[0][:k], "g_gene": g[1][:k],
+            "g_umi": g[2][:k], "g_reads": g[3][:k]}
+
+
+def collapse_host(bc, gene, umi, umi_len: int, max_dist: int = 0, device: int = 0):
+    """numpy in, numpy out (uint32 arrays)."""
+    import torch
+    dev = torch.device("cuda", device)
+    t = [torch.from_numpy(np.ascontiguousarray(x, np.uint32).view(np.int32)).to(dev)
+         for x in (bc, gene, umi)]
+    r = collapse_device(t[0], t[1], t[2], umi_len, max_dist)
+    out = {"n_groups": r["n_groups"]}
+    for k in ("rep_umi", "g_bc", "g_gene", "g_umi", "g_reads"):
+        out[k] = r[k].cpu().numpy().view(np.uint32)
+    return out
+
+
+# ---- multi-GPU: all records of one barcode must land on one rank ---------------------------------
+
+def owner_rank(bc: np.ndarray, world: int) -> np.ndarray:
+    """hash(barcode idx) % world (Fibonacci hashing so neighbouring indices spread)."""
+    h = (bc.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(40)
+    return (h % np.uint64(world)).astype(np.int64)
+
+
+def partition_records(bc, gene, umi, world: int):
+    """-> (packed [n,3] int64-free uint32 records ordered by owner, send_counts [world])."""
+    own = owner_rank(bc, world)
+    order = np.argsort(own, kind="stable")
+    counts = np.bincount(own, minlength=world).astype(np.int64)
+    rec = np.stack([np.asarray(x, np.uint32)[order] for x in (bc, gene, umi)], axis=1)
+    return rec, counts
+
+
+def exchange_records(rec_t, send_counts, group=None):
+    """One variable-count all-to-all of (bc, gene, umi) records (torch int32 [n,3] on the
+    process group's device: NCCL over NVLink on GPUs, gloo in the CPU tests).
+    -> received records [m,3]."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    sc = torch.as_tensor(send_counts, dtype=torch.int64, device=rec_t.device)
+    rc = torch.empty(world, dtype=torch.int64, device=rec_t.device)
+    dist.all_to_all_single(rc, sc, group=group)
+    rcl = [int(x) for x in rc.tolist()]
+    out = torch.empty((sum(rcl), 3), dtype=rec_t.dtype, device=rec_t.device)
+    dist.all_to_all_single(out, rec_t.contiguous(), output_split_sizes=rcl,
+                           input_split_sizes=[int(x) for x in send_counts], group=group)
+    return out
+
+
+def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
+    """contiguous candidate shard of a rank (keeps output order)."""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)

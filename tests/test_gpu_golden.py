@@ -1,0 +1,113 @@
+"""Committed fixtures (tests/golden, made by make_golden.py from the reference's sample FASTQs):
+candidates through the reference-shaped host layer (barcode_ref -> barcode_align -> SAM ->
+process_matching_*) on the GPU, compared with the stored oracle results.  Bit-exact."""
+import gzip
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from helpers import compare
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    from nanoranger_b200 import fastx
+    names, seqs, off = fastx.read_fasta(os.path.join(G, f"{name}.fa.gz"))
+    ref = dict(np.load(os.path.join(G, f"{name}.oracle.npz")))
+    return names, seqs, off, ref
+
+
+@pytest.mark.parametrize("name", ["tcr3", "mtdna1026"])
+def test_5p_fixtures_all_modes(cuda_device, name):
+    from nanoranger_b200 import (NR_MODE_AUTO, NR_MODE_EXHAUSTIVE, NR_MODE_FILTERED, Whitelist,
+                                 whitelists)
+    names, seqs, off, ref = _load(name)
+    wl = Whitelist(whitelists.load_737k(), 30, 40)
+    r = wl.match_host(seqs, off, min_score=14, mode=NR_MODE_FILTERED)
+    assert compare(ref, r, 14, exact_below=False, label=f"{name} filtered") > 2000
+    r = wl.match_host(seqs, off, min_score=14, mode=NR_MODE_AUTO)
+    compare(ref, r, 14, exact_below=True, label=f"{name} auto")
+    sub = {k: (v[:300] if getattr(v, "ndim", 0) else v) for k, v in ref.items()}
+    r = wl.match_host(seqs[:int(off[300])], off[:301], min_score=14, mode=NR_MODE_EXHAUSTIVE)
+    compare(sub, r, 14, exact_below=True, label=f"{name} exhaustive")
+
+
+def test_slideseq_fixture(cuda_device):
+    from nanoranger_b200 import NR_MODE_AUTO, Whitelist
+    from nanoranger_b200.whitelists import LINKER_SLIDESEQ
+    names, seqs, off, ref = _load("slideseq")
+    bcs = gzip.open(os.path.join(G, "slideseq_whitelist.txt.gz"), "rt").read().split()
+    wl = Whitelist([b[:8] + LINKER_SLIDESEQ + b[8:] for b in bcs], 15, 24)
+    r = wl.match_host(seqs, off, min_score=30, mode=NR_MODE_AUTO)
+    assert compare(ref, r, 30, exact_below=True, label="slideseq") > 1000
+
+
+def _expected_from_oracle(names, seqs, off, ref, wl_names, thr, umi_len, exact_len):
+    """What the reference's process_matching_* computes, restated on the oracle arrays."""
+    o = off.astype(np.int64)
+    raw = seqs.tobytes()
+    uniq = ref["n_best"] == 1
+    fwd_scores = ref["best_score"][uniq & (ref["strand"] == 0)]
+    triples = []
+    for i in np.flatnonzero(uniq & (ref["strand"] == 0) & (ref["best_score"] >= thr)):
+        u = int(ref["umi_q"][i])
+        s = raw[o[i]:o[i + 1]].decode()
+        umi = s[u:u + umi_len] if u >= 0 else "N"
+        if (len(umi) != umi_len) if exact_len else (len(umi) < umi_len):
+            continue
+        triples.append((names[i], wl_names[ref["best_idx"][i]], umi))
+    return fwd_scores, triples
+
+
+def test_pipeline_tcr3_files(cuda_device, tmp_path):
+    """config 1 (TCR3, 5' 10x TCR mode): write_bc_5p10X -> barcode_ref -> barcode_align ->
+    process_matching_5p10XTCR, files compared with the oracle-derived expectation."""
+    from nanoranger_b200 import utils, whitelists
+    names, seqs, off, ref = _load("tcr3")
+    out = str(tmp_path)
+    wl_a = whitelists.load_737k()
+    wl_names = whitelists.ascii_to_strings(wl_a)
+    with open(f"{out}/wl.txt", "w") as f:
+        f.write("\n".join(n + "-1" for n in wl_names) + "\n")
+    os.link(os.path.join(G, "tcr3.fa.gz"), f"{out}/s_BCUMI.fasta.gz") if hasattr(os, "link") else None
+    utils.write_bc_5p10X("s", out, f"{out}/wl.txt")
+    utils.barcode_ref(f"{out}/s_bcreads.fasta", f"{out}/s_ref/")
+    n = utils.barcode_align(f"{out}/s_BCUMI.fasta.gz", f"{out}/s_ref/", f"{out}/s_matching", 4, "-1")
+    assert n == int((ref["n_best"] == 1).sum())
+    utils.process_matching_5p10XTCR("s", out)
+    fwd_scores, triples = _expected_from_oracle(names, seqs, off, ref, wl_names, 14, 12, False)
+    got = pd.read_csv(f"{out}/s_barcode_scores.csv")
+    v, c = np.unique(fwd_scores, return_counts=True)
+    assert set(zip(got.score.tolist(), got["count"].tolist())) == set(zip(v.tolist(), c.tolist()))
+    per = {}
+    for nme, b, u in triples:
+        per[nme] = (b, u)
+    exp = {}
+    for b, u in per.values():
+        exp.setdefault(b, []).append(u)
+    ded = pd.read_csv(f"{out}/s_bcumi_dedup.csv", index_col=0)
+    assert len(ded) == len(exp)
+    for b, us in exp.items():
+        assert ded.loc[b, "umi_cnt"] == len(set(us)) and ded.loc[b, "read_cnt"] == len(us)
+        assert abs(ded.loc[b, "dup_rate"] - len(us) / len(set(us))) < 1e-12
+    assert (np.diff(ded.umi_cnt.values) <= 0).all()
+
+
+def test_pipeline_5p10X_tags(cuda_device, tmp_path):
+    """config 3 geometry (5p10XGEX: UMI 10 nt): name -> (CB, UB, XT) table."""
+    from nanoranger_b200 import utils, whitelists
+    names, seqs, off, ref = _load("mtdna1026")
+    out = str(tmp_path)
+    wl_a = whitelists.load_737k()
+    wl_names = whitelists.ascii_to_strings(wl_a)
+    np.savez_compressed(f"{out}/nr_whitelist.npz", cores=wl_a, names=np.array(wl_names),
+                        pad_l=30, pad_r=40)
+    utils.barcode_align(os.path.join(G, "mtdna1026.fa.gz"), out, f"{out}/s_matching", 8)
+    table = utils.process_matching_5p10X("s", out)
+    _, triples = _expected_from_oracle(names, seqs, off, ref, wl_names, 14, 10, False)
+    exp = {n: (b, u, "lite") for n, b, u in triples}
+    assert table == exp and len(table) > 3000

@@ -1,0 +1,139 @@
+"""Host-side logic that needs no GPU: file formats, geometry, partitioning, generators."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+
+def test_read_fasta_two_line_multimember_gzip(tmp_path):
+    from nanoranger_b200 import fastx
+    p = tmp_path / "x_BCUMI.fasta.gz"
+    with open(p, "wb") as f:                        # two gzip members, as `cat part_*` produces
+        f.write(gzip.compress(b">r1_0_50_0_TRBV1 extra words\nACGTN\n>r2_1_2_16_X\nGG\n"))
+        f.write(gzip.compress(b">r3\nTTTT\n"))
+    names, seqs, off = fastx.read_fasta(str(p))
+    assert names == ["r1_0_50_0_TRBV1", "r2_1_2_16_X", "r3"]
+    assert seqs.tobytes() == b"ACGTNGGTTTT" and off.tolist() == [0, 5, 7, 11]
+
+
+def test_read_fasta_multiline_and_empty(tmp_path):
+    from nanoranger_b200 import fastx
+    p = tmp_path / "m.fa"
+    p.write_text(">a\nAC\nGT\n>b\n>c\nT\r\n")
+    names, seqs, off = fastx.read_fasta(str(p))
+    assert names == ["a", "b", "c"] and seqs.tobytes() == b"ACGTT" and off.tolist() == [0, 4, 4, 5]
+    q = tmp_path / "e.fa"
+    q.write_text("")
+    assert fastx.read_fasta(str(q))[0] == []
+
+
+def test_anchored_alignment_roundtrip():
+    from nanoranger_b200 import samio
+    for (m, u, pl, L, pr) in [(50, 30, 30, 16, 40), (50, 46, 30, 16, 40), (64, 60, 30, 16, 40),
+                              (35, 19, 4, 16, 17), (35, 34, 4, 16, 17), (20, 0, 30, 16, 40),
+                              (60, 15, 4, 16, 17)]:
+        pos, cig = samio.anchored_alignment(m, u, pl, L, pr)
+        assert samio.query_index_at(pos, cig, pl + L) == u, (m, u, cig)
+        qlen = sum(int(n) for n, op in samio._CIG.findall(cig) if op in "MI")
+        assert qlen == m and pos >= 1
+    pos, cig = samio.anchored_alignment(20, -1, 30, 16, 40)
+    assert samio.query_index_at(pos, cig, 46) is None           # the reference's `except` branch
+    assert samio.query_index_at(pos, cig, 45) == 19
+
+
+def test_sam_write_read(tmp_path):
+    from nanoranger_b200 import samio
+    p = str(tmp_path / "a.sam")
+    recs = [("q1", 0, 2, 17, "50M", "A" * 50, 16), ("q2", 16, 0, 1, "3I47M", "C" * 50, 13)]
+    assert samio.write_sam(p, ["b0", "b1", "b2"], 86, recs) == 2
+    txt = open(p).read()
+    assert "@SQ\tSN:b2\tLN:86" in txt and "@SQ\tSN:b1" not in txt
+    back = samio.read_sam(p)
+    assert [(r["qname"], r["flag"], r["rname"], r["AS"]) for r in back] == \
+        [("q1", 0, "b2", 16), ("q2", 16, "b0", 13)]
+
+
+def test_write_bc_and_barcode_ref(tmp_path):
+    from nanoranger_b200 import utils
+    wl = tmp_path / "wl.txt"
+    wl.write_text("ACGTACGTACGTACGT-1\nTTTTCCCCGGGGAAAA-1\n")
+    utils.write_bc_5p10X("s", str(tmp_path), str(wl))
+    lines = open(tmp_path / "s_bcreads.fasta").read().split("\n")
+    assert lines[0] == ">ACGTACGTACGTACGT" and lines[1] == "N" * 30 + "ACGTACGTACGTACGT" + "N" * 40
+    g = utils.barcode_ref(str(tmp_path / "s_bcreads.fasta"), str(tmp_path / "s_ref"))
+    d = np.load(os.path.join(g, "nr_whitelist.npz"))
+    assert int(d["pad_l"]) == 30 and int(d["pad_r"]) == 40 and d["cores"].shape == (2, 16)
+    assert bytes(d["cores"][1]) == b"TTTTCCCCGGGGAAAA" and str(d["names"][0]) == "ACGTACGTACGTACGT"
+
+
+def test_write_bc_slideseq_geometry(tmp_path):
+    from nanoranger_b200 import utils
+    f = tmp_path / "x.matched.barcodes.tsv"
+    f.write_text("TTTTTTTTAAAAAA-1\nACGTACGTNCGTAC-1\n")
+    utils.write_bc_slideseq("s", str(tmp_path), str(f))
+    lines = open(tmp_path / "s_bcreads.fasta").read().split("\n")
+    assert lines[0] == ">ACGTACGTNCGTAC"                       # np.unique sorts
+    assert lines[1] == "N" * 15 + "ACGTACGT" + "TCTTCAGCGTTCCCGAGA" + "NCGTAC" + "N" * 24
+    utils.barcode_ref(str(tmp_path / "s_bcreads.fasta"), str(tmp_path / "ref"))
+    d = np.load(tmp_path / "ref" / "nr_whitelist.npz")
+    assert (int(d["pad_l"]), int(d["pad_r"]), d["cores"].shape[1]) == (15, 24, 32)
+
+
+def test_write_bc_3p10XGEX(tmp_path):
+    import json
+    from nanoranger_b200 import utils
+    os.makedirs(tmp_path / "split")
+    json.dump({"A" * 16: 15, "C" * 16: 30}, open(tmp_path / "split" / "part_1_bc_count.json", "w"))
+    json.dump({"A" * 16: 10, "G" * 16: 50}, open(tmp_path / "split" / "part_2_bc_count.json", "w"))
+    wl = tmp_path / "3M.txt"
+    wl.write_text("A" * 16 + "\n" + "C" * 16 + "\n" + "T" * 16 + "\n")
+    utils.write_bc_3p10XGEX("s", str(tmp_path), str(wl))
+    txt = open(tmp_path / "s_bcreads.fasta").read().split("\n")
+    assert txt[0] == ">" + "A" * 16 and txt[1] == "NNNN" + "A" * 16 + "N" * 17     # 25 reads, listed
+    assert txt[2] == ">" + "C" * 16 and len(txt) == 5                              # G*16 not whitelisted
+    assert os.path.exists(tmp_path / "s_bc_read_count.csv")
+
+
+def test_sort_cnt_and_pack_umis():
+    from nanoranger_b200 import umi, utils
+    df = utils.sort_cnt([16, 14, 16, 15, 16, 14])
+    assert df.iloc[0].tolist() == [16, 3] and set(map(tuple, df.values.tolist())) == {(16, 3), (14, 2), (15, 1)}
+    codes, ok = umi.pack_umis(["ACGT", "TTTT", "ANGT"], 4)
+    assert ok.tolist() == [True, True, False] and codes[0] == 0b11100100 and codes[1] == 0xFF
+    assert umi.unpack_umis(codes[:2], 4) == ["ACGT", "TTTT"]
+
+
+def test_partition_and_shards():
+    from nanoranger_b200 import umi
+    rng = np.random.default_rng(0)
+    bc = rng.integers(0, 5000, 20000).astype(np.uint32)
+    own = umi.owner_rank(bc, 8)
+    assert own.min() == 0 and own.max() == 7
+    assert np.bincount(own, minlength=8).min() > 1500                    # balanced
+    rec, counts = umi.partition_records(bc, bc * 0, bc * 3, 8)
+    assert counts.sum() == len(bc) and rec.shape == (20000, 3)
+    assert (np.diff(umi.owner_rank(rec[:, 0], 8)) >= 0).all()            # grouped by owner
+    assert np.array_equal(rec[:, 2], rec[:, 0] * 3)
+    cover = [umi.shard_bounds(1001, 8, r) for r in range(8)]
+    assert cover[0][0] == 0 and cover[-1][1] == 1001
+    assert all(cover[i][1] == cover[i + 1][0] for i in range(7))
+    assert umi.shard_bounds(3, 8, 7) == (3, 3)
+
+
+def test_synth_is_seeded_and_shaped():
+    from nanoranger_b200 import synth, whitelists
+    wl = whitelists.load_737k()
+    assert wl.shape == (737280, 16) and bytes(wl[0]) == b"AAACCTGAGAAACCAT"
+    a = synth.make_candidates(wl, 2000, seed=5)
+    b = synth.make_candidates(wl, 2000, seed=5)
+    assert np.array_equal(a["seqs"], b["seqs"]) and np.array_equal(a["offsets"], b["offsets"])
+    lens = np.diff(a["offsets"].astype(np.int64))
+    assert lens.max() <= 64 and 49 < lens.mean() < 55
+    assert 0.05 < (a["true_idx"] < 0).mean() < 0.15
+    clean = synth.make_candidates(wl, 50, seed=1, p_sub=0, p_ins=0, p_del=0, frac_negative=0)
+    s = synth.to_strings(clean["seqs"], clean["offsets"])
+    for i, q in enumerate(s):
+        assert q[:14] == "CGCTCTTCCGATCT" and q[14:30] == bytes(wl[clean["true_idx"][i]]).decode()
+    sw = whitelists.synthetic_whitelist(5000, seed=3)
+    assert len({bytes(r) for r in sw}) == 5000
