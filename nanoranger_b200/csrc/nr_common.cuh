@@ -35,10 +35,11 @@ struct nr_whitelist {
     uint32_t *d_hi;  // n (L > 16) or nullptr
     uint32_t *d_nm;  // n (has_n) or nullptr
     // seed index: for j in 0..3 the 24-bit key made of the three 4-base quarters other than
-    // quarter j.  bm[j][w] = {bitmap word of keys 32w..32w+31, number of distinct keys below
-    // 32w} (2^19 + 1 words); kstart[j][r] = first row of the r-th distinct key (+ sentinel n);
-    // ents[j] = rows {entry idx, core} sorted by key_j.
-    uint2 *d_bm[4];
+    // quarter j.  bits[j][w] = bitmap word of keys 32w..32w+31, rank[j][w] = number of distinct
+    // keys below 32w (2^19 + 1 words each); kstart[j][r] = first row of the r-th distinct key
+    // (+ sentinel n); ents[j] = rows {entry idx, core} sorted by key_j.
+    uint32_t *d_bits[4];
+    uint32_t *d_rank[4];
     uint2 *d_ents[4];
     uint32_t *d_kstart[4];
     size_t bytes;

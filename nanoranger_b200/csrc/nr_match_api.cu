@@ -154,10 +154,15 @@ extern "C" void *nr_host_alloc(size_t bytes)
 extern "C" void nr_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 // ---- host-buffer entry point ---------------------------------------------------------------------
+// Chunks of CHUNK_CAND candidates rotate through NSLOT slots, each with its own stream, so the
+// H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the kernels of chunk k.  Caller
+// buffers that are pinned (nr_host_alloc, cudaHostAlloc, cudaHostRegister) are copied from / to
+// directly; pageable buffers go through the slot's pinned staging area.
 namespace {
 
-constexpr uint64_t CHUNK_CAND = 1ull << 21;               // candidates per chunk
+constexpr uint64_t CHUNK_CAND = 1ull << 19;               // candidates per chunk
 constexpr uint64_t CHUNK_BYTES = CHUNK_CAND * 64;         // sequence bytes per chunk
+constexpr int NSLOT = 3;
 
 struct Slot {
     cudaStream_t st = nullptr;
@@ -174,14 +179,21 @@ struct Slot {
     uint8_t *d_ws = nullptr;
     size_t ws_bytes = 0;
     uint64_t c0 = 0, cn = 0;        // chunk in flight
-    bool busy = false;
+    bool busy = false, staged_out = false;
 };
 
 struct HostCtx {
     std::mutex mu;
-    Slot slot[2];
+    Slot slot[NSLOT];
     bool ready = false;
 };
+
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
 
 int slot_init(Slot &s, const nr_whitelist *wl)
 {
@@ -215,18 +227,20 @@ void slot_free(Slot &s)
     s = Slot();
 }
 
-// copy the finished chunk of a slot into the caller's arrays
+// wait for the slot's chunk; copy it out of the staging area when the caller's arrays are pageable
 int slot_collect(Slot &s, int32_t *idx, int8_t *score, uint8_t *nbest, uint8_t *flags,
                  uint8_t *umi_q)
 {
     if (!s.busy) return NR_OK;
     NR_CHECK_CUDA(cudaEventSynchronize(s.done));
-    const uint8_t *o = s.h_out;
-    memcpy(idx + s.c0, o, s.cn * 4); o += s.cn * 4;
-    memcpy(score + s.c0, o, s.cn); o += s.cn;
-    memcpy(nbest + s.c0, o, s.cn); o += s.cn;
-    memcpy(flags + s.c0, o, s.cn); o += s.cn;
-    memcpy(umi_q + s.c0, o, s.cn);
+    if (s.staged_out) {
+        const uint8_t *o = s.h_out;
+        memcpy(idx + s.c0, o, s.cn * 4); o += s.cn * 4;
+        memcpy(score + s.c0, o, s.cn); o += s.cn;
+        memcpy(nbest + s.c0, o, s.cn); o += s.cn;
+        memcpy(flags + s.c0, o, s.cn); o += s.cn;
+        memcpy(umi_q + s.c0, o, s.cn);
+    }
     s.busy = false;
     return NR_OK;
 }
@@ -237,8 +251,7 @@ void nr_host_ctx_destroy(void *p)
 {
     HostCtx *c = (HostCtx *)p;
     if (!c) return;
-    slot_free(c->slot[0]);
-    slot_free(c->slot[1]);
+    for (int k = 0; k < NSLOT; k++) slot_free(c->slot[k]);
     delete c;
 }
 
@@ -271,12 +284,18 @@ extern "C" int nr_match_host(const nr_whitelist_t *wlc, const char *seqs, const 
     HostCtx *ctx = (HostCtx *)wl->host_ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
     if (!ctx->ready) {
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < NSLOT; k++) {
             int rc = slot_init(ctx->slot[k], wl);
-            if (rc != NR_OK) { slot_free(ctx->slot[0]); slot_free(ctx->slot[1]); return rc; }
+            if (rc != NR_OK) {
+                for (int j = 0; j < NSLOT; j++) slot_free(ctx->slot[j]);
+                return rc;
+            }
         }
         ctx->ready = true;
     }
+    const bool in_pinned = is_pinned(seqs) && is_pinned(offsets);
+    const bool out_pinned = is_pinned(idx) && is_pinned(score) && is_pinned(nbest) &&
+                            is_pinned(flags) && is_pinned(umi_q);
     uint64_t c0 = 0;
     int k = 0;
     int rc = NR_OK;
@@ -296,14 +315,19 @@ extern "C" int nr_match_host(const nr_whitelist_t *wlc, const char *seqs, const 
         }
         Slot &s = ctx->slot[k];
         if ((rc = slot_collect(s, idx, score, nbest, flags, umi_q)) != NR_OK) break;
-        uint64_t cn = c1 - c0, b0 = offsets[c0], nb = offsets[c1] - b0;
-        memcpy(s.h_in, seqs + b0, nb);
-        uint64_t *h_off = (uint64_t *)(s.h_in + CHUNK_BYTES);
-        memcpy(h_off, offsets + c0, (cn + 1) * sizeof(uint64_t));
+        const uint64_t cn = c1 - c0, b0 = offsets[c0], nb = offsets[c1] - b0;
+        const void *src_seq = seqs + b0;
+        const void *src_off = offsets + c0;
+        if (!in_pinned) {
+            memcpy(s.h_in, seqs + b0, nb);
+            memcpy(s.h_in + CHUNK_BYTES, offsets + c0, (cn + 1) * sizeof(uint64_t));
+            src_seq = s.h_in;
+            src_off = s.h_in + CHUNK_BYTES;
+        }
         cudaError_t e;
-        e = cudaMemcpyAsync(s.d_seqs, s.h_in, nb, cudaMemcpyHostToDevice, s.st);
+        e = cudaMemcpyAsync(s.d_seqs, src_seq, nb, cudaMemcpyHostToDevice, s.st);
         if (e == cudaSuccess)
-            e = cudaMemcpyAsync(s.d_off, h_off, (cn + 1) * sizeof(uint64_t),
+            e = cudaMemcpyAsync(s.d_off, src_off, (cn + 1) * sizeof(uint64_t),
                                 cudaMemcpyHostToDevice, s.st);
         if (e != cudaSuccess) { nr_set_error("H2D failed: %s", cudaGetErrorString(e)); rc = NR_ECUDA; break; }
         // offsets are absolute: bias the sequence pointer instead of rewriting them
@@ -312,26 +336,30 @@ extern "C" int nr_match_host(const nr_whitelist_t *wlc, const char *seqs, const 
         rc = nr_match_device(wl, s.d_bases, s.d_meta, s.d_nmask, cn, min_score, mode, s.d_idx,
                              s.d_score, s.d_nbest, s.d_flags, s.d_umi, s.d_ws, s.ws_bytes, s.st);
         if (rc != NR_OK) break;
-        // results are contiguous on the device when cn == CHUNK_CAND; otherwise five copies
         uint8_t *o = s.h_out;
-        e = cudaMemcpyAsync(o, s.d_idx, cn * 4, cudaMemcpyDeviceToHost, s.st); o += cn * 4;
-        if (e == cudaSuccess) { e = cudaMemcpyAsync(o, s.d_score, cn, cudaMemcpyDeviceToHost, s.st); o += cn; }
-        if (e == cudaSuccess) { e = cudaMemcpyAsync(o, s.d_nbest, cn, cudaMemcpyDeviceToHost, s.st); o += cn; }
-        if (e == cudaSuccess) { e = cudaMemcpyAsync(o, s.d_flags, cn, cudaMemcpyDeviceToHost, s.st); o += cn; }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(o, s.d_umi, cn, cudaMemcpyDeviceToHost, s.st);
+        void *dst[5] = {o, o + cn * 4, o + cn * 5, o + cn * 6, o + cn * 7};
+        if (out_pinned) {
+            dst[0] = idx + c0; dst[1] = score + c0; dst[2] = nbest + c0; dst[3] = flags + c0;
+            dst[4] = umi_q + c0;
+        }
+        e = cudaMemcpyAsync(dst[0], s.d_idx, cn * 4, cudaMemcpyDeviceToHost, s.st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dst[1], s.d_score, cn, cudaMemcpyDeviceToHost, s.st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dst[2], s.d_nbest, cn, cudaMemcpyDeviceToHost, s.st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dst[3], s.d_flags, cn, cudaMemcpyDeviceToHost, s.st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dst[4], s.d_umi, cn, cudaMemcpyDeviceToHost, s.st);
         if (e == cudaSuccess) e = cudaEventRecord(s.done, s.st);
         if (e != cudaSuccess) { nr_set_error("D2H failed: %s", cudaGetErrorString(e)); rc = NR_ECUDA; break; }
-        s.c0 = c0; s.cn = cn; s.busy = true;
+        s.c0 = c0; s.cn = cn; s.busy = true; s.staged_out = !out_pinned;
         c0 = c1;
-        k ^= 1;
+        k = (k + 1) % NSLOT;
     }
-    for (int j = 0; j < 2; j++) {
-        int r2 = slot_collect(ctx->slot[j], idx, score, nbest, flags, umi_q);
+    for (int j = 0; j < NSLOT; j++) {
+        int r2 = slot_collect(ctx->slot[(k + j) % NSLOT], idx, score, nbest, flags, umi_q);
         if (rc == NR_OK) rc = r2;
     }
     if (rc != NR_OK) {
         cudaDeviceSynchronize();
-        ctx->slot[0].busy = ctx->slot[1].busy = false;
+        for (int j = 0; j < NSLOT; j++) ctx->slot[j].busy = false;
     }
     return rc;
 }

@@ -9,8 +9,10 @@
 // 128-bit packed record (one coalesced 512 B request per warp) and stores its 8 B of results;
 // the candidates of the tile are then resolved one after another by the whole warp:
 //   probe    lane = (strand, slot position); the 34 probes of a slot are unrolled with
-//            compile-time offsets; each is one 8 B read of the L2-resident 24-bit key bitmap
-//   queue    bitmap hits are compacted with ballot/popc into a per-warp shared-memory queue
+//            compile-time offsets; each is one 4 B read of the L2-resident 24-bit key bitmap;
+//            the hit bits of a lane are collected in a register mask
+//   queue    one warp scan per 32 slots places the hits in a per-warp shared-memory queue
+//            (key rank = rank word + popc of the bitmap word below the key)
 //   verify   32 queued hits are expanded into the index rows sharing their keys (prefix sum over
 //            the row counts); lane = one row: reads {entry, core} and runs the 3-level shift-and
 //            automaton over the <= 27 read rows around the slot (registers only)
@@ -25,13 +27,11 @@
 
 #define NR_FILTER_MIN_LEN 24
 #define NR_FWARPS 8                        // warps per block
-#define NR_PBATCH 6                        // probes issued back to back before their hits are queued
-#define NR_NBATCH 6                        // main probe batches per slot chunk (34 = 5 * 6 + 4)
 #define NR_QCAP 480                        // queue slots per warp
-#define NR_QROOM (32 * NR_PBATCH)          // free slots a batch may need
 
 struct nr_filter_params {
-    const uint2 *bm[4];
+    const uint32_t *bits[4];      // key bitmap, 2^19 words per dropped quarter
+    const uint32_t *rank[4];      // distinct keys below each bitmap word
     const uint2 *ents[4];
     const uint32_t *kstart[4];
     uint32_t n;
@@ -150,54 +150,31 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, A
     }
 }
 
+// one probe of a slot: key from the window, one 4 B read of the key bitmap, hit bit into `mask`
 template <int T>
-__device__ __forceinline__ void probe_issue(const nr_filter_params &P, uint64_t W, int p, int m,
-                                            bool slot_ok, uint32_t &key, uint2 &w)
+__device__ __forceinline__ void probe_one(const nr_filter_params &P, uint64_t W, bool slot_ok,
+                                          uint64_t &mask)
 {
     constexpr nr_probe_t t = NR_PROBES[T];
-    constexpr int first = t.o0;
-    constexpr int end = t.o2 + (t.var == 2 ? 5 : 4);
-    key = nr_probe_key(W, t);
-    bool valid = slot_ok && (p + first >= 0) && (p + end <= m);
-    w = valid ? __ldg(P.bm[t.drop] + (key >> 5)) : make_uint2(0u, 0u);
+    const uint32_t key = nr_probe_key(W, t);
+    const uint32_t w = slot_ok ? __ldg(P.bits[t.drop] + (key >> 5)) : 0u;
+    mask |= (uint64_t)((w >> (key & 31u)) & 1u) << T;
 }
 
-template <int T, bool COUNT>
-__device__ __forceinline__ void probe_commit(WarpSmem &sm, Acc &acc, int p, int strand,
-                                             uint32_t key, uint2 w)
+template <int... I>
+__device__ __forceinline__ uint64_t probe_all(const nr_filter_params &P, uint64_t W, bool slot_ok,
+                                              std::integer_sequence<int, I...>)
 {
-    constexpr nr_probe_t t = NR_PROBES[T];
-    const uint32_t lane = nr_lane();
-    bool hit = (w.x >> (key & 31u)) & 1u;
-    uint32_t mask = __ballot_sync(0xffffffffu, hit);
-    if (mask) {
-        if (hit) {
-            uint32_t kr = w.y + (uint32_t)__popc(w.x & ((1u << (key & 31u)) - 1u));
-            int pos = acc.qn + __popc(mask & ((1u << lane) - 1u));
-            sm.queue[pos] = make_uint2(kr | ((uint32_t)t.drop << 28),
-                                       ((uint32_t)strand << 24) | ((uint32_t)(p + 16) << 25));
-            if (COUNT) acc.c_hits++;
-        }
-        acc.qn += __popc(mask);
-    }
+    uint64_t mask = 0;
+    (probe_one<I>(P, W, slot_ok, mask), ...);
+    return mask;
 }
 
-template <int T0, bool COUNT, int... I>
-__device__ __forceinline__ void probe_batch(const nr_filter_params &P, WarpSmem &sm, Acc &acc,
-                                            uint64_t W, int p, int strand, int m, bool slot_ok,
-                                            std::integer_sequence<int, I...>)
-{
-    uint32_t key[sizeof...(I)];
-    uint2 w[sizeof...(I)];
-    (probe_issue<T0 + I>(P, W, p, m, slot_ok, key[I], w[I]), ...);
-    (probe_commit<T0 + I, COUNT>(sm, acc, p, strand, key[I], w[I]), ...);
-}
-
-// edge probes (table rows NR_PROBES_MAIN..), dynamic row index
-__device__ __constant__ nr_probe_t c_edge_probes[NR_PROBES_EDGE];
+// the whole probe table in constant memory, for the places that index it dynamically
+__device__ __constant__ nr_probe_t c_probes[NR_PROBES_ALL];
 
 template <bool COUNT>
-__global__ void __launch_bounds__(NR_FWARPS * 32, 2)
+__global__ void __launch_bounds__(NR_FWARPS * 32, 3)
 nr_match_filtered_kernel(const nr_filter_params P)
 {
     __shared__ WarpSmem smem[NR_FWARPS];
@@ -205,7 +182,7 @@ nr_match_filtered_kernel(const nr_filter_params P)
     const int warp = threadIdx.x >> 5;
     WarpSmem &sm = smem[warp];
     const uint64_t n_tiles = (P.n_cand + 31) >> 5;
-    unsigned long long c_probes = 0, c_listed = 0;
+    unsigned long long c_probes_n = 0, c_listed = 0;
     Acc acc;
     acc.c_hits = acc.c_ver = acc.c_pass = 0;
 
@@ -256,65 +233,62 @@ nr_match_filtered_kernel(const nr_filter_params P)
                 const int nP = p1 - p0 + 1;
                 const int nslots = nP > 0 ? 2 * nP : 0;
                 const int nchunks = (nslots + 31) >> 5;
-                // work items: NR_NBATCH main batches per chunk, then one edge batch
-                const int n_items = nchunks * NR_NBATCH + 1;
-                int item = 0;
-                while (true) {
-                    // phase A: probe until everything is issued or the queue may overflow
+                const bool edge = p0 <= -1 && p1 >= -1;
+                // work items: one per chunk of 32 slots, then the edge probes (slot -1 only),
+                // then a flush item that only drains
 #pragma unroll 1
-                    while (item < n_items && acc.qn + NR_QROOM <= NR_QCAP) {
-                        if (item < n_items - 1) {
-                            const int chunk = item / NR_NBATCH, tb = item - chunk * NR_NBATCH;
-                            const int slot = chunk * 32 + (int)lane;
-                            const bool slot_ok = slot < nslots;
-                            const int strand = slot >= nP ? 1 : 0;
-                            const int p = p0 + slot - strand * nP;
-                            uint64_t W = 0;
-                            if (slot_ok) W = nr_window64(sm.rdp[strand], p);
-                            if (COUNT) c_probes += slot_ok ? (tb < 5 ? 6 : 4) : 0;
-                            switch (tb) {
-                            case 0: probe_batch<0, COUNT>(P, sm, acc, W, p, strand, m, slot_ok, std::make_integer_sequence<int, 6>{}); break;
-                            case 1: probe_batch<6, COUNT>(P, sm, acc, W, p, strand, m, slot_ok, std::make_integer_sequence<int, 6>{}); break;
-                            case 2: probe_batch<12, COUNT>(P, sm, acc, W, p, strand, m, slot_ok, std::make_integer_sequence<int, 6>{}); break;
-                            case 3: probe_batch<18, COUNT>(P, sm, acc, W, p, strand, m, slot_ok, std::make_integer_sequence<int, 6>{}); break;
-                            case 4: probe_batch<24, COUNT>(P, sm, acc, W, p, strand, m, slot_ok, std::make_integer_sequence<int, 6>{}); break;
-                            default: probe_batch<30, COUNT>(P, sm, acc, W, p, strand, m, slot_ok, std::make_integer_sequence<int, 4>{}); break;
-                            }
-                        } else if (p0 <= -1 && p1 >= -1) {
-                            // one-column start overhang + interior insertion: slot position -1 only
-                            const bool ok = lane < 2 * NR_PROBES_EDGE;
-                            const int strand = lane >= NR_PROBES_EDGE ? 1 : 0;
-                            const int ti = (int)lane - strand * NR_PROBES_EDGE;
-                            bool hit = false;
-                            uint32_t key = 0;
-                            uint2 w = make_uint2(0u, 0u);
-                            const nr_probe_t t = c_edge_probes[ok ? ti : 0];
-                            if (ok && -1 + nr_probe_end(t) <= m) {
-                                uint64_t W = nr_window64(sm.rdp[strand], -1);
-                                key = nr_probe_key(W, t);
-                                w = __ldg(P.bm[0] + (key >> 5));
-                                hit = (w.x >> (key & 31u)) & 1u;
-                                if (COUNT) c_probes++;
-                            }
-                            const uint32_t mask = __ballot_sync(0xffffffffu, hit);
-                            if (mask) {
-                                if (hit) {
-                                    uint32_t kr = w.y + (uint32_t)__popc(w.x & ((1u << (key & 31u)) - 1u));
-                                    int pos = acc.qn + __popc(mask & ((1u << lane) - 1u));
-                                    sm.queue[pos] = make_uint2(kr, ((uint32_t)strand << 24) |
-                                                                       ((uint32_t)(-1 + 16) << 25));
-                                    if (COUNT) acc.c_hits++;
-                                }
-                                acc.qn += __popc(mask);
-                            }
+                for (int item = 0; item <= nchunks + 1; item++) {
+                    uint64_t mask = 0, W = 0;
+                    int strand = 0, p = 0;
+                    if (item < nchunks) {
+                        const int slot = item * 32 + (int)lane;
+                        const bool slot_ok = slot < nslots;
+                        strand = slot >= nP ? 1 : 0;
+                        p = p0 + slot - strand * nP;
+                        if (slot_ok) W = nr_window64(sm.rdp[strand], p);
+                        mask = probe_all(P, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_MAIN>{});
+                        if (COUNT) c_probes_n += slot_ok ? NR_PROBES_MAIN : 0;
+                    } else if (item == nchunks && edge) {
+                        // one-column start overhang + interior insertion
+                        if (lane < 2 * NR_PROBES_EDGE) {
+                            strand = lane >= NR_PROBES_EDGE ? 1 : 0;
+                            p = -1;
+                            const int ti = NR_PROBES_MAIN + (int)lane - strand * NR_PROBES_EDGE;
+                            W = nr_window64(sm.rdp[strand], -1);
+                            const nr_probe_t t = c_probes[ti];
+                            const uint32_t key = nr_probe_key(W, t);
+                            const uint32_t w = __ldg(P.bits[0] + (key >> 5));
+                            mask = (uint64_t)((w >> (key & 31u)) & 1u) << ti;
+                            if (COUNT) c_probes_n++;
                         }
-                        item++;
                     }
+                    // queue positions of this item's hits: exclusive scan of the per-lane counts
+                    const int mine = __popcll(mask);
+                    int incl = mine;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        int v = __shfl_up_sync(0xffffffffu, incl, o);
+                        if ((int)lane >= o) incl += v;
+                    }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (total > NR_QCAP) { acc.overflow = 1; continue; }
+                    while (acc.qn + total > NR_QCAP || (item == nchunks + 1 && acc.qn > 0))
+                        drain<COUNT>(P, sm, acc, m);
+                    int pos = acc.qn + incl - mine;
+                    while (mask) {
+                        const int T = __ffsll((long long)mask) - 1;
+                        mask &= mask - 1;
+                        const nr_probe_t t = c_probes[T];
+                        const uint32_t key = nr_probe_key(W, t);
+                        const uint32_t w = __ldg(P.bits[t.drop] + (key >> 5));
+                        const uint32_t kr = __ldg(P.rank[t.drop] + (key >> 5)) +
+                                            (uint32_t)__popc(w & ((1u << (key & 31u)) - 1u));
+                        sm.queue[pos++] = make_uint2(kr | ((uint32_t)t.drop << 28),
+                                                     ((uint32_t)strand << 24) | ((uint32_t)(p + 16) << 25));
+                        if (COUNT) acc.c_hits++;
+                    }
+                    acc.qn += total;
                     __syncwarp();
-                    // phase B: verify everything queued
-#pragma unroll 1
-                    while (acc.qn > 0) drain<COUNT>(P, sm, acc, m);
-                    if (item >= n_items) break;
                 }
 
                 if (acc.overflow || (acc.best == 3 && P.resolve_below)) {
@@ -353,7 +327,7 @@ nr_match_filtered_kernel(const nr_filter_params P)
         }
     }
     if (COUNT && P.counters) {
-        atomicAdd(P.counters + 0, c_probes);
+        atomicAdd(P.counters + 0, c_probes_n);
         atomicAdd(P.counters + 1, acc.c_hits);
         atomicAdd(P.counters + 2, acc.c_ver);
         atomicAdd(P.counters + 3, acc.c_pass);
@@ -378,12 +352,15 @@ int nr_launch_filtered(const nr_whitelist *wl, const void *d_bases, const uint8_
         return NR_EUNSUPPORTED;
     }
     if (g_edge_uploaded_device != wl->device) {
-        NR_CHECK_CUDA(cudaMemcpyToSymbol(c_edge_probes, &NR_PROBES[NR_PROBES_MAIN],
-                                         sizeof(nr_probe_t) * NR_PROBES_EDGE));
+        NR_CHECK_CUDA(cudaMemcpyToSymbol(c_probes, &NR_PROBES[0],
+                                         sizeof(nr_probe_t) * NR_PROBES_ALL));
         g_edge_uploaded_device = wl->device;
     }
     nr_filter_params P;
-    for (int j = 0; j < 4; j++) { P.bm[j] = wl->d_bm[j]; P.ents[j] = wl->d_ents[j]; P.kstart[j] = wl->d_kstart[j]; }
+    for (int j = 0; j < 4; j++) {
+        P.bits[j] = wl->d_bits[j]; P.rank[j] = wl->d_rank[j];
+        P.ents[j] = wl->d_ents[j]; P.kstart[j] = wl->d_kstart[j];
+    }
     P.n = (uint32_t)wl->n; P.padL = (int)wl->pad_l; P.padR = (int)wl->pad_r;
     P.bases = (const uint4 *)d_bases; P.meta = d_meta; P.n_cand = n_cand;
     P.min_score = min_score; P.resolve_below = resolve_below;

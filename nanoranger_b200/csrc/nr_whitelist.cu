@@ -43,13 +43,13 @@ __global__ void nr_index_keys_kernel(const uint32_t *__restrict__ lo, uint32_t n
 // after the (key, idx) rows are sorted by key: bitmap bits, {idx, core} rows, head flags
 __global__ void nr_index_fill_kernel(const uint32_t *__restrict__ lo, uint32_t n,
                                      const uint32_t *__restrict__ keys,
-                                     const uint32_t *__restrict__ vals, uint2 *__restrict__ bm,
+                                     const uint32_t *__restrict__ vals, uint32_t *__restrict__ bits,
                                      uint2 *__restrict__ ents, uint32_t *__restrict__ heads)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         uint32_t k = keys[i];
-        atomicOr(&bm[k >> 5].x, 1u << (k & 31u));
+        atomicOr(&bits[k >> 5], 1u << (k & 31u));
         uint32_t e = vals[i];
         ents[i] = make_uint2(e, lo[e]);
         heads[i] = (i == 0 || keys[i - 1] != k) ? 1u : 0u;
@@ -68,10 +68,10 @@ __global__ void nr_index_kstart_kernel(const uint32_t *__restrict__ keys,
     }
 }
 
-// bm[w].y = number of distinct keys < 32 w  (w in 0..2^19 inclusive)
+// rank[w] = number of distinct keys < 32 w  (w in 0..2^19 inclusive)
 __global__ void nr_index_rank_kernel(const uint32_t *__restrict__ keys,
                                      const uint32_t *__restrict__ hs, uint32_t n,
-                                     uint2 *__restrict__ bm)
+                                     uint32_t *__restrict__ rank)
 {
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w > NR_BM_WORDS) return;
@@ -81,7 +81,7 @@ __global__ void nr_index_rank_kernel(const uint32_t *__restrict__ keys,
         uint32_t mid = (a + b) >> 1;
         if ((uint64_t)keys[mid] < target) a = mid + 1; else b = mid;
     }
-    bm[w].y = (a == n) ? hs[n - 1] : hs[a] - 1;
+    rank[w] = (a == n) ? hs[n - 1] : hs[a] - 1;
 }
 
 static int code_of(char c)
@@ -154,31 +154,32 @@ extern "C" int nr_whitelist_create(const char *cores, uint64_t n, uint32_t core_
             nr_set_error("cudaMalloc index scratch");
             return fail(NR_ENOMEM);
         }
-        size_t bmb = (size_t)(NR_BM_WORDS + 1) * sizeof(uint2);
+        size_t bmb = (size_t)(NR_BM_WORDS + 1) * sizeof(uint32_t);
         uint32_t nn = (uint32_t)n;
         uint32_t blocks = (nn + 255) / 256;
         for (int j = 0; j < 4; j++) {
-            if (cudaMalloc(&w->d_bm[j], bmb) != cudaSuccess ||
+            if (cudaMalloc(&w->d_bits[j], bmb) != cudaSuccess ||
+                cudaMalloc(&w->d_rank[j], bmb) != cudaSuccess ||
                 cudaMalloc(&w->d_ents[j], n * sizeof(uint2)) != cudaSuccess ||
                 cudaMalloc(&w->d_kstart[j], (n + 1) * sizeof(uint32_t)) != cudaSuccess) {
                 cudaFree(d_keys); cudaFree(d_vals); cudaFree(d_heads);
                 nr_set_error("cudaMalloc seed index");
                 return fail(NR_ENOMEM);
             }
-            w->bytes += bmb + n * sizeof(uint2) + (n + 1) * sizeof(uint32_t);
-            cudaMemset(w->d_bm[j], 0, bmb);
+            w->bytes += 2 * bmb + n * sizeof(uint2) + (n + 1) * sizeof(uint32_t);
+            cudaMemset(w->d_bits[j], 0, bmb);
             nr_index_keys_kernel<<<blocks, 256>>>(w->d_lo, nn, j, d_keys, d_vals);
             thrust::stable_sort_by_key(thrust::device, thrust::device_pointer_cast(d_keys),
                                        thrust::device_pointer_cast(d_keys) + n,
                                        thrust::device_pointer_cast(d_vals));
-            nr_index_fill_kernel<<<blocks, 256>>>(w->d_lo, nn, d_keys, d_vals, w->d_bm[j],
+            nr_index_fill_kernel<<<blocks, 256>>>(w->d_lo, nn, d_keys, d_vals, w->d_bits[j],
                                                   w->d_ents[j], d_heads);
             thrust::inclusive_scan(thrust::device, thrust::device_pointer_cast(d_heads),
                                    thrust::device_pointer_cast(d_heads) + n,
                                    thrust::device_pointer_cast(d_heads));
             nr_index_kstart_kernel<<<blocks, 256>>>(d_keys, d_heads, nn, w->d_kstart[j]);
             nr_index_rank_kernel<<<(NR_BM_WORDS + 1 + 255) / 256, 256>>>(d_keys, d_heads, nn,
-                                                                         w->d_bm[j]);
+                                                                         w->d_rank[j]);
         }
         cudaError_t e = cudaDeviceSynchronize();
         cudaFree(d_keys); cudaFree(d_vals); cudaFree(d_heads);
@@ -205,7 +206,7 @@ extern "C" void nr_whitelist_destroy(nr_whitelist_t *w)
     cudaSetDevice(w->device);
     nr_host_ctx_destroy(w->host_ctx);
     cudaFree(w->d_lo); cudaFree(w->d_hi); cudaFree(w->d_nm);
-    for (int j = 0; j < 4; j++) { cudaFree(w->d_bm[j]); cudaFree(w->d_ents[j]); cudaFree(w->d_kstart[j]); }
+    for (int j = 0; j < 4; j++) { cudaFree(w->d_bits[j]); cudaFree(w->d_rank[j]); cudaFree(w->d_ents[j]); cudaFree(w->d_kstart[j]); }
     delete w;
     if (prev >= 0) cudaSetDevice(prev);
 }
