@@ -231,3 +231,131 @@ NR_HD int nr_nfa16_w(uint64_t Wn, int m, uint32_t core, int padL, int padR, int 
     NR_NFA16_BODY(NR_BASE_AT)
 #undef NR_BASE_AT
 }
+
+// ---- interior scorer: furthest-reaching diagonals ------------------------------------------------
+// For a hit whose probe pins one end of the core (quarter 0 kept: the core starts at read
+// position a; quarter 0 dropped: the core ends just before read position e) the placements that
+// agree with the probe all start (end) there, and with cost <= 2 they are: no edit, one
+// insertion, two insertions, one substitution, one deletion.  Landau-Vishkin style: follow
+// diagonal 0 while it matches, then branch.  V holds the read as seen from the pinned end:
+// base t of V is sequence index t-1 relative to the pinned column (forward: read[a-1+t];
+// backward: read[e-t], used with the base-reversed core), vm has bit 2t set where base t exists.
+// Positions outside the read count as matches, so the result is exact when all of
+// V[0..18] exists and a lower bound on the cost otherwise (then the automaton decides).
+// Returns reach flags: 1 (cost 0, diagonal 0), 2 (cost 1, diagonal +1), 4 (cost 2, diagonal +2),
+// 8 (cost 2, diagonal 0), 16 (cost 2, diagonal -1).
+NR_HD int nr_ctz32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+
+NR_HD uint32_t nr_lv_diag(uint64_t V, uint64_t vm, uint32_t core, int s)   // s in -1..2
+{
+    uint32_t w = (uint32_t)(V >> (2 * (s + 1)));
+    uint32_t v = (uint32_t)(vm >> (2 * (s + 1))) & 0x55555555u;
+    uint32_t x = core ^ w;
+    return ((x | (x >> 1)) & 0x55555555u) & v;      // bit 2j: column j mismatches on diagonal s
+}
+
+NR_HD int nr_lv_run(uint32_t nz, int j)   // matches from column j on (0 <= j <= 16)
+{
+    if (j >= 16) return 0;
+    uint32_t t = nz >> (2 * j);
+    return t ? (nr_ctz32(t) >> 1) : 16 - j;
+}
+
+NR_HD int nr_lv16(uint64_t V, uint64_t vm, uint32_t core)
+{
+    const uint32_t n0 = nr_lv_diag(V, vm, core, 0);
+    const int j0 = nr_lv_run(n0, 0);
+    if (j0 == 16) return 1;
+    int r = 0;
+    const int j1 = j0 + nr_lv_run(nr_lv_diag(V, vm, core, 1), j0);
+    if (j1 == 16) r |= 2;
+    else if (j1 + nr_lv_run(nr_lv_diag(V, vm, core, 2), j1) == 16) r |= 4;
+    if (j0 + 1 + nr_lv_run(n0, j0 + 1) == 16) r |= 8;
+    if (j0 + 1 + nr_lv_run(nr_lv_diag(V, vm, core, -1), j0 + 1) == 16) r |= 16;
+    return r;
+}
+
+// bit 2t set for t in [lo, hi) (0 <= lo, hi <= 32 after clamping)
+NR_HD uint64_t nr_valid_mask(int lo, int hi)
+{
+    if (lo < 0) lo = 0;
+    if (hi > 32) hi = 32;
+    if (hi <= lo) return 0;
+    uint64_t a = hi >= 32 ? ~0ull : ((1ull << (2 * hi)) - 1ull);
+    uint64_t b = (1ull << (2 * lo)) - 1ull;
+    return (a & ~b) & 0x5555555555555555ull;
+}
+
+NR_HD uint64_t nr_rev_bases64(uint64_t x)
+{
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+#if defined(__CUDA_ARCH__)
+    lo = __brev(lo); hi = __brev(hi);
+#else
+    for (int k = 0; k < 2; k++) {
+        uint32_t v = k ? hi : lo;
+        v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+        v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+        v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+        v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
+        v = (v >> 16) | (v << 16);
+        if (k) hi = v; else lo = v;
+    }
+#endif
+    lo = ((lo & 0x55555555u) << 1) | ((lo >> 1) & 0x55555555u);
+    hi = ((hi & 0x55555555u) << 1) | ((hi >> 1) & 0x55555555u);
+    return ((uint64_t)lo << 32) | hi;        // halves swapped: full 32-base reversal
+}
+
+NR_HD uint32_t nr_rev_bases32(uint32_t x) { return (uint32_t)(nr_rev_bases64((uint64_t)x) >> 32); }
+
+// Verification of one nominated (entry, strand) for the probe `t` at slot position p.
+// Returns the cost (0..2, 3 = none) and *umi as nr_nfa16 does.  Exact for the placements that
+// agree with the probe; where the probe's pinned end is too close to a read end for the
+// diagonal walk to be exact, the walk only filters and the automaton scores.
+NR_HD int nr_verify16(const uint32_t *rdp, int m, uint32_t core, int padL, int padR, int p,
+                      const nr_probe_t &t, int *umi)
+{
+    int flags, pinned, interior;
+    const int fwd = t.drop != 0;
+    if (fwd) {
+        const int a = p;                                  // core column 0 at read position a
+        const uint64_t V = nr_window64(rdp, a - 1);
+        const uint64_t vm = nr_valid_mask(1 - a, m - a + 1);
+        flags = nr_lv16(V, vm, core);
+        pinned = a;
+        interior = a >= 0 && a + 18 <= m;
+    } else {
+        const int e = p + nr_probe_end(t);                // core column 15 at read position e-1
+        const uint64_t V = nr_rev_bases64(nr_window64(rdp, e - 19)) >> 24;   // base t = read[e-t]
+        const uint64_t vm = nr_valid_mask(e - m + 1, e + 1);
+        flags = nr_lv16(V, vm, nr_rev_bases32(core));
+        pinned = e;
+        interior = e >= 19 && e <= m;
+    }
+    if (!flags) { *umi = -1; return 3; }
+    if (!interior)
+        return nr_nfa16_w(nr_window64(rdp, nr_rows_first(p)), m, core, padL, padR,
+                          nr_rows_first(p), nr_rows_last(p, m), umi);
+    // totals: edit cost + read prefix beyond padL + read suffix beyond padR
+    int best = 3, arg = -1;
+    const int ks[5] = {0, 1, 2, 2, 2}, ss[5] = {0, 1, 2, 0, -1};
+    for (int c = 0; c < 5; c++) {
+        if (!(flags >> c & 1)) continue;
+        int start = fwd ? pinned : pinned - 16 - ss[c];
+        int end = fwd ? pinned + 16 + ss[c] : pinned;
+        int pre = start - padL, suf = m - end - padR;
+        int tot = ks[c] + (pre > 0 ? pre : 0) + (suf > 0 ? suf : 0);
+        if (tot < best || (tot == best && end < arg)) { best = tot; arg = end; }
+    }
+    if (best > 2) { *umi = -1; return 3; }
+    *umi = arg;
+    return best;
+}

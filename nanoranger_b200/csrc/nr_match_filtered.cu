@@ -14,8 +14,10 @@
 //   queue    one warp scan per 32 slots places the hits in a per-warp shared-memory queue
 //            (key rank = rank word + popc of the bitmap word below the key)
 //   verify   32 queued hits are expanded into the index rows sharing their keys (prefix sum over
-//            the row counts); lane = one row: reads {entry, core} and runs the 3-level shift-and
-//            automaton over the <= 27 read rows around the slot (registers only)
+//            the row counts); lane = one row: reads {entry, core} and scores it with
+//            nr_verify16: a furthest-reaching-diagonal walk from the end of the core the probe
+//            pins (exact in the read interior), the 3-level shift-and automaton over the <= 27
+//            read rows around the slot where the core may hang over a read end
 //   merge    best cost, the distinct (entry, strand) pairs attaining it (kept one per lane),
 //            smallest UMI row per pair
 // Candidates the filter cannot take (contain N, shorter than NR_FILTER_MIN_LEN, more than 32
@@ -69,6 +71,9 @@ struct Acc {                 // running answer of the candidate in flight (warp-
     unsigned long long c_hits, c_ver, c_pass;   // per lane partial counters
 };
 
+// the whole probe table in constant memory, for the places that index it dynamically
+__device__ __constant__ nr_probe_t c_probes[NR_PROBES_ALL];
+
 __device__ __forceinline__ int merge_umi(int a, int b) { return a < 0 ? b : (b < 0 ? a : min(a, b)); }
 
 // Take up to 32 queued bitmap hits, expand each into the index rows that share its key
@@ -85,7 +90,7 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, A
     __syncwarp();
     const uint32_t d = item.x >> 28, kr = item.x & 0x0FFFFFFFu;
     uint32_t start = 0, rows = 0;
-    if (have) {
+    if (have && kr != 0x0FFFFFFFu) {
         const uint32_t *ks = P.kstart[d] + kr;
         start = __ldg(ks);
         rows = __ldg(ks + 1) - start;
@@ -120,10 +125,9 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, A
             const uint32_t od = o_x >> 28;
             const int strand = (int)((o_y >> 24) & 1u);
             const int p = (int)(o_y >> 25) - 16;
-            const int r0 = nr_rows_first(p), r1 = nr_rows_last(p, m);
-            const uint64_t Wn = nr_window64(sm.rdp[strand], r0);
+            const nr_probe_t t = c_probes[(o_y >> 16) & 63u];
             const uint2 e = __ldg(P.ents[od] + o_start + (g - o_excl));
-            cost = nr_nfa16_w(Wn, m, e.y, P.padL, P.padR, r0, r1, &u);
+            cost = nr_verify16(sm.rdp[strand], m, e.y, P.padL, P.padR, p, t, &u);
             k = (e.x << 1) | (uint32_t)strand;
             if (COUNT) { acc.c_ver++; acc.c_pass += cost < 3; }
         }
@@ -169,9 +173,6 @@ __device__ __forceinline__ uint64_t probe_all(const nr_filter_params &P, uint64_
     (probe_one<I>(P, W, slot_ok, mask), ...);
     return mask;
 }
-
-// the whole probe table in constant memory, for the places that index it dynamically
-__device__ __constant__ nr_probe_t c_probes[NR_PROBES_ALL];
 
 template <bool COUNT>
 __global__ void __launch_bounds__(NR_FWARPS * 32, 3)
@@ -279,13 +280,18 @@ nr_match_filtered_kernel(const nr_filter_params P)
                         const int T = __ffsll((long long)mask) - 1;
                         mask &= mask - 1;
                         const nr_probe_t t = c_probes[T];
+                        // a probe reaching outside the read nominates nothing: its queue slot is
+                        // kept (positions were fixed by the scan) but marked as having no rows
+                        const bool valid = p + nr_probe_first(t) >= 0 && p + nr_probe_end(t) <= m;
                         const uint32_t key = nr_probe_key(W, t);
                         const uint32_t w = __ldg(P.bits[t.drop] + (key >> 5));
-                        const uint32_t kr = __ldg(P.rank[t.drop] + (key >> 5)) +
-                                            (uint32_t)__popc(w & ((1u << (key & 31u)) - 1u));
+                        uint32_t kr = __ldg(P.rank[t.drop] + (key >> 5)) +
+                                      (uint32_t)__popc(w & ((1u << (key & 31u)) - 1u));
+                        if (!valid) kr = 0x0FFFFFFFu;
                         sm.queue[pos++] = make_uint2(kr | ((uint32_t)t.drop << 28),
-                                                     ((uint32_t)strand << 24) | ((uint32_t)(p + 16) << 25));
-                        if (COUNT) acc.c_hits++;
+                                                     ((uint32_t)T << 16) | ((uint32_t)strand << 24) |
+                                                         ((uint32_t)(p + 16) << 25));
+                        if (COUNT) acc.c_hits += valid;
                     }
                     acc.qn += total;
                     __syncwarp();

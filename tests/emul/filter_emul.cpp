@@ -60,7 +60,8 @@ void nr_emul_revcomp(const uint8_t *q, int m, uint8_t *out)
 // the filtered matcher, serial.  wl: n packed cores.  cand: N x 64 codes (4 = N), clen: N.
 // took[i] = 0 when the candidate is left to the exhaustive kernel (contains N, too short).
 // score[i] = -128 / idx -1 / nbest 0 when no pair reaches cost <= 2.
-// windowed != 0: score hits on the row window of their slot (as the kernel does).
+// windowed != 0: score hits as the kernel does (nr_verify16: diagonal walk, automaton at the
+// read ends); 0: whole-read automaton.
 int nr_emul_filtered(const uint32_t *wl, int64_t n, int padL, int padR, const uint8_t *cand,
                      const uint8_t *clen, int64_t N, int windowed, int min_len, int32_t *idx,
                      int8_t *score, int32_t *nbest, uint8_t *strand, int16_t *umi, uint8_t *took,
@@ -128,7 +129,9 @@ int nr_emul_filtered(const uint32_t *wl, int64_t n, int padL, int padR, const ui
                         int r0 = windowed ? nr_rows_first(p) : 0;
                         int r1 = windowed ? nr_rows_last(p, m) : m;
                         int u;
-                        int cost = windowed ? nr_nfa16_w(nr_window64(rdp[s], r0), m, wl[it->second], padL, padR, r0, r1, &u) : nr_nfa16(rdp[s], m, wl[it->second], padL, padR, r0, r1, &u);
+                        int cost = windowed
+                            ? nr_verify16(rdp[s], m, wl[it->second], padL, padR, p, pr, &u)
+                            : nr_nfa16(rdp[s], m, wl[it->second], padL, padR, r0, r1, &u);
                         counters[2]++;
                         if (cost > 2) continue;
                         uint32_t k = (it->second << 1) | (uint32_t)s;
