@@ -323,23 +323,16 @@ NR_HD uint32_t nr_rev_bases32(uint32_t x) { return (uint32_t)(nr_rev_bases64((ui
 NR_HD int nr_verify16(const uint32_t *rdp, int m, uint32_t core, int padL, int padR, int p,
                       const nr_probe_t &t, int *umi)
 {
-    int flags, pinned, interior;
     const int fwd = t.drop != 0;
-    if (fwd) {
-        const int a = p;                                  // core column 0 at read position a
-        const uint64_t V = nr_window64(rdp, a - 1);
-        const uint64_t vm = nr_valid_mask(1 - a, m - a + 1);
-        flags = nr_lv16(V, vm, core);
-        pinned = a;
-        interior = a >= 0 && a + 18 <= m;
-    } else {
-        const int e = p + nr_probe_end(t);                // core column 15 at read position e-1
-        const uint64_t V = nr_rev_bases64(nr_window64(rdp, e - 19)) >> 24;   // base t = read[e-t]
-        const uint64_t vm = nr_valid_mask(e - m + 1, e + 1);
-        flags = nr_lv16(V, vm, nr_rev_bases32(core));
-        pinned = e;
-        interior = e >= 19 && e <= m;
-    }
+    // forward: core column 0 at read position a = p; backward: core column 15 at read
+    // position e - 1, base t of V = read[e - t], scored against the base-reversed core
+    const int pinned = fwd ? p : p + nr_probe_end(t);
+    uint64_t V = nr_window64(rdp, fwd ? pinned - 1 : pinned - 19);
+    if (!fwd) V = nr_rev_bases64(V) >> 24;
+    const uint64_t vm = fwd ? nr_valid_mask(1 - pinned, m - pinned + 1)
+                            : nr_valid_mask(pinned - m + 1, pinned + 1);
+    const int flags = nr_lv16(V, vm, fwd ? core : nr_rev_bases32(core));
+    const int interior = fwd ? (pinned >= 0 && pinned + 18 <= m) : (pinned >= 19 && pinned <= m);
     if (!flags) { *umi = -1; return 3; }
     if (!interior)
         return nr_nfa16_w(nr_window64(rdp, nr_rows_first(p)), m, core, padL, padR,

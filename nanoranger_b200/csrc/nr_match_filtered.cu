@@ -58,7 +58,7 @@ namespace {
 struct WarpSmem {
     uint4 tile[32];                  // packed records of the warp's 32 candidates
     uint32_t rdp[2][NR_RDP_WORDS];   // candidate in flight: forward / reverse complement, padded
-    uint2 queue[NR_QCAP];            // bitmap hits waiting for verification
+    uint32_t queue[NR_QCAP];         // bitmap hits waiting for verification: probe | strand | slot
 };
 
 struct Acc {                 // running answer of the candidate in flight (warp-uniform unless noted)
@@ -86,14 +86,24 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, A
     const int base = acc.qn - cnt;
     acc.qn = base;
     const bool have = (int)lane < cnt;
-    const uint2 item = have ? sm.queue[base + lane] : make_uint2(0u, 0u);
+    const uint32_t item = have ? sm.queue[base + lane] : 0u;
     __syncwarp();
-    const uint32_t d = item.x >> 28, kr = item.x & 0x0FFFFFFFu;
+    // the hit's key again (cheap, and now 32 hits wide), its rank among the distinct keys of the
+    // table, and through kstart its rows; probes reaching outside the read nominate nothing
+    const nr_probe_t t = c_probes[(item >> 16) & 63u];
+    const int h_strand = (int)((item >> 24) & 1u);
+    const int h_p = (int)(item >> 25) - 16;
+    const uint32_t d = (uint32_t)t.drop;
     uint32_t start = 0, rows = 0;
-    if (have && kr != 0x0FFFFFFFu) {
+    if (have && h_p + nr_probe_first(t) >= 0 && h_p + nr_probe_end(t) <= m) {
+        const uint32_t key = nr_probe_key(nr_window64(sm.rdp[h_strand], h_p), t);
+        const uint32_t w = __ldg(P.bits[d] + (key >> 5));
+        const uint32_t kr = __ldg(P.rank[d] + (key >> 5)) +
+                            (uint32_t)__popc(w & ((1u << (key & 31u)) - 1u));
         const uint32_t *ks = P.kstart[d] + kr;
         start = __ldg(ks);
         rows = __ldg(ks + 1) - start;
+        if (COUNT) acc.c_hits++;
     }
     // exclusive prefix of the row counts
     uint32_t incl = rows;
@@ -117,17 +127,16 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, A
         }
         const uint32_t o_start = __shfl_sync(0xffffffffu, start, lo);
         const uint32_t o_excl = __shfl_sync(0xffffffffu, excl, lo);
-        const uint32_t o_x = __shfl_sync(0xffffffffu, item.x, lo);
-        const uint32_t o_y = __shfl_sync(0xffffffffu, item.y, lo);
+        const uint32_t o_item = __shfl_sync(0xffffffffu, item, lo);
         int cost = 3, u = -1;
         uint32_t k = 0;
         if (active) {
-            const uint32_t od = o_x >> 28;
-            const int strand = (int)((o_y >> 24) & 1u);
-            const int p = (int)(o_y >> 25) - 16;
-            const nr_probe_t t = c_probes[(o_y >> 16) & 63u];
+            const nr_probe_t ot = c_probes[(o_item >> 16) & 63u];
+            const uint32_t od = (uint32_t)ot.drop;
+            const int strand = (int)((o_item >> 24) & 1u);
+            const int p = (int)(o_item >> 25) - 16;
             const uint2 e = __ldg(P.ents[od] + o_start + (g - o_excl));
-            cost = nr_verify16(sm.rdp[strand], m, e.y, P.padL, P.padR, p, t, &u);
+            cost = nr_verify16(sm.rdp[strand], m, e.y, P.padL, P.padR, p, ot, &u);
             k = (e.x << 1) | (uint32_t)strand;
             if (COUNT) { acc.c_ver++; acc.c_pass += cost < 3; }
         }
@@ -276,22 +285,13 @@ nr_match_filtered_kernel(const nr_filter_params P)
                     while (acc.qn + total > NR_QCAP || (item == nchunks + 1 && acc.qn > 0))
                         drain<COUNT>(P, sm, acc, m);
                     int pos = acc.qn + incl - mine;
+                    // queue item = (probe, strand, slot position); the key, its rank and its rows
+                    // are worked out in drain(), one hit per lane
+                    const uint32_t where = ((uint32_t)strand << 24) | ((uint32_t)(p + 16) << 25);
                     while (mask) {
                         const int T = __ffsll((long long)mask) - 1;
                         mask &= mask - 1;
-                        const nr_probe_t t = c_probes[T];
-                        // a probe reaching outside the read nominates nothing: its queue slot is
-                        // kept (positions were fixed by the scan) but marked as having no rows
-                        const bool valid = p + nr_probe_first(t) >= 0 && p + nr_probe_end(t) <= m;
-                        const uint32_t key = nr_probe_key(W, t);
-                        const uint32_t w = __ldg(P.bits[t.drop] + (key >> 5));
-                        uint32_t kr = __ldg(P.rank[t.drop] + (key >> 5)) +
-                                      (uint32_t)__popc(w & ((1u << (key & 31u)) - 1u));
-                        if (!valid) kr = 0x0FFFFFFFu;
-                        sm.queue[pos++] = make_uint2(kr | ((uint32_t)t.drop << 28),
-                                                     ((uint32_t)T << 16) | ((uint32_t)strand << 24) |
-                                                         ((uint32_t)(p + 16) << 25));
-                        if (COUNT) acc.c_hits += valid;
+                        sm.queue[pos++] = where | ((uint32_t)T << 16);
                     }
                     acc.qn += total;
                     __syncwarp();
