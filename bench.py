@@ -39,8 +39,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1 << 22, help="candidates per GPU per step")
     ap.add_argument("--whitelist", default="737K", choices=["737K", "3M-synthetic"])
-    ap.add_argument("--cpu-sample", type=int, default=1200)
-    ap.add_argument("--ref-sample", type=int, default=256, help="candidates per step of the CPU arm")
+    ap.add_argument("--cpu-sample", type=int, default=8000)
+    ap.add_argument("--ref-sample", type=int, default=1024, help="candidates per step of the CPU arm")
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -314,25 +314,40 @@ def main():
     wkey = f"{args.whitelist}-5p"
     ipc = inst_per_candidate(wkey)
     n_wl = len(wl_ascii)
-    if ipc is not None:
-        ops_per_cand, ops_src = ipc["thread_inst_per_candidate"], ipc["source"]
+    lanes_peak = ip["alu_ops_per_s"] / 1e9            # G lane-ops/s the ALU pipe can issue
+    if ipc is not None and ipc.get("alu_warp_inst_per_candidate"):
+        # ALU-pipe warp instructions per candidate counted by ncu for this kernel on this
+        # workload (profiles/), x 32 lanes an issued warp instruction occupies, x live rate
+        lane_ops = ipc["alu_warp_inst_per_candidate"] * 32.0
+        thread_ops = ipc.get("thread_inst_per_candidate")
+        ops_src = ipc["source"]
+        traffic = ipc.get("dram_bytes_per_candidate")
+        traffic = traffic * B if traffic is not None else None
     else:
-        # fallback: 14 thread-instructions per probe, 28 per verified row (27 rows), from SASS
-        ops_per_cand = (counters["probes"] * 14 + counters["verifications"] * 27 * 28) / B
-        ops_src = "estimate from kernel counters (no ncu figure in profiles/ yet)"
-    achieved = ops_per_cand * B / (ms_match * 1e-3) / 1e9
+        # fallback: 14 warp-wide instructions per probe slot, 28 per verified row, from SASS
+        lane_ops = (counters["probes"] * 14 + counters["verifications"] * 28) / B
+        thread_ops = None
+        ops_src = "estimate from kernel counters (profiles/inst_per_candidate.json missing)"
+        traffic = None
+    achieved = lane_ops * B / (ms_match * 1e-3) / 1e9
+    alg_bytes = n_bytes_in / B + 25 + 8                # ASCII + offsets in, packed record r/w, results out
     roofline = {
-        "bound": "alu", "achieved": achieved, "peak": ip["alu_ops_per_s"] / 1e9,
-        "unit": "G thread-inst/s", "frac": achieved / (ip["alu_ops_per_s"] / 1e9),
-        "traffic": None,
-        "peak_source": "nr_int_peak: LOP3+SHF chains on every SM, measured in this run "
-                       "(MEASURED_PEAKS.json has no integer peak)",
+        "bound": "alu", "achieved": achieved, "peak": lanes_peak, "unit": "G lane-ops/s",
+        "frac": achieved / lanes_peak, "traffic": traffic,
+        "definition": "ALU-pipe issue slots used by nr_match_filtered_kernel: ncu-counted ALU warp "
+                      "instructions per candidate x 32 lanes x candidates/s of the kernel timed live "
+                      "with CUDA events, over the LOP3/SHF issue rate nr_int_peak measures on the same "
+                      "GPU in the same run (= 148 SM x 64 lanes x SM clock)",
+        "peak_source": "nr_int_peak, measured in this run (MEASURED_PEAKS.json has no integer peak)",
         "peak_dual_issue": ip["dual_ops_per_s"] / 1e9,
-        "thread_inst_per_candidate": ops_per_cand, "thread_inst_source": ops_src,
+        "alu_lane_ops_per_candidate": lane_ops, "active_thread_inst_per_candidate": thread_ops,
+        "per_candidate_source": ops_src,
         "kernel": "nr_match_filtered_kernel", "kernel_ms_per_launch": ms_match,
-        "hbm": {"algorithmic_bytes_per_candidate": n_bytes_in / B + 25 + 8,
-                "achieved_gbs": (n_bytes_in + 33 * B) / (ms_step * 1e-3) / 1e9,
-                "peak_gbs": pk.get("hbm_gbs"), "peak_kind": pk_kind},
+        "kernel_share_of_step": ms_match / ms_step,
+        "hbm": {"algorithmic_bytes_per_candidate": alg_bytes,
+                "achieved_gbs": alg_bytes * B / (ms_step * 1e-3) / 1e9,
+                "peak_gbs": pk.get("hbm_gbs"), "peak_kind": pk_kind,
+                "frac": alg_bytes * B / (ms_step * 1e-3) / 1e9 / pk.get("hbm_gbs")},
     }
     line = {
         "metric": "barcode_candidates_per_sec", "value": value, "unit": "candidates/s",
