@@ -50,6 +50,10 @@ void nr_host_ctx_destroy(void *ctx);
 
 #define NR_BM_WORDS (1u << 19)
 
+// exhaustive kernel's split scratch: NR_EX_MAXGRID u32 counters, then NR_EX_MAXGRID uint4 partials
+#define NR_EX_MAXGRID 2048
+#define NR_EX_SCRATCH_BYTES (NR_EX_MAXGRID * 4 + NR_EX_MAXGRID * 16)
+
 // ---------------------------------------------------------------------------------------
 // device helpers
 

@@ -12,15 +12,19 @@ int nr_launch_exhaustive(const nr_whitelist *wl, const void *d_bases, const uint
                          const uint64_t *d_nmask, const uint32_t *d_list,
                          const uint32_t *d_list_count, uint64_t n_cand, int min_score,
                          int32_t *d_idx, int8_t *d_score, uint8_t *d_nbest, uint8_t *d_flags,
-                         uint8_t *d_umi, int grid_cap, cudaStream_t stream);
+                         uint8_t *d_umi, int grid_cap, void *d_scratch, cudaStream_t stream);
 int nr_launch_filtered(const nr_whitelist *wl, const void *d_bases, const uint8_t *d_meta,
                        uint64_t n_cand, int min_score, int resolve_below, int32_t *d_idx,
                        int8_t *d_score, uint8_t *d_nbest, uint8_t *d_flags, uint8_t *d_umi,
                        uint32_t *d_list, uint32_t *d_list_count, unsigned long long *d_counters,
                        int *grid_out, cudaStream_t stream);
 
-// workspace layout: [0,64) eight u64 counters, [64,68) list count, [128, 128 + 4n) list
-#define NR_WS_HEADER 128
+// workspace layout: [0,64) eight u64 counters, [64,68) list count, [128, 128 + 8 KB) the
+// exhaustive kernel's arrival counters (zeroed with the header), then its partials,
+// [NR_WS_HEADER, NR_WS_HEADER + 4n) list
+#define NR_WS_ZERO (128 + NR_EX_MAXGRID * 4)
+#define NR_WS_HEADER 65536
+static_assert(128 + NR_EX_SCRATCH_BYTES <= NR_WS_HEADER, "workspace header too small");
 
 namespace {
 struct DeviceGuard {
@@ -76,9 +80,19 @@ extern "C" int nr_match_device(const nr_whitelist_t *wl, const void *d_bases,
     }
     DeviceGuard guard(wl->device);
     cudaStream_t st = (cudaStream_t)stream;
-    if (eff == NR_MODE_EXHAUSTIVE)
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
+    if (eff == NR_MODE_EXHAUSTIVE) {
+        // the workspace is optional here: with one, batches smaller than the grid are split
+        // over the whitelist
+        void *scratch = nullptr;
+        if (d_workspace && workspace_bytes >= NR_WS_HEADER) {
+            NR_CHECK_CUDA(cudaMemsetAsync(d_workspace, 0, NR_WS_ZERO, st));
+            scratch = (uint8_t *)d_workspace + 128;
+        }
         return nr_launch_exhaustive(wl, d_bases, d_meta, d_nmask, nullptr, nullptr, n, min_score,
-                                    d_idx, d_score, d_nbest, d_flags, d_umi_q, 0, st);
+                                    d_idx, d_score, d_nbest, d_flags, d_umi_q, sms * 2, scratch, st);
+    }
     if (!d_workspace || workspace_bytes < nr_match_workspace_bytes(wl, n, mode)) {
         nr_set_error("nr_match_device: workspace too small (%zu < %zu)", workspace_bytes,
                      nr_match_workspace_bytes(wl, n, mode));
@@ -87,7 +101,7 @@ extern "C" int nr_match_device(const nr_whitelist_t *wl, const void *d_bases,
     uint8_t *ws = (uint8_t *)d_workspace;
     uint32_t *d_count = (uint32_t *)(ws + 64);
     uint32_t *d_list = (uint32_t *)(ws + NR_WS_HEADER);
-    NR_CHECK_CUDA(cudaMemsetAsync(ws, 0, NR_WS_HEADER, st));
+    NR_CHECK_CUDA(cudaMemsetAsync(ws, 0, NR_WS_ZERO, st));
     int grid = 0;
     int rc = nr_launch_filtered(wl, d_bases, d_meta, n, min_score, eff == NR_MODE_AUTO ? 1 : 0,
                                 d_idx, d_score, d_nbest, d_flags, d_umi_q, d_list, d_count,
@@ -95,10 +109,8 @@ extern "C" int nr_match_device(const nr_whitelist_t *wl, const void *d_bases,
     if (rc != NR_OK) return rc;
     // candidates the filter left (N, short, > 32 co-optimal pairs; in AUTO also everything below
     // cost 2) are resolved exactly, count read on the device
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
     return nr_launch_exhaustive(wl, d_bases, d_meta, d_nmask, d_list, d_count, n, min_score, d_idx,
-                                d_score, d_nbest, d_flags, d_umi_q, sms * 2, st);
+                                d_score, d_nbest, d_flags, d_umi_q, sms * 2, ws + 128, st);
 }
 
 // Debug/bench variant: same as NR_MODE_FILTERED but with the counting kernel; fills the five
@@ -117,7 +129,7 @@ extern "C" int nr_match_device_counted(const nr_whitelist_t *wl, const void *d_b
     DeviceGuard guard(wl->device);
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t *ws = (uint8_t *)d_workspace;
-    NR_CHECK_CUDA(cudaMemsetAsync(ws, 0, NR_WS_HEADER, st));
+    NR_CHECK_CUDA(cudaMemsetAsync(ws, 0, NR_WS_ZERO, st));
     int rc = nr_launch_filtered(wl, d_bases, d_meta, n, min_score, 0, d_idx, d_score, d_nbest,
                                 d_flags, d_umi_q, (uint32_t *)(ws + NR_WS_HEADER),
                                 (uint32_t *)(ws + 64), (unsigned long long *)ws, nullptr, st);
@@ -126,7 +138,7 @@ extern "C" int nr_match_device_counted(const nr_whitelist_t *wl, const void *d_b
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
     return nr_launch_exhaustive(wl, d_bases, d_meta, d_nmask, (uint32_t *)(ws + NR_WS_HEADER),
                                 (uint32_t *)(ws + 64), n, min_score, d_idx, d_score, d_nbest,
-                                d_flags, d_umi_q, sms * 2, st);
+                                d_flags, d_umi_q, sms * 2, ws + 128, st);
 }
 
 extern "C" int nr_match_counters(const void *d_workspace, uint64_t *c5, void *stream)

@@ -126,6 +126,54 @@ __device__ __forceinline__ void write_result(const Best &r, uint64_t cand, int m
     o_umi[cand] = (uint8_t)(u < 0 ? NR_UMI_NONE : u);
 }
 
+
+// ---- short lists: split the whitelist over blocks -------------------------------------------
+// When fewer candidates than blocks are to be resolved (the usual case for the list the filtered
+// kernel leaves: reads with N, very short reads), each candidate's scan of the whitelist is cut
+// into S slices handled by S blocks.  Partials go to `part` (one slot per work item); the last
+// block to arrive for a candidate (counter in `done`) merges them and writes the result.
+// total * S <= gridDim.x, so a block handles at most one work item when S > 1.
+#define NR_EX_MAXS 64
+
+struct ExScratch {
+    uint32_t *done;   // NR_EX_MAXGRID counters, zero between launches (the merging block resets)
+    uint4 *part;      // NR_EX_MAXGRID partials {score, cnt, key, -}
+};
+
+__device__ __forceinline__ uint32_t ex_slices(uint64_t total, const ExScratch &sc)
+{
+    if (!sc.done || total == 0 || total >= gridDim.x || gridDim.x > NR_EX_MAXGRID) return 1u;
+    uint32_t S = gridDim.x / (uint32_t)total;
+    return S > NR_EX_MAXS ? NR_EX_MAXS : S;
+}
+
+// returns true in the block that must write the candidate's result; `r` then holds the merge
+__device__ __forceinline__ bool ex_merge(Best &r, uint64_t w, uint64_t it, uint32_t S,
+                                         const ExScratch &sc, int *sh_flag)
+{
+    if (S == 1) return true;
+    if (threadIdx.x == 0) {
+        sc.part[w] = make_uint4((uint32_t)r.score, r.cnt, r.key, 0u);
+        __threadfence();
+        uint32_t prev = atomicAdd(&sc.done[it], 1u);
+        *sh_flag = (prev == S - 1);
+    }
+    __syncthreads();
+    const bool last = *sh_flag != 0;
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        Best m; m.score = -1000; m.cnt = 0; m.key = 0xFFFFFFFFu;
+        for (uint32_t k = 0; k < S; k++) {
+            uint4 v = __ldcg(sc.part + it * S + k);
+            best_merge(m, (int)v.x, v.y, v.z);
+        }
+        r = m;
+        sc.done[it] = 0u;
+    }
+    __syncthreads();
+    return last;
+}
+
 #define P2(x) ((uint32_t)((x) & 0xFFFF) * 0x10001u)
 
 // ---- L = 16, N-free whitelist: DPX s16x2, two entries per thread ---------------------------
@@ -137,13 +185,20 @@ nr_match_exhaustive16_kernel(const uint32_t *__restrict__ wl, uint32_t n, int pa
                              const uint32_t *__restrict__ list_count, uint64_t n_cand,
                              int min_score, int32_t *__restrict__ o_idx,
                              int8_t *__restrict__ o_score, uint8_t *__restrict__ o_nbest,
-                             uint8_t *__restrict__ o_flags, uint8_t *__restrict__ o_umi)
+                             uint8_t *__restrict__ o_flags, uint8_t *__restrict__ o_umi,
+                             ExScratch sc)
 {
     __shared__ uint8_t cf[NR_MAX_QUERY], cr[NR_MAX_QUERY];
     __shared__ Best shb[32];
+    __shared__ int sh_flag;
     uint64_t total = list ? (uint64_t)*list_count : n_cand;
     uint32_t npairs = (n + 1) >> 1;
-    for (uint64_t it = blockIdx.x; it < total; it += gridDim.x) {
+    const uint32_t S = ex_slices(total, sc);
+    const uint32_t per = (npairs + S - 1) / S;
+    for (uint64_t w = blockIdx.x; w < total * S; w += gridDim.x) {
+        const uint64_t it = w / S;
+        const uint32_t p_lo = (uint32_t)(w % S) * per;
+        const uint32_t p_hi = min(npairs, p_lo + per);
         uint64_t cand = list ? (uint64_t)list[it] : it;
         uint8_t mt = meta[cand];
         if (mt == 0xFF) {
@@ -160,7 +215,7 @@ nr_match_exhaustive16_kernel(const uint32_t *__restrict__ wl, uint32_t n, int pa
         __syncthreads();
         Best b; b.score = -1000; b.cnt = 0; b.key = 0xFFFFFFFFu;
         const uint32_t aleft = P2(-max(0, m - padL));
-        for (uint32_t p = threadIdx.x; p < npairs; p += blockDim.x) {
+        for (uint32_t p = p_lo + threadIdx.x; p < p_hi; p += blockDim.x) {
             uint32_t ea = wl[2 * p];
             bool vb = 2 * p + 1 < n;
             uint32_t eb = vb ? wl[2 * p + 1] : ea;
@@ -219,7 +274,7 @@ nr_match_exhaustive16_kernel(const uint32_t *__restrict__ wl, uint32_t n, int pa
             }
         }
         Best r = block_reduce_best(b, shb);
-        if (threadIdx.x == 0)
+        if (ex_merge(r, w, it, S, sc, &sh_flag) && threadIdx.x == 0)
             write_result(r, cand, m, cf, wl, nullptr, nullptr, 16, padL, padR, min_score, o_idx,
                          o_score, o_nbest, o_flags, o_umi);
     }
@@ -237,12 +292,19 @@ nr_match_exhaustive_generic_kernel(const uint32_t *__restrict__ wlo,
                                    const uint32_t *__restrict__ list_count, uint64_t n_cand,
                                    int min_score, int32_t *__restrict__ o_idx,
                                    int8_t *__restrict__ o_score, uint8_t *__restrict__ o_nbest,
-                                   uint8_t *__restrict__ o_flags, uint8_t *__restrict__ o_umi)
+                                   uint8_t *__restrict__ o_flags, uint8_t *__restrict__ o_umi,
+                                   ExScratch sc)
 {
     __shared__ uint8_t cf[NR_MAX_QUERY], cr[NR_MAX_QUERY];
     __shared__ Best shb[32];
+    __shared__ int sh_flag;
     uint64_t total = list ? (uint64_t)*list_count : n_cand;
-    for (uint64_t it = blockIdx.x; it < total; it += gridDim.x) {
+    const uint32_t S = ex_slices(total, sc);
+    const uint32_t per = (n + S - 1) / S;
+    for (uint64_t w = blockIdx.x; w < total * S; w += gridDim.x) {
+        const uint64_t it = w / S;
+        const uint32_t e_lo = (uint32_t)(w % S) * per;
+        const uint32_t e_hi = min(n, e_lo + per);
         uint64_t cand = list ? (uint64_t)list[it] : it;
         uint8_t mt = meta[cand];
         if (mt == 0xFF) {
@@ -259,7 +321,7 @@ nr_match_exhaustive_generic_kernel(const uint32_t *__restrict__ wlo,
         __syncthreads();
         Best b; b.score = -1000; b.cnt = 0; b.key = 0xFFFFFFFFu;
         const int aleft = -max(0, m - padL);
-        for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+        for (uint32_t e = e_lo + threadIdx.x; e < e_hi; e += blockDim.x) {
             uint32_t lo = wlo[e], hi = whi ? whi[e] : 0u, nm = wnm ? wnm[e] : 0u;
 #pragma unroll 1
             for (int strand = 0; strand < 2; strand++) {
@@ -302,7 +364,7 @@ nr_match_exhaustive_generic_kernel(const uint32_t *__restrict__ wlo,
             }
         }
         Best r = block_reduce_best(b, shb);
-        if (threadIdx.x == 0)
+        if (ex_merge(r, w, it, S, sc, &sh_flag) && threadIdx.x == 0)
             write_result(r, cand, m, cf, wlo, whi, wnm, L, padL, padR, min_score, o_idx, o_score,
                          o_nbest, o_flags, o_umi);
     }
@@ -316,22 +378,27 @@ int nr_launch_exhaustive(const nr_whitelist *wl, const void *d_bases, const uint
                          const uint64_t *d_nmask, const uint32_t *d_list,
                          const uint32_t *d_list_count, uint64_t n_cand, int min_score,
                          int32_t *d_idx, int8_t *d_score, uint8_t *d_nbest, uint8_t *d_flags,
-                         uint8_t *d_umi, int grid_cap, cudaStream_t stream)
+                         uint8_t *d_umi, int grid_cap, void *d_scratch, cudaStream_t stream)
 {
     if (!d_list && n_cand == 0) return NR_OK;
-    uint64_t want = d_list ? (uint64_t)grid_cap : n_cand;
+    // list mode: a fixed grid (the count lives on the device); full mode: one block per
+    // candidate, but never fewer blocks than grid_cap so that short batches get split
+    uint64_t want = d_list ? (uint64_t)grid_cap : (n_cand > (uint64_t)grid_cap ? n_cand : (uint64_t)grid_cap);
     unsigned grid = (unsigned)(want < 65535ull * 8 ? want : 65535ull * 8);
     if (grid == 0) grid = 1;
+    ExScratch sc;
+    sc.done = d_scratch ? (uint32_t *)d_scratch : nullptr;
+    sc.part = d_scratch ? (uint4 *)((uint8_t *)d_scratch + NR_EX_MAXGRID * sizeof(uint32_t)) : nullptr;
     if (wl->L == 16 && !wl->has_n) {
         nr_match_exhaustive16_kernel<<<grid, 256, 0, stream>>>(
             wl->d_lo, (uint32_t)wl->n, (int)wl->pad_l, (int)wl->pad_r, (const uint4 *)d_bases,
             d_meta, d_nmask, d_list, d_list_count, n_cand, min_score, d_idx, d_score, d_nbest,
-            d_flags, d_umi);
+            d_flags, d_umi, sc);
     } else {
         nr_match_exhaustive_generic_kernel<<<grid, 256, 0, stream>>>(
             wl->d_lo, wl->d_hi, wl->d_nm, (uint32_t)wl->n, (int)wl->L, (int)wl->pad_l,
             (int)wl->pad_r, (const uint4 *)d_bases, d_meta, d_nmask, d_list, d_list_count,
-            n_cand, min_score, d_idx, d_score, d_nbest, d_flags, d_umi);
+            n_cand, min_score, d_idx, d_score, d_nbest, d_flags, d_umi, sc);
     }
     NR_CHECK_CUDA(cudaGetLastError());
     return NR_OK;

@@ -272,29 +272,36 @@ nr_match_filtered_kernel(const nr_filter_params P)
                             if (COUNT) c_probes_n++;
                         }
                     }
-                    // queue positions of this item's hits: exclusive scan of the per-lane counts
-                    const int mine = __popcll(mask);
-                    int incl = mine;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        int v = __shfl_up_sync(0xffffffffu, incl, o);
-                        if ((int)lane >= o) incl += v;
-                    }
-                    const int total = __shfl_sync(0xffffffffu, incl, 31);
-                    if (total > NR_QCAP) { acc.overflow = 1; continue; }
-                    while (acc.qn + total > NR_QCAP || (item == nchunks + 1 && acc.qn > 0))
-                        drain<COUNT>(P, sm, acc, m);
-                    int pos = acc.qn + incl - mine;
-                    // queue item = (probe, strand, slot position); the key, its rank and its rows
-                    // are worked out in drain(), one hit per lane
+                    // an item with more hits than the queue holds (dense key bitmaps: whitelists
+                    // of millions of entries) is queued in four probe ranges of <= 9 x 32 hits
+                    const int total_all = __reduce_add_sync(0xffffffffu, __popcll(mask));
+                    const int nparts = total_all > NR_QCAP ? 4 : 1;
                     const uint32_t where = ((uint32_t)strand << 24) | ((uint32_t)(p + 16) << 25);
-                    while (mask) {
-                        const int T = __ffsll((long long)mask) - 1;
-                        mask &= mask - 1;
-                        sm.queue[pos++] = where | ((uint32_t)T << 16);
+#pragma unroll 1
+                    for (int part = 0; part < nparts; part++) {
+                        uint64_t pm = nparts == 1 ? mask : (mask & (0x1FFull << (9 * part)));
+                        // queue positions of the hits: exclusive scan of the per-lane counts
+                        const int mine = __popcll(pm);
+                        int incl = mine;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            int v = __shfl_up_sync(0xffffffffu, incl, o);
+                            if ((int)lane >= o) incl += v;
+                        }
+                        const int total = __shfl_sync(0xffffffffu, incl, 31);
+                        while (acc.qn + total > NR_QCAP || (item == nchunks + 1 && acc.qn > 0))
+                            drain<COUNT>(P, sm, acc, m);
+                        int pos = acc.qn + incl - mine;
+                        // queue item = (probe, strand, slot position); the key, its rank and its
+                        // rows are worked out in drain(), one hit per lane
+                        while (pm) {
+                            const int T = __ffsll((long long)pm) - 1;
+                            pm &= pm - 1;
+                            sm.queue[pos++] = where | ((uint32_t)T << 16);
+                        }
+                        acc.qn += total;
+                        __syncwarp();
                     }
-                    acc.qn += total;
-                    __syncwarp();
                 }
 
                 if (acc.overflow || (acc.best == 3 && P.resolve_below)) {

@@ -134,3 +134,36 @@ def test_filtered_mode_refused_when_unsupported(cuda_device):
     wl16 = Whitelist(["ACGTACGTACGTACGT", "ACGTACGTACGTACGA"], 4, 4)
     with pytest.raises(RuntimeError):
         wl16.match_host(["ACGTACGTACGTACGTACGTAA"], min_score=10, mode=NR_MODE_FILTERED)
+
+
+@pytest.mark.parametrize("n", [1, 3, 37, 295, 297])
+def test_exhaustive_small_batches_split_over_whitelist(cuda_device, oracle, n):
+    """Batches smaller than the grid: the whitelist scan of each candidate is cut into slices
+    handled by different blocks and merged by the last block to arrive."""
+    from nanoranger_b200 import Whitelist, NR_MODE_AUTO, NR_MODE_EXHAUSTIVE
+    rng = np.random.default_rng(700 + n)
+    wl_strs = tie_rich_whitelist(rng, 5000)
+    seqs = mixed_candidates(rng, wl_strs, n, 30, 50, with_n=0.3)
+    wl = Whitelist(wl_strs, 30, 40)
+    ref = _oracle(oracle, wl_strs, 30, 40, seqs)
+    for mode in (NR_MODE_EXHAUSTIVE, NR_MODE_AUTO):
+        for rep in range(2):      # twice: the arrival counters must be back at zero
+            res, _ = _run_device(wl, seqs, 14, mode)
+            compare(ref, res, 14, exact_below=True, label=f"split n={n} mode={mode} rep={rep}")
+
+
+def test_dense_index_3M_sized_whitelist_vs_oracle(cuda_device, oracle):
+    """C4's whitelist size (6 794 880 synthetic 16-mers): a third of all 24-bit keys are set, items
+    overflow the hit queue and are queued in probe ranges; every answer still equals the oracle's."""
+    from nanoranger_b200 import Whitelist, NR_MODE_FILTERED, synth, whitelists
+    wl_a = whitelists.synthetic_whitelist(6794880)
+    d = synth.make_candidates(wl_a, 160, seed=4)
+    seqs = synth.to_strings(d["seqs"], d["offsets"])
+    wl = Whitelist(wl_a, 30, 40)
+    wlc = oracle._CODE[wl_a]
+    cc, cl = oracle.encode_many(seqs, 64)
+    ref = oracle.match(wlc, 30, 40, cc, cl)
+    res, ws = _run_device(wl, seqs, 14, NR_MODE_FILTERED, counted=True)
+    nhi = compare(ref, res, 14, exact_below=False, label="3M filtered")
+    assert nhi > 40
+    assert wl.counters(ws)["hits"] > 300 * len(seqs)
