@@ -42,6 +42,10 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=8000)
     ap.add_argument("--ref-sample", type=int, default=1024, help="candidates per step of the CPU arm")
     ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--workload", default="flanks", choices=["flanks", "kinnex"],
+                    help="flanks: BASELINE metric config (5' flanks vs 737K); kinnex: config 5, 16 "
+                         "sub-reads per read, 3' geometry, barcode match + UMI collapse")
+    ap.add_argument("--max-dist", type=int, default=1, help="kinnex: UMI clustering distance")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -184,6 +188,126 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_kinnex(args, rank, local_rank, world):
+    """BASELINE config 5: synthetic MAS-ISO-seq/Kinnex concatemers, 16 sub-reads per read, 10x 3'
+    GEX geometry (35-nt candidates, pads 4/17, UMI 12 at reference column 20: utils.py:1374,
+    1451-1452, 1490-1491), whitelist = the observed cells (write_bc_3p10XGEX keeps raw 16-mers
+    with > 20 reads that are on the 737K list).  One step = pack -> match -> records ->
+    partition by barcode hash -> ONE all-to-all -> UMI collapse of the owned barcodes."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from nanoranger_b200 import NR_MODE_FILTERED, Whitelist, synth, whitelists
+    from nanoranger_b200 import umi as U
+    n_cells, n_genes, sub = 10000, 20000, 16
+    rng = np.random.Generator(np.random.PCG64(20180201))
+    wl_all = whitelists.load_737k()
+    cells = np.sort(rng.choice(len(wl_all), n_cells, replace=False))
+    wl_ascii = wl_all[cells]
+    wl = Whitelist(wl_ascii, 4, 17, device=local_rank)
+    reads = args.batch // sub
+    B = reads * sub
+    r2 = np.random.Generator(np.random.PCG64(args.seed + 1000 * rank))
+    w = 1.0 / np.arange(1, n_cells + 1) ** 0.8
+    cell = r2.choice(n_cells, size=B, p=w / w.sum())
+    gene = (r2.zipf(1.4, B) % n_genes).astype(np.uint32)
+    mol = r2.integers(0, 6, B).astype(np.uint64)                 # few molecules per (cell, gene): PCR duplicates
+    h = (cell.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15) ^ gene.astype(np.uint64) * np.uint64(0xC2B2AE3D27D4EB4F)
+         ^ mol * np.uint64(0x165667B19E3779F9))
+    h ^= h >> np.uint64(29)
+    umi_codes = np.stack([((h >> np.uint64(2 * k + 7)) & np.uint64(3)).astype(np.uint8) for k in range(12)], 1)
+    d = synth.make_candidates(wl_ascii, B, seed=args.seed + 7 + 1000 * rank, geometry="3p", umi_len=12,
+                              cell_idx=cell, umi_codes=umi_codes)
+    d_seqs = torch.from_numpy(d["seqs"]).to(dev)
+    d_off = torch.from_numpy(d["offsets"].view(np.int64)).to(dev)
+    d_gene = torch.from_numpy(gene.view(np.int32)).to(dev)
+    ws = wl.workspace(B, dev, NR_MODE_FILTERED)
+    out = wl.alloc_result(B, dev)
+    info = {}
+
+    phases = {}
+
+    def step(timed=False):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)] if timed else None
+        mark = (lambda k: ev[k].record()) if timed else (lambda k: None)
+        mark(0)
+        bases, meta, nmask = wl.pack_device(d_seqs, d_off)
+        wl.match_device(bases, meta, nmask, min_score=14, mode=NR_MODE_FILTERED, out=out, workspace=ws)
+        mark(1)
+        rec = U.records_device(bases, meta, nmask, out, 14, 12, gene=d_gene, with_src=False)
+        mark(2)
+        if world > 1:
+            rows, counts = U.partition_device(rec["bc"], rec["gene"], rec["umi"], world)
+            mark(3)
+            got = U.exchange_records(rows, counts)
+            mark(4)
+            bc, gene_r, umi_r, _ = U.unzip_device(got)
+        else:
+            mark(3)
+            mark(4)
+            bc, gene_r, umi_r = rec["bc"], rec["gene"], rec["umi"]
+        r = U.collapse_device(bc, gene_r, umi_r, 12, args.max_dist)
+        mark(5)
+        info.update(n_records=rec["n_records"], n_groups=r["n_groups"], short=rec["n_short_umi"])
+        if timed:
+            torch.cuda.synchronize()
+            for k, nm in enumerate(("pack+match", "records", "partition", "all_to_all", "collapse")):
+                phases[nm] = ev[k].elapsed_time(ev[k + 1])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    step(timed=True)                       # one extra, untimed-for-the-metric step with phase events
+    barrier()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(info["n_records"]), float(info["n_groups"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        ms = float(t.item())
+        line = {
+            "metric": "barcode_candidates_per_sec", "value": world * B / (ms * 1e-3), "unit": "candidates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic",
+            "config": {"workload": "synthetic-kinnex16-3p-gex-match+umi-collapse",
+                       "reads_per_gpu_per_step": reads, "subreads_per_read": sub,
+                       "whitelist": f"{n_cells} observed cells drawn from 737K-august-2016", "pads": [4, 17],
+                       "min_score": 14, "umi_len": 12, "umi_max_dist": args.max_dist, "genes": n_genes,
+                       "exchange": "one variable-count all-to-all of 16 B records (NCCL)" if world > 1 else "none (1 GPU)",
+                       "l2": "inputs larger than L2 (%.0f MB ASCII per GPU)" % (d["seqs"].nbytes / 1e6)},
+            "reads_per_sec": world * reads / (ms * 1e-3),
+            "umi": {"records": int(tot[0].item()), "molecules": int(tot[1].item()),
+                    "short_umi_rank0": info["short"]},
+            "phases_ms_rank0": phases,
+            "gpu_launches": None, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -197,6 +321,9 @@ def main():
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback exists)")
+    if args.workload == "kinnex":
+        run_kinnex(args, rank, local_rank, world)
+        return
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:

@@ -131,6 +131,34 @@ int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_gene, const u
                            size_t workspace_bytes, void *stream);
 size_t nr_umi_workspace_bytes(uint64_t n);
 
+/* ---- matcher results -> UMI records (device-resident pipelines) ------------------------------
+ * Replaces the per-record loop of utils.process_matching_* (utils.py:697-718, 843-868,
+ * 1148-1170, 1477-1504): a candidate becomes a record iff it is assigned (see nr_match_device)
+ * and SEQ[umi_q : umi_q + umi_len] exists; record = (barcode idx, gene id, 2-bit packed UMI,
+ * source candidate).  d_gene (nullable) gives the gene/transcript id of every candidate.
+ * Records keep candidate order.  d_stats[0] = records written, [1] = assigned candidates dropped
+ * for a short/missing UMI (the reference's "short UMI reads", utils.py:715-716), [2] = dropped
+ * because the UMI contains a non-ACGT base (not representable in 2 bit/base). */
+int nr_umi_records_device(const void *d_bases, const uint8_t *d_meta, const uint64_t *d_nmask,
+                          const int32_t *d_idx, const int8_t *d_score, const uint8_t *d_nbest,
+                          const uint8_t *d_flags, const uint8_t *d_umi_q, const uint32_t *d_gene,
+                          uint64_t n, int min_score, int umi_len, uint32_t *d_rec_bc,
+                          uint32_t *d_rec_gene, uint32_t *d_rec_umi, uint32_t *d_rec_src,
+                          uint64_t *d_stats, void *d_workspace, size_t workspace_bytes,
+                          void *stream);
+size_t nr_umi_records_workspace_bytes(uint64_t n);
+
+/* Multi-GPU UMI collapse (no reference counterpart: the reference is single-process).  Orders
+ * the records by owner rank = hash(barcode idx) % world into 16-byte rows (bc, gene, umi, src)
+ * and fills d_counts[world], the send counts of the one variable-count all-to-all that puts
+ * every record of a barcode on one GPU.  d_cursor_scratch: world x u64.  nr_umi_unzip_device
+ * splits received rows back into the arrays nr_umi_collapse_device takes (d_src nullable). */
+int nr_umi_partition_device(const uint32_t *d_bc, const uint32_t *d_gene, const uint32_t *d_umi,
+                            const uint32_t *d_src, uint64_t n, int world, void *d_out_records,
+                            uint64_t *d_counts, uint64_t *d_cursor_scratch, void *stream);
+int nr_umi_unzip_device(const void *d_records, uint64_t n, uint32_t *d_bc, uint32_t *d_gene,
+                        uint32_t *d_umi, uint32_t *d_src, void *stream);
+
 /* ---- measurement support -------------------------------------------------------------------
  * INT-pipe roofline denominator: runs a dependent LOP3/IADD3 chain on
  * every SM for `iters` iterations and returns executed integer thread-ops per second. */

@@ -34,6 +34,8 @@ SYMBOLS = (
     "nr_match_device", "nr_match_workspace_bytes", "nr_match_host", "nr_host_alloc",
     "nr_host_free", "nr_umi_collapse_device", "nr_umi_workspace_bytes", "nr_int_peak",
     "nr_int_peak_dual", "nr_match_device_counted", "nr_match_counters",
+    "nr_umi_records_device", "nr_umi_records_workspace_bytes", "nr_umi_partition_device",
+    "nr_umi_unzip_device",
 )
 
 _lib = None
@@ -81,6 +83,14 @@ def lib() -> C.CDLL:
     L.nr_umi_collapse_device.restype = i32
     L.nr_umi_workspace_bytes.argtypes = [u64]
     L.nr_umi_workspace_bytes.restype = sz
+    L.nr_umi_records_device.argtypes = [vp] * 9 + [u64, i32, i32] + [vp] * 6 + [sz, vp]
+    L.nr_umi_records_device.restype = i32
+    L.nr_umi_records_workspace_bytes.argtypes = [u64]
+    L.nr_umi_records_workspace_bytes.restype = sz
+    L.nr_umi_partition_device.argtypes = [vp, vp, vp, vp, u64, i32, vp, vp, vp, vp]
+    L.nr_umi_partition_device.restype = i32
+    L.nr_umi_unzip_device.argtypes = [vp, u64, vp, vp, vp, vp, vp]
+    L.nr_umi_unzip_device.restype = i32
     L.nr_int_peak.argtypes = [i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.nr_int_peak.restype = i32
     L.nr_int_peak_dual.argtypes = [i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]

@@ -61,9 +61,10 @@ size_t carve(uint8_t *base, uint64_t n, UmiWs *w, size_t cub_bytes)
 
 size_t cub_temp_bytes(uint64_t n)
 {
-    // radix sort temp is O(#tiles); scans likewise.  A generous closed form keeps this callable
-    // without a device: 16 bytes per 1024 keys per pass-histogram plus fixed slack.
-    return align_up((size_t)(n / 64 + 1) * 64 + (8u << 20));
+    // The in/out (non-DoubleBuffer) radix sort keeps one more copy of keys and values for its
+    // odd passes (12 B per record for u64 keys + u32 values) next to the per-tile histograms;
+    // a closed form keeps this callable without a device.
+    return align_up((size_t)n * 16 + (size_t)(n / 64 + 1) * 64 + (8u << 20));
 }
 
 __global__ void k_init(const uint32_t *umi, uint64_t n, uint32_t *umi_a, uint32_t *idx_a)

@@ -93,7 +93,7 @@ def partition_records(bc, gene, umi, world: int):
 
 
 def exchange_records(rec_t, send_counts, group=None):
-    """One variable-count all-to-all of (bc, gene, umi) records (torch int32 [n,3] on the
+    """One variable-count all-to-all of (bc, gene, umi[, src]) records (torch int32 [n,3|4] on the
     process group's device: NCCL over NVLink on GPUs, gloo in the CPU tests).
     -> received records [m,3]."""
     import torch
@@ -103,7 +103,7 @@ def exchange_records(rec_t, send_counts, group=None):
     rc = torch.empty(world, dtype=torch.int64, device=rec_t.device)
     dist.all_to_all_single(rc, sc, group=group)
     rcl = [int(x) for x in rc.tolist()]
-    out = torch.empty((sum(rcl), 3), dtype=rec_t.dtype, device=rec_t.device)
+    out = torch.empty((sum(rcl), rec_t.shape[1]), dtype=rec_t.dtype, device=rec_t.device)
     dist.all_to_all_single(out, rec_t.contiguous(), output_split_sizes=rcl,
                            input_split_sizes=[int(x) for x in send_counts], group=group)
     return out
@@ -114,3 +114,80 @@ def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
     per = (n + world - 1) // world
     lo = min(n, rank * per)
     return lo, min(n, lo + per)
+
+
+# ---- device-resident pipeline: matcher results -> records -> (all-to-all) -> collapse -------------
+
+def records_device(bases, meta, nmask, res, min_score: int, umi_len: int, gene=None,
+                   with_src: bool = True):
+    """Matcher outputs (torch tensors on one GPU, see Whitelist.match_device) -> UMI records of
+    the assigned candidates, in candidate order (device twin of the loop in
+    utils.process_matching_*, utils.py:697-718).  -> dict(bc, gene, umi, src [k] int32 tensors,
+    n_records, n_short_umi, n_umi_with_n).  Reading the counts is the only synchronisation."""
+    import torch
+    n = meta.numel()
+    dev = meta.device
+    L = _lib.lib()
+    out = [torch.empty(max(n, 1), dtype=torch.int32, device=dev) for _ in range(4)]
+    stats = torch.zeros(3, dtype=torch.int64, device=dev)
+    ws = torch.empty(int(L.nr_umi_records_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _lib.check(L.nr_umi_records_device(
+            bases.data_ptr(), meta.data_ptr(), nmask.data_ptr(), res.idx.data_ptr(),
+            res.score.data_ptr(), res.nbest.data_ptr(), res.flags.data_ptr(), res.umi_q.data_ptr(),
+            gene.data_ptr() if gene is not None else None, n, min_score, umi_len,
+            out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+            out[3].data_ptr() if with_src else None, stats.data_ptr(), ws.data_ptr(), ws.numel(),
+            st), "nr_umi_records_device")
+    k, short, with_n = (int(x) for x in stats.tolist())
+    return {"bc": out[0][:k], "gene": out[1][:k], "umi": out[2][:k], "src": out[3][:k],
+            "n_records": k, "n_short_umi": short, "n_umi_with_n": with_n}
+
+
+def partition_device(d_bc, d_gene, d_umi, world: int, d_src=None):
+    """Device records -> ([n,4] int32 rows (bc, gene, umi, src) ordered by owner rank,
+    send_counts list[world]).  Same owner hash as owner_rank()."""
+    import torch
+    n = d_bc.numel()
+    dev = d_bc.device
+    L = _lib.lib()
+    rows = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev)
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    cursor = torch.empty(world, dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _lib.check(L.nr_umi_partition_device(
+            d_bc.data_ptr(), d_gene.data_ptr() if d_gene is not None else None, d_umi.data_ptr(),
+            d_src.data_ptr() if d_src is not None else None, n, world, rows.data_ptr(),
+            counts.data_ptr(), cursor.data_ptr(), st), "nr_umi_partition_device")
+    return rows[:n], [int(x) for x in counts.tolist()]
+
+
+def unzip_device(rows):
+    """[m,4] int32 rows -> (bc, gene, umi, src) int32 tensors."""
+    import torch
+    m = rows.shape[0]
+    dev = rows.device
+    out = [torch.empty(max(m, 1), dtype=torch.int32, device=dev) for _ in range(4)]
+    st = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().nr_umi_unzip_device(
+            rows.data_ptr(), m, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+            out[3].data_ptr(), st), "nr_umi_unzip_device")
+    return tuple(t[:m] for t in out)
+
+
+def collapse_distributed(d_bc, d_gene, d_umi, umi_len: int, max_dist: int = 0, group=None):
+    """UMI collapse over all ranks of `group` (one process per GPU, NCCL): partition the local
+    records by owner rank on the device, ONE variable-count all-to-all of 16-byte rows, local
+    collapse of the barcodes this rank owns.  -> collapse_device() dict for the owned barcodes.
+    With no process group (single GPU) this is collapse_device()."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return collapse_device(d_bc, d_gene, d_umi, umi_len, max_dist)
+    world = dist.get_world_size(group)
+    rows, counts = partition_device(d_bc, d_gene, d_umi, world)
+    got = exchange_records(rows, counts, group)
+    bc, gene, umi, _ = unzip_device(got)
+    return collapse_device(bc, gene, umi, umi_len, max_dist)

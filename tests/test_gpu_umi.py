@@ -65,3 +65,88 @@ def test_exact_dedup_equals_numpy_unique_per_barcode(cuda_device):
     assert len(df) == len(exp)
     for b, us in exp.items():
         assert df.loc[b, "umi_cnt"] == len(np.unique(us)) and df.loc[b, "read_cnt"] == len(us)
+
+
+def test_records_from_match_results(cuda_device, oracle):
+    """nr_umi_records_device == the per-record loop of process_matching_* on the oracle's
+    answers: assigned candidates only, umi = seq[q:q+len], short and N-containing UMIs dropped."""
+    import torch
+    from nanoranger_b200 import NR_MODE_FILTERED, Whitelist, pack_ascii, synth, whitelists
+    from nanoranger_b200 import umi as U
+    wl_a = whitelists.load_737k()
+    d = synth.make_candidates(wl_a, 3000, seed=11)
+    seqs = synth.to_strings(d["seqs"], d["offsets"])
+    rng = np.random.default_rng(1)
+    for i in rng.integers(0, len(seqs), 150):              # sprinkle N into some UMIs / barcodes
+        j = int(rng.integers(0, len(seqs[i])))
+        seqs[i] = seqs[i][:j] + "N" + seqs[i][j + 1:]
+    seqs += [s[:34] for s in seqs[:200]]                   # cut inside the UMI: short
+    wl = Whitelist(wl_a, 30, 40)
+    buf, off = pack_ascii(seqs)
+    dev = torch.device("cuda:0")
+    bases, meta, nmask = wl.pack_device(torch.from_numpy(buf.copy()).to(dev),
+                                        torch.from_numpy(off.view(np.int64).copy()).to(dev))
+    res = wl.match_device(bases, meta, nmask, min_score=14, mode=NR_MODE_FILTERED)
+    gene = torch.arange(len(seqs), dtype=torch.int32, device=dev) % 7
+    for umi_len in (10, 12, 16):
+        r = U.records_device(bases, meta, nmask, res, 14, umi_len, gene=gene)
+        cc, cl = oracle.encode_many(seqs, 64)
+        ref = oracle.match(oracle._CODE[wl_a], 30, 40, cc, cl)
+        exp, short, with_n = [], 0, 0
+        for i, s in enumerate(seqs):
+            if ref["n_best"][i] == 1 and ref["strand"][i] == 0 and ref["best_score"][i] >= 14:
+                q = int(ref["umi_q"][i])
+                u = s[q:q + umi_len] if q >= 0 else ""
+                if len(u) < umi_len:
+                    short += 1
+                elif "N" in u:
+                    with_n += 1
+                else:
+                    exp.append((int(ref["best_idx"][i]), i % 7, U.pack_umis([u], umi_len)[0][0], i))
+        got = list(zip(*(r[k].cpu().numpy().view(np.uint32).tolist() for k in ("bc", "gene", "umi", "src"))))
+        assert got == [tuple(int(x) for x in e) for e in exp]
+        assert (r["n_records"], r["n_short_umi"], r["n_umi_with_n"]) == (len(exp), short, with_n)
+        assert with_n > 0 and (short > 0 or umi_len < 12)
+
+
+@pytest.mark.parametrize("world", [1, 2, 8, 200])
+def test_partition_by_owner(cuda_device, world):
+    import torch
+    from nanoranger_b200 import umi as U
+    rng = np.random.default_rng(world)
+    n = 100003
+    bc = rng.integers(0, 5000, n).astype(np.uint32)
+    gene = rng.integers(0, 9, n).astype(np.uint32)
+    um = rng.integers(0, 1 << 24, n).astype(np.uint32)
+    dev = torch.device("cuda:0")
+    t = [torch.from_numpy(x.view(np.int32)).to(dev) for x in (bc, gene, um)]
+    rows, counts = U.partition_device(t[0], t[1], t[2], world)
+    rows = rows.cpu().numpy().view(np.uint32)
+    own = U.owner_rank(bc, world)
+    assert counts == np.bincount(own, minlength=world).tolist()
+    got_own = U.owner_rank(rows[:, 0], world)
+    assert (np.diff(got_own) >= 0).all()                         # ordered by owner
+    src = rows[:, 3].astype(np.int64)
+    assert np.array_equal(np.sort(src), np.arange(n))            # a permutation of the input
+    assert np.array_equal(rows[:, 0], bc[src]) and np.array_equal(rows[:, 1], gene[src])
+    assert np.array_equal(rows[:, 2], um[src])
+    b2, g2, u2, s2 = (x.cpu().numpy().view(np.uint32) for x in U.unzip_device(
+        torch.from_numpy(rows.view(np.int32)).to(dev)))
+    assert np.array_equal(np.stack([b2, g2, u2, s2], 1), rows)
+
+
+def test_umi_collapse_millions_of_records(cuda_device):
+    """workspace sizing at C5 scale (CUB's sort storage grows with n) + exact dedup invariants."""
+    import torch
+    from nanoranger_b200 import umi as U
+    rng = np.random.default_rng(77)
+    n = 5_000_000
+    bc = rng.integers(0, 10000, n).astype(np.uint32)
+    gene = rng.integers(0, 2000, n).astype(np.uint32)
+    um = rng.integers(0, 1 << 6, n).astype(np.uint32)
+    r = U.collapse_host(bc, gene, um, 12, 0)
+    key = (bc.astype(np.uint64) << np.uint64(40)) | (gene.astype(np.uint64) << np.uint64(24)) | um
+    uk, cnt = np.unique(key, return_counts=True)
+    assert r["n_groups"] == len(uk)
+    assert int(r["g_reads"].sum()) == n and np.array_equal(r["g_reads"], cnt.astype(np.uint32))
+    assert np.array_equal(r["rep_umi"], um)
