@@ -34,6 +34,7 @@ struct UmiWs {
     uint32_t *du_rep;                      // per distinct: distinct id of its representative
     uint32_t *rep_reads;                   // per distinct: reads of the cluster it represents
     uint32_t *rep_flag, *rep_pos;          // per distinct
+    uint32_t *rep_u, *rep_c;               // per group slot: UMI / reads of the representatives found so far
     uint32_t *totals;                      // [0] n distinct, [1] n groups, [2] n reps
     void *cub_tmp;
     size_t cub_bytes;
@@ -49,7 +50,7 @@ size_t carve(uint8_t *base, uint64_t n, UmiWs *w, size_t cub_bytes)
     uint32_t **a32[] = {&w->umi_a, &w->umi_b, &w->idx_a, &w->idx_b, &w->s_bc, &w->s_gene, &w->s_umi,
                         &w->head_u, &w->head_g, &w->du_id, &w->grp_id, &w->du_first,
                         &w->grp_first, &w->du_rank_order, &w->du_rep, &w->rep_reads,
-                        &w->rep_flag, &w->rep_pos};
+                        &w->rep_flag, &w->rep_pos, &w->rep_u, &w->rep_c};
     for (auto p : a32) *p = (uint32_t *)take(n4);
     w->key_a = (uint64_t *)take(n8);
     w->key_b = (uint64_t *)take(n8);
@@ -123,11 +124,35 @@ __device__ __forceinline__ int hamming_2bit(uint32_t a, uint32_t b)
     return __popc(x);
 }
 
-// one warp per (barcode, gene) group
+// walk order of the distinct UMIs of every group: (reads desc, umi asc).  Distinct ids are
+// umi-ascending inside a group, so a STABLE sort by (group, ~reads) gives it for all groups at once.
+__global__ void k_order_keys(const uint32_t *du_first, const uint32_t *grp_id, const uint32_t *totals,
+                             uint64_t n, uint64_t *key, uint32_t *val)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = ~0ull;
+    if (i < totals[0]) {
+        uint32_t f = du_first[i];
+        k = ((uint64_t)grp_id[f] << 32) | (uint64_t)(0xFFFFFFFFu - (du_first[i + 1] - f));
+    }
+    key[i] = k;
+    val[i] = (uint32_t)i;
+}
+
+#define NR_UMI_LARGE 96      // groups with more distinct UMIs go to the block-wide kernel
+
+__device__ __forceinline__ bool umi_joins(uint32_t rep_umi, uint32_t rep_cnt, uint32_t u,
+                                          uint32_t cnt, int max_dist)
+{
+    return hamming_2bit(rep_umi, u) <= max_dist && rep_cnt + 1 >= 2 * cnt;
+}
+
+// one warp per small (barcode, gene) group: sequential walk, 32 representatives compared per step
 __global__ void __launch_bounds__(256)
-k_cluster(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ du_first,
-          const uint32_t *__restrict__ grp_first, const uint32_t *__restrict__ totals, int max_dist,
-          uint32_t *__restrict__ order, uint32_t *__restrict__ du_rep)
+k_cluster_small(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ du_first,
+                const uint32_t *__restrict__ grp_first, const uint32_t *__restrict__ totals,
+                int max_dist, uint32_t *__restrict__ order, uint32_t *__restrict__ du_rep)
 {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n_groups = totals[1];
@@ -139,18 +164,7 @@ k_cluster(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ du_fi
             for (uint32_t i = d0 + lane; i < d1; i += 32) du_rep[i] = i;
             continue;
         }
-        // walk order: rank = number of distinct UMIs that come first by (reads desc, umi asc);
-        // distinct ids are already umi-ascending inside the group
-        for (uint32_t i = d0 + lane; i < d1; i += 32) {
-            uint32_t ci = du_first[i + 1] - du_first[i];
-            uint32_t rank = 0;
-            for (uint32_t j = d0; j < d1; j++) {
-                uint32_t cj = du_first[j + 1] - du_first[j];
-                rank += (cj > ci) || (cj == ci && j < i);
-            }
-            order[d0 + rank] = i;
-        }
-        __syncwarp();
+        if (nd > NR_UMI_LARGE) continue;
         // representatives are kept compacted at the front of the walked prefix: order[d0..d0+nrep)
         // is overwritten in place (a walked position is never read again once passed)
         uint32_t nrep = 0;
@@ -165,8 +179,7 @@ k_cluster(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ du_fi
                 uint32_t e = 0;
                 if (q < nrep) {
                     e = order[d0 + q];
-                    uint32_t ce = du_first[e + 1] - du_first[e];
-                    ok = hamming_2bit(s_umi[du_first[e]], u) <= max_dist && ce + 1 >= 2 * cnt;
+                    ok = umi_joins(s_umi[du_first[e]], du_first[e + 1] - du_first[e], u, cnt, max_dist);
                 }
                 uint32_t mask = __ballot_sync(0xffffffffu, ok);
                 if (mask) found = __shfl_sync(0xffffffffu, e, __ffs(mask) - 1);
@@ -179,6 +192,85 @@ k_cluster(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ du_fi
                 du_rep[d] = found;
             }
             __syncwarp();
+        }
+    }
+}
+
+// one block per large group.  Same walk, 32 UMIs at a time: (1) all threads compare the chunk
+// with the representatives found so far (earliest qualifying one wins: atomicMin on its slot),
+// (2) one warp settles the chunk in walk order -- a UMI without an earlier representative may
+// still join a representative created earlier in the same chunk.
+__global__ void __launch_bounds__(256)
+k_cluster_large(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ du_first,
+                const uint32_t *__restrict__ grp_first, const uint32_t *__restrict__ totals,
+                int max_dist, uint32_t *__restrict__ order, uint32_t *__restrict__ du_rep,
+                uint32_t *__restrict__ rep_u, uint32_t *__restrict__ rep_c)
+{
+    __shared__ uint32_t c_d[32], c_u[32], c_c[32], c_best[32];
+    __shared__ uint32_t s_nrep;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_groups = totals[1];
+    if (max_dist <= 0) return;
+    for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const uint32_t d0 = grp_first[g], d1 = grp_first[g + 1];
+        const uint32_t nd = d1 - d0;
+        if (nd <= NR_UMI_LARGE) continue;
+        __syncthreads();
+        if (threadIdx.x == 0) s_nrep = 0;
+        for (uint32_t r0 = 0; r0 < nd; r0 += 32) {
+            __syncthreads();
+            const uint32_t in_chunk = min(32u, nd - r0);
+            if (threadIdx.x < 32) {
+                uint32_t d = 0, u = 0, c = 0;
+                if (lane < in_chunk) {
+                    d = order[d0 + r0 + lane];
+                    u = s_umi[du_first[d]];
+                    c = du_first[d + 1] - du_first[d];
+                }
+                c_d[lane] = d; c_u[lane] = u; c_c[lane] = c; c_best[lane] = 0xFFFFFFFFu;
+            }
+            __syncthreads();
+            const uint32_t nrep = s_nrep;
+            for (uint32_t q = threadIdx.x; q < nrep; q += blockDim.x) {
+                const uint32_t ru = rep_u[d0 + q], rc = rep_c[d0 + q];
+#pragma unroll 8
+                for (uint32_t k = 0; k < 32; k++)
+                    if (k < in_chunk && umi_joins(ru, rc, c_u[k], c_c[k], max_dist))
+                        atomicMin(&c_best[k], q);
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                const bool have = lane < in_chunk;
+                const uint32_t u = c_u[lane], c = c_c[lane], d = c_d[lane];
+                // in-chunk predecessors this UMI could join if they become representatives
+                uint32_t adj = 0;
+                for (uint32_t j = 0; j < in_chunk; j++)
+                    if (j < lane && umi_joins(c_u[j], c_c[j], u, c, max_dist)) adj |= 1u << j;
+                const uint32_t best = c_best[lane];
+                uint32_t R = 0;                      // chunk members that became representatives
+                uint32_t join = 0xFFFFFFFFu;         // in-chunk representative joined
+                for (uint32_t k = 0; k < in_chunk; k++) {
+                    bool is_rep = false;
+                    if (lane == k && have && best == 0xFFFFFFFFu) {
+                        uint32_t m = adj & R;
+                        if (m) join = (uint32_t)__ffs((int)m) - 1u;
+                        else is_rep = true;
+                    }
+                    R |= __ballot_sync(0xffffffffu, is_rep);
+                }
+                if (have) {
+                    if (best != 0xFFFFFFFFu) {
+                        du_rep[d] = order[d0 + best];
+                    } else if (join != 0xFFFFFFFFu) {
+                        du_rep[d] = c_d[join];
+                    } else {
+                        const uint32_t pos = nrep + (uint32_t)__popc(R & ((1u << lane) - 1u));
+                        du_rep[d] = d;
+                        order[d0 + pos] = d; rep_u[d0 + pos] = u; rep_c[d0 + pos] = c;
+                    }
+                }
+                if (lane == 0) s_nrep = nrep + (uint32_t)__popc(R);
+            }
         }
     }
 }
@@ -289,8 +381,19 @@ extern "C" int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_ge
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    k_cluster<<<sms * 8, 256, 0, st>>>(w.s_umi, w.du_first, w.grp_first, w.totals, max_dist,
-                                       w.du_rank_order, w.du_rep);
+    if (max_dist > 0) {
+        // walk order for every group at once (key_a/key_b and umi_a are free again here)
+        k_order_keys<<<nb, T, 0, st>>>(w.du_first, w.grp_id, w.totals, n, w.key_a, w.umi_a);
+        tb = w.cub_bytes;
+        NR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.key_a, w.key_b, w.umi_a,
+                                                      w.du_rank_order, N, 0, 64, st));
+    }
+    k_cluster_small<<<sms * 8, 256, 0, st>>>(w.s_umi, w.du_first, w.grp_first, w.totals, max_dist,
+                                             w.du_rank_order, w.du_rep);
+    if (max_dist > 0)
+        k_cluster_large<<<sms * 4, 256, 0, st>>>(w.s_umi, w.du_first, w.grp_first, w.totals,
+                                                 max_dist, w.du_rank_order, w.du_rep, w.rep_u,
+                                                 w.rep_c);
     NR_CHECK_CUDA(cudaMemsetAsync(w.rep_reads, 0, (size_t)(n + 1) * 4, st));
     k_rep_reads<<<sms * 8, 256, 0, st>>>(w.du_first, w.du_rep, w.totals, w.rep_reads, w.rep_flag);
     // rep_flag is defined for the first n_distinct entries only; the scan also runs over the
