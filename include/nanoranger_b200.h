@@ -159,6 +159,23 @@ int nr_umi_partition_device(const uint32_t *d_bc, const uint32_t *d_gene, const 
 int nr_umi_unzip_device(const void *d_records, uint64_t n, uint32_t *d_bc, uint32_t *d_gene,
                         uint32_t *d_umi, uint32_t *d_src, void *stream);
 
+/* ---- adapter-motif search (candidate extraction) ---------------------------------------------
+ * Replaces edlib.align(const, window, "HW", "locations", k[, ad_seq]) in the reference's
+ * extractors (utils.py:134, 271, 345, 437, 1051, 1367): infix unit-cost edit distance of
+ * `pattern` (m <= 64) against every window.  text/offsets: concatenated ASCII windows,
+ * n + 1 offsets.  wildcard_n != 0: N equals A/C/G/T on either side (utils.py:15).  Per window:
+ *   ed[i]        edit distance, -1 if > k (requires k < m)
+ *   first[2i..]  (start, end) of the first optimal end location, end inclusive as in edlib;
+ *                start = smallest start of an optimal alignment ending there
+ *   last[2i..]   the same for the last optimal end location (`ed["locations"][-1]`)
+ *   nloc[i]      number of optimal end locations */
+int nr_hw_search_device(const uint8_t *d_text, const uint64_t *d_offsets, uint64_t n,
+                        const char *pattern, int m, int k, int wildcard_n, int8_t *d_ed,
+                        int32_t *d_first, int32_t *d_last, int32_t *d_nloc, void *stream);
+int nr_hw_search_host(const char *text, const uint64_t *offsets, uint64_t n, const char *pattern,
+                      int m, int k, int wildcard_n, int8_t *ed, int32_t *first, int32_t *last,
+                      int32_t *nloc, int device);
+
 /* ---- measurement support -------------------------------------------------------------------
  * INT-pipe roofline denominator: runs a dependent LOP3/IADD3 chain on
  * every SM for `iters` iterations and returns executed integer thread-ops per second. */

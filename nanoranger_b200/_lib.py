@@ -35,7 +35,7 @@ SYMBOLS = (
     "nr_host_free", "nr_umi_collapse_device", "nr_umi_workspace_bytes", "nr_int_peak",
     "nr_int_peak_dual", "nr_match_device_counted", "nr_match_counters",
     "nr_umi_records_device", "nr_umi_records_workspace_bytes", "nr_umi_partition_device",
-    "nr_umi_unzip_device",
+    "nr_umi_unzip_device", "nr_hw_search_device", "nr_hw_search_host",
 )
 
 _lib = None
@@ -91,6 +91,10 @@ def lib() -> C.CDLL:
     L.nr_umi_partition_device.restype = i32
     L.nr_umi_unzip_device.argtypes = [vp, u64, vp, vp, vp, vp, vp]
     L.nr_umi_unzip_device.restype = i32
+    L.nr_hw_search_device.argtypes = [vp, vp, u64, C.c_char_p, i32, i32, i32, vp, vp, vp, vp, vp]
+    L.nr_hw_search_device.restype = i32
+    L.nr_hw_search_host.argtypes = [vp, vp, u64, C.c_char_p, i32, i32, i32, vp, vp, vp, vp, i32]
+    L.nr_hw_search_host.restype = i32
     L.nr_int_peak.argtypes = [i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.nr_int_peak.restype = i32
     L.nr_int_peak_dual.argtypes = [i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]

@@ -402,3 +402,81 @@ int64_t nr_oracle_umi_cluster(const uint32_t *bc, const uint32_t *gene, const ui
     free(r);
     return clusters;
 }
+
+/* ---- adapter-motif search (candidate extraction) ---------------------
+ * Restates what the reference asks of edlib (third-party, pinned edlib==1.3.9 in
+ * /root/reference/requirements.txt, not vendored; PARITY UNPINNED -- edlib is not installed here):
+ *   edlib.align(query, target, "HW", "locations", k[, additionalEqualities])
+ * at /root/reference/utils.py:134, 271, 345, 437, 1051, 1367.  Published definition (Sosic &
+ * Sikic, Bioinformatics 2017; edlib.h): HW = infix mode, unit-cost edit distance of the whole
+ * query against the best substring of the target; editDistance = -1 when it exceeds k; end
+ * locations = all target positions (ascending) at which an optimal alignment ends; the start
+ * location given for an end location is the smallest start of an optimal alignment ending there
+ * (edlib.cpp: reversed SHW alignment, "taking last location as start").  With the reference's
+ * ad_seq (utils.py:15) N equals A, C, G, T on either side; otherwise bytes compare exactly.
+ * Plain O(m*n) DP, no bit tricks.  out: ed, nloc, first (start,end), last (start,end). */
+static int hw_equal(uint8_t p, uint8_t c, int wild)
+{
+    if (p == c) return 1;
+    if (!wild) return 0;
+    int pb = p == 'A' || p == 'C' || p == 'G' || p == 'T';
+    int cb = c == 'A' || c == 'C' || c == 'G' || c == 'T';
+    return (p == 'N' && cb) || (c == 'N' && pb);
+}
+
+static int hw_smallest_start(const uint8_t *q, int m, const uint8_t *t, int e, int best, int wild)
+{
+    /* D[i][r]: first i chars of reversed q vs first r chars of t[e], t[e-1], ...; whole query,
+     * prefix of the reversed target (SHW): D[0][r] = r */
+    int lim = e + 1 < m + best ? e + 1 : m + best;
+    int *prev = (int *)malloc(sizeof(int) * (size_t)(m + 1));
+    int *cur = (int *)malloc(sizeof(int) * (size_t)(m + 1));
+    for (int i = 0; i <= m; i++) prev[i] = i;
+    int far = 0;
+    for (int r = 1; r <= lim; r++) {
+        cur[0] = r;
+        uint8_t c = t[e - (r - 1)];
+        for (int i = 1; i <= m; i++) {
+            int s = prev[i - 1] + (hw_equal(q[m - i], c, wild) ? 0 : 1);
+            int a = prev[i] + 1, b = cur[i - 1] + 1;
+            if (a < s) s = a;
+            if (b < s) s = b;
+            cur[i] = s;
+        }
+        if (cur[m] == best) far = r - 1;
+        int *tmp = prev; prev = cur; cur = tmp;
+    }
+    free(prev); free(cur);
+    return e - far;
+}
+
+int nr_oracle_hw_search(const uint8_t *q, int m, const uint8_t *t, int n, int k, int wild,
+                        int *out6)
+{
+    int *col = (int *)malloc(sizeof(int) * (size_t)(m + 1));
+    for (int i = 0; i <= m; i++) col[i] = i;
+    int best = m + 1, first = -1, last = -1, nloc = 0;
+    for (int j = 0; j < n; j++) {
+        int diag = col[0];              /* D[0][j] = 0: free start in the target */
+        col[0] = 0;
+        for (int i = 1; i <= m; i++) {
+            int s = diag + (hw_equal(q[i - 1], t[j], wild) ? 0 : 1);
+            int a = col[i] + 1, b = col[i - 1] + 1;
+            diag = col[i];
+            if (a < s) s = a;
+            if (b < s) s = b;
+            col[i] = s;
+        }
+        if (col[m] < best) { best = col[m]; first = last = j; nloc = 1; }
+        else if (col[m] == best) { last = j; nloc++; }
+    }
+    free(col);
+    if (n == 0 || best > k) {
+        out6[0] = -1; out6[1] = 0; out6[2] = out6[3] = out6[4] = out6[5] = -1;
+        return 0;
+    }
+    out6[0] = best; out6[1] = nloc;
+    out6[2] = hw_smallest_start(q, m, t, first, best, wild); out6[3] = first;
+    out6[4] = hw_smallest_start(q, m, t, last, best, wild); out6[5] = last;
+    return 0;
+}

@@ -54,6 +54,9 @@ def lib():
         L.nr_oracle_scores.restype = C.c_int
         L.nr_oracle_umi_cluster.argtypes = [u32p, u32p, u32p, C.c_int64, C.c_int, u32p]
         L.nr_oracle_umi_cluster.restype = C.c_int64
+        L.nr_oracle_hw_search.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int,
+                                          C.POINTER(C.c_int)]
+        L.nr_oracle_hw_search.restype = C.c_int
         _lib = L
     return _lib
 
@@ -168,3 +171,47 @@ def as_padded_numpy(q: str, ref: str) -> int:
 
 def revcomp(s: str) -> str:
     return s.translate(str.maketrans("ACGTNacgtn", "TGCANtgcan"))[::-1]
+
+
+def hw_search(query: str, target: str, k: int, wildcard: bool = True) -> dict:
+    """What the reference asks of edlib.align(query, target, "HW", "locations", k[, ad_seq])
+    (utils.py:134 ...): {"editDistance": d or -1, "locations": [first (start, end), last (start,
+    end)], "n_locations": count}; end inclusive, as edlib reports it."""
+    out = (C.c_int * 6)()
+    lib().nr_oracle_hw_search(query.encode(), len(query), target.encode(), len(target), k,
+                              1 if wildcard else 0, out)
+    return {"editDistance": out[0], "n_locations": out[1], "first": (out[2], out[3]),
+            "last": (out[4], out[5])}
+
+
+def hw_search_numpy(query: str, target: str, k: int, wildcard: bool = True) -> dict:
+    """Independent twin of nr_oracle_hw_search: full DP matrix in numpy, every optimal start
+    enumerated by brute force over substrings (small inputs only)."""
+    def eq(p, c):
+        if p == c:
+            return True
+        return wildcard and ((p == "N" and c in "ACGT") or (c == "N" and p in "ACGT"))
+
+    def dist(a, b):          # global unit-cost edit distance
+        D = np.arange(len(b) + 1)
+        for i in range(1, len(a) + 1):
+            prev, D = D, np.empty(len(b) + 1, np.int64)
+            D[0] = i
+            for j in range(1, len(b) + 1):
+                D[j] = min(prev[j - 1] + (0 if eq(a[i - 1], b[j - 1]) else 1), prev[j] + 1, D[j - 1] + 1)
+        return int(D[-1])
+
+    n = len(target)
+    best, ends = None, {}
+    for e in range(n):
+        for s in range(e + 2):                       # s == e + 1: empty substring ending at e
+            d = dist(query, target[s:e + 1])
+            if best is None or d < best:
+                best, ends = d, {}
+            if d == best:
+                ends.setdefault(e, s)                 # smallest start first
+    if best is None or best > k:
+        return {"editDistance": -1, "n_locations": 0, "first": (-1, -1), "last": (-1, -1)}
+    es = sorted(ends)
+    return {"editDistance": best, "n_locations": len(es), "first": (ends[es[0]], es[0]),
+            "last": (ends[es[-1]], es[-1])}
