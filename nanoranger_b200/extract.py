@@ -254,3 +254,144 @@ def decon_3pXCR_slideseq(sample, outdir, device: int = 0):
     _gz_write(f"{outdir}/{sample}_BCUMI.fasta", fa)
     _gz_write(f"{outdir}/{sample}_polyA.fasta", pa_out)
     return len(fa)
+
+
+# ---- 3' 10x ------------------------------------------------------------------------------------------
+
+def decon_3p10XTCR(sample, outdir, device: int = 0):
+    """utils.py:313-373: 6A + 28N + TruSeq motif (k = 5, N wildcard, FIRST location) in the 150 nt
+    after the alignment; `{sample}_VDJ.fastq.gz`, `{sample}_BCUMI.fasta.gz`, `{sample}_eds.csv`."""
+    from .utils import sort_cnt
+    const = 6 * "A" + 28 * "N" + "AGATCGGAAGAGCGTCGTGT"
+    lclip, r_search, rclip = 350, 150, 100
+    recs = read_alignments(f"{outdir}/{sample}_trns.sam")
+    wins = []
+    for r in recs:
+        qe = r.query_alignment_end
+        wins.append(r.seq[qe: qe + r_search] if r.rlen - qe > r_search else r.seq[qe:])
+    res = hw_search(wins, const, 5, True, device)
+    fq, fa, eds = [], [], []
+    for i, r in enumerate(recs):
+        qs = r.query_alignment_start
+        sub_e = qs + rclip
+        sub_s = qs - lclip if qs > lclip else 0
+        sub_seq = r.seq[sub_s:sub_e]
+        dist = int(res["ed"][i])
+        eds.append(dist)
+        name = (f"{r.qname[-10:]}_q{r.qlen}_d{dist}_s{sub_s}_e{sub_e}_f{r.flag}_"
+                f"{r.reference_name.split('-')[0]}")
+        if -1 < dist < 6 and len(sub_seq) > 100 and r.qlen > 100:
+            fq.append(f"@{name}\n{sub_seq}\n+\n{r.qual[sub_s:sub_e]}\n")
+            a, b = (int(x) for x in res["first"][i])
+            fa.append(f">{name}\n{rev(wins[i][a:b])[14:]}\n")
+    _gz_write(f"{outdir}/{sample}_VDJ.fastq", fq)
+    _gz_write(f"{outdir}/{sample}_BCUMI.fasta", fa)
+    sort_cnt(eds).to_csv(f"{outdir}/{sample}_eds.csv")
+    return len(fa)
+
+
+def _stepped_first_hit(tails, const, k, accept_below, device, step=200, overlap=70):
+    """windows end_qu[step*i : step*(i+1)+overlap] for i = 0..len//step of every tail (None:
+    record not searched); -> per tail (i, start, end, ed) of the first window with
+    editDistance < accept_below, or None (utils.py:1045-1083, 1359-1383)."""
+    wins, owner = [], []
+    for ti, t in enumerate(tails):
+        if t is None:
+            continue
+        for i in range(int(len(t) / step) + 1):
+            wins.append(t[step * i: step * (i + 1) + overlap])
+            owner.append((ti, i))
+    res = hw_search(wins, const, k, False, device)
+    hit = [None] * len(tails)
+    for w, (ti, i) in enumerate(owner):
+        d = int(res["ed"][w])
+        if hit[ti] is None and -1 < d < accept_below:
+            hit[ti] = (i, int(res["first"][w][0]), int(res["first"][w][1]), d)
+    return hit
+
+
+def decon_3p10XTCR_nuc(sample, outdir, device: int = 0):
+    """utils.py:982-1113: TruSeq adapter (k = 2, FIRST location) in 270-nt windows every 200 nt of
+    the 2000 nt after the alignment; candidate = rev(end_qu[start-35 : end-12]), kept if > 30 nt."""
+    const = "AGATCGGAAGAGCGTCGTGT"
+    r_search, rclip = 2000, 100
+    recs = read_alignments(f"{outdir}/{sample}_trns.sam")
+    tails, fq, names = [], [], []
+    for r in recs:
+        qs, qe = r.query_alignment_start, r.query_alignment_end
+        end_qu = r.seq[qe: qe + r_search] if r.rlen - qe > r_search else r.seq[qe:]
+        sub_e = qe + rclip if r.rlen - qe > rclip else r.rlen
+        sub_seq = r.seq[qs:sub_e]
+        name = f"{r.qname}_{sample}_{qs}_{sub_e}_{r.flag}_{r.reference_name.split('-')[0]}"
+        names.append(name)
+        if len(sub_seq) > 100:
+            fq.append(f"@{name}\n{sub_seq}\n+\n{r.qual[qs:sub_e]}\n")
+            tails.append(end_qu)
+        else:
+            tails.append(None)
+    hits = _stepped_first_hit(tails, const, 2, 3, device)
+    fa, short_bc = [], 0
+    for ti, h in enumerate(hits):
+        if h is None:
+            continue
+        i, a, b, _ = h
+        start, end = a + 200 * i, b + 200 * i
+        bcumi = rev(tails[ti][start - 35: end - 12])
+        if len(bcumi) > 30:
+            fa.append(f">{names[ti]}\n{bcumi}\n")
+        else:
+            short_bc += 1
+    print(short_bc)
+    _gz_write(f"{outdir}/{sample}_VDJ.fastq", fq)
+    _gz_write(f"{outdir}/{sample}_BCUMI.fasta", fa)
+    return len(fa)
+
+
+def decon_3p10XGEX(sample, outdir, device: int = 0):
+    """utils.py:1283-1410: TruSeq adapter (k = 3, FIRST location) in stepped windows of
+    seq[qend-70 : qend+700]; candidate = rev(end_qu[start-32 : start+3]) (35 nt), raw barcode
+    counts to `{sample}_bc_count.json`."""
+    import json
+    import os
+    bc_count_json = f"{outdir}/{sample}_bc_count.json"
+    if os.path.isfile(bc_count_json):
+        print(bc_count_json, " exists, skip")
+        return
+    const = "AGATCGGAAGAGCGTCGTGT"
+    r_search, rclip, lclip = 700, 1, 1
+    recs = read_alignments(f"{outdir}/{sample}_trns.sam")
+    tails, fq, names = [], [], []
+    for r in recs:
+        qs, qe = r.query_alignment_start, r.query_alignment_end
+        end_qu = r.seq[qe - 70: qe + r_search] if r.rlen - qe > r_search else r.seq[qe - 70:]
+        sub_e = qe + rclip if r.rlen - qe > rclip else r.rlen
+        sub_s = 0 if qs < lclip else qs - lclip
+        sub_seq = r.seq[sub_s:sub_e]
+        qsm, qem = _mod_coords(r)
+        name = f"{r.qname}_{qsm}_{qem}_{r.flag}_{r.reference_name}"
+        names.append(name)
+        if len(sub_seq) > 50:
+            fq.append(f"@{name}\n{sub_seq}\n+\n{r.qual[sub_s:sub_e]}\n")
+            tails.append(end_qu)
+        else:
+            tails.append(None)
+    hits = _stepped_first_hit(tails, const, 3, 4, device)
+    fa, short_bc, counts = [], 0, {}
+    for ti, h in enumerate(hits):
+        if h is None:
+            continue
+        i, a, _, _ = h
+        start = a + 200 * i
+        bcumi = rev(tails[ti][start - 16 - 12 - 4: start + 3])
+        raw = bcumi[3:3 + 16]
+        counts[raw] = counts.get(raw, 0) + 1
+        if len(bcumi) > 30:
+            fa.append(f">{names[ti]}\n{bcumi}\n")
+        else:
+            short_bc += 1
+    print("number of short BCUMIs = ", short_bc)
+    _gz_write(f"{outdir}/{sample}_deconcat.fastq", fq)
+    _gz_write(f"{outdir}/{sample}_BCUMI.fasta", fa)
+    with open(bc_count_json, "w") as f:
+        json.dump(counts, f)
+    return len(fa)

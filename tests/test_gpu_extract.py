@@ -199,3 +199,90 @@ def test_decon_slideseq_files(cuda_device, oracle, tmp_path):
                     break
     assert gzip.open(tmp_path / "x_BCUMI.fasta.gz", "rt").read() == "".join(exp)
     assert n == len(exp) and n > 200
+
+
+def _tail_sam(path, rng, n, adapter, before_len):
+    """records whose 3' soft clip holds [polyA][before_len random nt][adapter][junk], sometimes
+    far downstream (second stepped window) or absent."""
+    lines = ["@HD\tVN:1.6\n", "@SQ\tSN:TRBV7-9-201|ENST9.1_700\tLN:700\n"]
+    for i in range(n):
+        pre = _rs(rng, int(rng.integers(0, 30)))
+        body = _rs(rng, int(rng.integers(30, 400)))
+        gap = _rs(rng, int(rng.choice([0, 5, 150, 260])))
+        ad = _mutate(rng, adapter, int(rng.integers(0, 4))) if rng.random() > 0.1 else ""
+        tail = "A" * int(rng.integers(0, 25)) + gap + _rs(rng, before_len) + ad + _rs(rng, int(rng.integers(0, 50)))
+        seq = pre + body + tail
+        cigar = (f"{len(pre)}S" if pre else "") + f"{len(body)}=" + (f"{len(tail)}S" if tail else "")
+        flag = [0, 16, 2048, 2064][i % 4]
+        lines.append(f"m64012_{i}/ccs\t{flag}\tTRBV7-9-201|ENST9.1_700\t3\t60\t{cigar}\t*\t0\t0\t{seq}\t{'F' * len(seq)}\tAS:i:50\n")
+    with open(path, "w") as f:
+        f.writelines(lines)
+
+
+def test_decon_3p10XGEX_files(cuda_device, oracle, tmp_path):
+    import json
+    from nanoranger_b200 import extract
+    rng = np.random.default_rng(50)
+    ad = "AGATCGGAAGAGCGTCGTGT"
+    _tail_sam(tmp_path / "p_trns.sam", rng, 600, ad, 32)
+    n = extract.decon_3p10XGEX("p", str(tmp_path))
+    fa, counts = [], {}
+    for r in extract.read_alignments(str(tmp_path / "p_trns.sam")):        # utils.py:1313-1383
+        qs, qe = r.query_alignment_start, r.query_alignment_end
+        end_qu = r.seq[qe - 70: qe + 700] if r.rlen - qe > 700 else r.seq[qe - 70:]
+        sub_e = qe + 1 if r.rlen - qe > 1 else r.rlen
+        sub_s = 0 if qs < 1 else qs - 1
+        qsm, qem = (r.rlen - qe, r.rlen - qs) if r.flag in (16, 2064) else (qs, qe)
+        if len(r.seq[sub_s:sub_e]) > 50:
+            for i in range(int(len(end_qu) / 200) + 1):
+                ed = oracle.hw_search(ad, end_qu[200 * i: 200 * (i + 1) + 70], 3, False)
+                if -1 < ed["editDistance"] < 4:
+                    start = ed["first"][0] + 200 * i
+                    bcumi = extract.rev(end_qu[start - 32: start + 3])
+                    counts[bcumi[3:19]] = counts.get(bcumi[3:19], 0) + 1
+                    if len(bcumi) > 30:
+                        fa.append(f">{r.qname}_{qsm}_{qem}_{r.flag}_{r.reference_name}\n{bcumi}\n")
+                    break
+    assert gzip.open(tmp_path / "p_BCUMI.fasta.gz", "rt").read() == "".join(fa)
+    assert json.load(open(tmp_path / "p_bc_count.json")) == counts
+    assert n == len(fa) and n > 300
+    assert extract.decon_3p10XGEX("p", str(tmp_path)) is None              # "exists, skip"
+
+
+def test_decon_3p10XTCR_variants_files(cuda_device, oracle, tmp_path):
+    from nanoranger_b200 import extract
+    rng = np.random.default_rng(51)
+    ad = "AGATCGGAAGAGCGTCGTGT"
+    _tail_sam(tmp_path / "n_trns.sam", rng, 500, ad, 35)
+    n = extract.decon_3p10XTCR_nuc("n", str(tmp_path))
+    fa = []
+    for r in extract.read_alignments(str(tmp_path / "n_trns.sam")):        # utils.py:998-1083
+        qs, qe = r.query_alignment_start, r.query_alignment_end
+        end_qu = r.seq[qe: qe + 2000] if r.rlen - qe > 2000 else r.seq[qe:]
+        sub_e = qe + 100 if r.rlen - qe > 100 else r.rlen
+        if len(r.seq[qs:sub_e]) > 100:
+            for i in range(int(len(end_qu) / 200) + 1):
+                ed = oracle.hw_search(ad, end_qu[200 * i: 200 * (i + 1) + 70], 2, False)
+                if -1 < ed["editDistance"] < 3:
+                    start, end = ed["first"][0] + 200 * i, ed["first"][1] + 200 * i
+                    bcumi = extract.rev(end_qu[start - 35: end - 12])
+                    if len(bcumi) > 30:
+                        fa.append(f">{r.qname}_n_{qs}_{sub_e}_{r.flag}_{r.reference_name.split('-')[0]}\n{bcumi}\n")
+                    break
+    assert gzip.open(tmp_path / "n_BCUMI.fasta.gz", "rt").read() == "".join(fa)
+    assert n == len(fa) and n > 150
+    # legacy 3p10XTCR: one window, wildcard motif
+    const = 6 * "A" + 28 * "N" + ad
+    _tail_sam(tmp_path / "t_trns.sam", rng, 300, ad, 40)
+    extract.decon_3p10XTCR("t", str(tmp_path))
+    fa = []
+    for r in extract.read_alignments(str(tmp_path / "t_trns.sam")):        # utils.py:316-357
+        qs, qe = r.query_alignment_start, r.query_alignment_end
+        end_qu = r.seq[qe: qe + 150] if r.rlen - qe > 150 else r.seq[qe:]
+        sub_s = qs - 350 if qs > 350 else 0
+        ed = oracle.hw_search(const, end_qu, 5, True)
+        d = ed["editDistance"]
+        if -1 < d < 6 and len(r.seq[sub_s:qs + 100]) > 100 and r.qlen > 100:
+            nm = f"{r.qname[-10:]}_q{r.qlen}_d{d}_s{sub_s}_e{qs + 100}_f{r.flag}_{r.reference_name.split('-')[0]}"
+            fa.append(f">{nm}\n{extract.rev(end_qu[ed['first'][0]:ed['first'][1]])[14:]}\n")
+    assert gzip.open(tmp_path / "t_BCUMI.fasta.gz", "rt").read() == "".join(fa)
