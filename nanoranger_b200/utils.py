@@ -14,9 +14,8 @@ in `outdir`:
   sort_cnt                                                 utils.py:36-41
 
 The compute (matching, UMI dedup) runs in the CUDA library; there is no CPU fallback.
-Out of scope this round: plots (matplotlib absent), BAM tagging of
-`{sample}_genome.bam` (needs a BAM reader/writer), MiXCR clone tables when their inputs are
-missing -- those steps are skipped with a message, never faked.
+Out of scope (SURVEY.md section 8f / DESIGN.md section 9): plots (matplotlib absent); MiXCR clone
+tables are merged when their input files exist and skipped with a message otherwise -- never faked.
 """
 from __future__ import annotations
 
@@ -298,8 +297,14 @@ def process_matching_5p10X(sample, outdir, device: int = 0):
     with open(f"{outdir}/{sample}_read_tags.tsv", "w") as f:
         for n, (b, u, t) in table.items():
             f.write(f"{n}\t{b}\t{u}\t{t}\n")
+    # utils.py:801-827: tag the genome alignments of the assigned reads, count their transcripts
     if os.path.isfile(f"{outdir}/{sample}_genome.bam"):
-        _skip("CB/UB/XT tagging of _genome.bam (needs a BAM reader/writer; tags are in _read_tags.tsv)")
+        from . import bamio
+        all_trns = bamio.tag_genome_bam(f"{outdir}/{sample}_genome.bam",
+                                        f"{outdir}/{sample}_genome_tagged.bam", table)
+        sort_cnt(all_trns).to_csv(f"{outdir}/{sample}_trns_ct.csv", index=None)
+    else:
+        _skip(f"{outdir}/{sample}_genome.bam missing, CB/UB/XT tagging")
     return table
 
 

@@ -107,7 +107,22 @@ def test_pipeline_5p10X_tags(cuda_device, tmp_path):
     np.savez_compressed(f"{out}/nr_whitelist.npz", cores=wl_a, names=np.array(wl_names),
                         pad_l=30, pad_r=40)
     utils.barcode_align(os.path.join(G, "mtdna1026.fa.gz"), out, f"{out}/s_matching", 8)
+    # a genome BAM of the same reads (every third one secondary: must not be tagged), plus a stranger
+    from nanoranger_b200 import bamio
+    recs = [bamio.make_record(n, [0, 16, 256][i % 3], 0, 100 + i, 60, "20M", "ACGT" * 5)
+            for i, n in enumerate(names)]
+    recs.append(bamio.make_record("not_a_candidate", 0, 0, 5, 60, "20M", "ACGT" * 5))
+    bamio.write_bam(f"{out}/s_genome.bam", "@HD\tVN:1.6\n@SQ\tSN:chrM\tLN:16569\n", [("chrM", 16569)], recs)
     table = utils.process_matching_5p10X("s", out)
     _, triples = _expected_from_oracle(names, seqs, off, ref, wl_names, 14, 10, False)
     exp = {n: (b, u, "lite") for n, b, u in triples}
     assert table == exp and len(table) > 3000
+    # utils.py:801-827: tagged BAM holds the assigned reads with flag < 20, CB/UB/XT set
+    tagged = list(bamio.BamReader(f"{out}/s_genome_tagged.bam"))
+    want = [n for i, n in enumerate(names) if n in exp and [0, 16, 256][i % 3] < 20]
+    assert [bamio.rec_qname(r) for r in tagged] == want
+    for r in tagged[:200]:
+        b, u, t = exp[bamio.rec_qname(r)]
+        assert (bamio.get_tag(r, "CB"), bamio.get_tag(r, "UB"), bamio.get_tag(r, "XT")) == (b, u, t)
+    ct = pd.read_csv(f"{out}/s_trns_ct.csv")
+    assert ct.iloc[0, 0] == "lite" and int(ct.iloc[0, 1]) == len(want)
