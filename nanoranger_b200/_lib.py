@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnanoranger_b200.so")
+LIB_PATH = os.environ.get("NANORANGER_B200_LIB") or os.path.join(_HERE, "libnanoranger_b200.so")
 
 NR_MAX_QUERY = 64
 NR_MAX_CORE = 32

@@ -29,6 +29,9 @@
 
 #define NR_FILTER_MIN_LEN 24
 #define NR_FWARPS 8                        // warps per block
+#ifndef NR_FBLOCKS
+#define NR_FBLOCKS 4                       // resident blocks per SM the register budget is set for
+#endif
 #define NR_QCAP 480                        // queue slots per warp
 
 struct nr_filter_params {
@@ -55,6 +58,32 @@ struct nr_filter_params {
 
 namespace {
 
+// probe table as packed words in shared memory: the hits a warp expands carry lane-varying probe
+// numbers, and a lane-varying index into __constant__ memory is serialised by the address
+// divergence unit (ncu: pipe_adu at 52 % of peak with the table in constant memory)
+__device__ __forceinline__ uint32_t probe_pack(const nr_probe_t &t)
+{
+    return (uint32_t)t.drop | ((uint32_t)t.o0 << 2) | ((uint32_t)t.o1 << 6) | ((uint32_t)t.o2 << 10) |
+           ((uint32_t)(t.var + 1) << 14) | ((uint32_t)t.del << 16);
+}
+__device__ __forceinline__ nr_probe_t probe_unpack(uint32_t w)
+{
+    nr_probe_t t;
+    t.drop = (int8_t)(w & 3u); t.o0 = (int8_t)((w >> 2) & 15u); t.o1 = (int8_t)((w >> 6) & 15u);
+    t.o2 = (int8_t)((w >> 10) & 15u); t.var = (int8_t)((int)((w >> 14) & 3u) - 1);
+    t.del = (int8_t)((w >> 16) & 3u);
+    return t;
+}
+
+// the four index tables' base pointers, copied to shared memory for the same reason (the
+// dropped quarter of a queued hit is lane-varying; kernel parameters live in constant memory)
+struct Tables {
+    const uint32_t *bits[4];
+    const uint32_t *rank[4];
+    const uint2 *ents[4];
+    const uint32_t *kstart[4];
+};
+
 struct WarpSmem {
     uint4 tile[32];                  // packed records of the warp's 32 candidates
     uint32_t rdp[2][NR_RDP_WORDS];   // candidate in flight: forward / reverse complement, padded
@@ -79,7 +108,8 @@ __device__ __forceinline__ int merge_umi(int a, int b) { return a < 0 ? b : (b <
 // Take up to 32 queued bitmap hits, expand each into the index rows that share its key
 // (kstart gives first row and count), and verify the rows 32 at a time, one row per lane.
 template <bool COUNT>
-__device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, Acc &acc, int m)
+__device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, Acc &acc, int m,
+                                      const uint32_t *s_probes, const Tables &T4)
 {
     const uint32_t lane = nr_lane();
     const int cnt = min(32, acc.qn);
@@ -90,17 +120,17 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, A
     __syncwarp();
     // the hit's key again (cheap, and now 32 hits wide), its rank among the distinct keys of the
     // table, and through kstart its rows; probes reaching outside the read nominate nothing
-    const nr_probe_t t = c_probes[(item >> 16) & 63u];
+    const nr_probe_t t = probe_unpack(s_probes[(item >> 16) & 63u]);
     const int h_strand = (int)((item >> 24) & 1u);
     const int h_p = (int)(item >> 25) - 16;
     const uint32_t d = (uint32_t)t.drop;
     uint32_t start = 0, rows = 0;
     if (have && h_p + nr_probe_first(t) >= 0 && h_p + nr_probe_end(t) <= m) {
         const uint32_t key = nr_probe_key(nr_window64(sm.rdp[h_strand], h_p), t);
-        const uint32_t w = __ldg(P.bits[d] + (key >> 5));
-        const uint32_t kr = __ldg(P.rank[d] + (key >> 5)) +
+        const uint32_t w = __ldg(T4.bits[d] + (key >> 5));
+        const uint32_t kr = __ldg(T4.rank[d] + (key >> 5)) +
                             (uint32_t)__popc(w & ((1u << (key & 31u)) - 1u));
-        const uint32_t *ks = P.kstart[d] + kr;
+        const uint32_t *ks = T4.kstart[d] + kr;
         start = __ldg(ks);
         rows = __ldg(ks + 1) - start;
         if (COUNT) acc.c_hits++;
@@ -131,11 +161,11 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, A
         int cost = 3, u = -1;
         uint32_t k = 0;
         if (active) {
-            const nr_probe_t ot = c_probes[(o_item >> 16) & 63u];
+            const nr_probe_t ot = probe_unpack(s_probes[(o_item >> 16) & 63u]);
             const uint32_t od = (uint32_t)ot.drop;
             const int strand = (int)((o_item >> 24) & 1u);
             const int p = (int)(o_item >> 25) - 16;
-            const uint2 e = __ldg(P.ents[od] + o_start + (g - o_excl));
+            const uint2 e = __ldg(T4.ents[od] + o_start + (g - o_excl));
             cost = nr_verify16(sm.rdp[strand], m, e.y, P.padL, P.padR, p, ot, &u);
             k = (e.x << 1) | (uint32_t)strand;
             if (COUNT) { acc.c_ver++; acc.c_pass += cost < 3; }
@@ -163,31 +193,92 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, A
     }
 }
 
-// one probe of a slot: key from the window, one 4 B read of the key bitmap, hit bit into `mask`
-template <int T>
+// Probes that differ only in their FIRST kept quarter (a plain probe and the three "5-mer minus
+// one base" variants of that quarter) address the same 32-byte sector of the bitmap: the key's low
+// 8 bits are that quarter.  The plain probe of such a family brings the whole sector with one
+// 256-bit load and all four members test their bit in registers; the variants issue no load.
+// (ncu: the kernel is L1TEX-bound -- l1tex throughput 73 %, ALU pipe 58 % -- and the tag stage
+// works per sector, so this removes 9 of the 34 lookups of a slot.)
+__host__ __device__ constexpr int probe_family(int T)   // first variant of the family T heads, or -1
+{
+    return T == 9 ? 16 : (T == 15 ? 19 : (T == 4 ? 22 : -1));
+}
+__host__ __device__ constexpr bool probe_in_family(int T) { return T >= 16 && T <= 24; }
+
+static_assert(NR_PROBES[9].drop == NR_PROBES[16].drop && NR_PROBES[9].o1 == NR_PROBES[16].o1 &&
+              NR_PROBES[9].o2 == NR_PROBES[18].o2 && NR_PROBES[16].var == 0 &&
+              NR_PROBES[15].drop == NR_PROBES[19].drop && NR_PROBES[15].o1 == NR_PROBES[21].o1 &&
+              NR_PROBES[15].o2 == NR_PROBES[19].o2 && NR_PROBES[19].var == 0 &&
+              NR_PROBES[4].drop == NR_PROBES[22].drop && NR_PROBES[4].o1 == NR_PROBES[24].o1 &&
+              NR_PROBES[4].o2 == NR_PROBES[22].o2 && NR_PROBES[22].var == 0 &&
+              NR_PROBES[9].var < 0 && NR_PROBES[15].var < 0 && NR_PROBES[4].var < 0,
+              "probe families out of step with NR_PROBES");
+
+struct Sector { uint32_t v[8]; };
+
+__device__ __forceinline__ uint32_t sector_bit(const Sector &s, uint32_t a)   // a = 0..255
+{
+    const uint32_t lo = (a & 64u) ? ((a & 32u) ? s.v[3] : s.v[2]) : ((a & 32u) ? s.v[1] : s.v[0]);
+    const uint32_t hi = (a & 64u) ? ((a & 32u) ? s.v[7] : s.v[6]) : ((a & 32u) ? s.v[5] : s.v[4]);
+    return (((a & 128u) ? hi : lo) >> (a & 31u)) & 1u;
+}
+
+// one probe of a slot: key from the window, one read of the key bitmap, hit bit into `mask`
+template <int T, bool WIDE>
 __device__ __forceinline__ void probe_one(const nr_filter_params &P, uint64_t W, bool slot_ok,
                                           uint64_t &mask)
 {
     constexpr nr_probe_t t = NR_PROBES[T];
-    const uint32_t key = nr_probe_key(W, t);
-    const uint32_t w = slot_ok ? __ldg(P.bits[t.drop] + (key >> 5)) : 0u;
-    mask |= (uint64_t)((w >> (key & 31u)) & 1u) << T;
+    if constexpr (WIDE && probe_in_family(T)) {
+        return;                                   // tested by the head of its family
+    } else if constexpr (WIDE && probe_family(T) >= 0) {
+        constexpr int F = probe_family(T);
+        const uint32_t key = nr_probe_key(W, t);
+        Sector s;
+        const uint32_t *sp = P.bits[t.drop] + ((key >> 8) << 3);
+        if (slot_ok) {
+            asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(s.v[0]), "=r"(s.v[1]), "=r"(s.v[2]), "=r"(s.v[3]), "=r"(s.v[4]),
+                           "=r"(s.v[5]), "=r"(s.v[6]), "=r"(s.v[7])
+                         : "l"(sp));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) s.v[k] = 0u;
+        }
+        mask |= (uint64_t)sector_bit(s, key & 255u) << T;
+        mask |= (uint64_t)sector_bit(s, nr_quarter(W, t.o0, 1)) << F;
+        mask |= (uint64_t)sector_bit(s, nr_quarter(W, t.o0, 2)) << (F + 1);
+        mask |= (uint64_t)sector_bit(s, nr_quarter(W, t.o0, 3)) << (F + 2);
+    } else {
+        const uint32_t key = nr_probe_key(W, t);
+        const uint32_t w = slot_ok ? __ldg(P.bits[t.drop] + (key >> 5)) : 0u;
+        mask |= (uint64_t)((w >> (key & 31u)) & 1u) << T;
+    }
 }
 
-template <int... I>
+template <bool WIDE, int... I>
 __device__ __forceinline__ uint64_t probe_all(const nr_filter_params &P, uint64_t W, bool slot_ok,
                                               std::integer_sequence<int, I...>)
 {
     uint64_t mask = 0;
-    (probe_one<I>(P, W, slot_ok, mask), ...);
+    (probe_one<I, WIDE>(P, W, slot_ok, mask), ...);
     return mask;
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(NR_FWARPS * 32, 3)
+__global__ void __launch_bounds__(NR_FWARPS * 32, NR_FBLOCKS)
 nr_match_filtered_kernel(const nr_filter_params P)
 {
     __shared__ WarpSmem smem[NR_FWARPS];
+    __shared__ uint32_t s_probes[64];
+    __shared__ Tables s_tab;
+    if (threadIdx.x < 64)
+        s_probes[threadIdx.x] = threadIdx.x < NR_PROBES_ALL ? probe_pack(c_probes[threadIdx.x]) : 0u;
+    if (threadIdx.x < 4) {
+        s_tab.bits[threadIdx.x] = P.bits[threadIdx.x]; s_tab.rank[threadIdx.x] = P.rank[threadIdx.x];
+        s_tab.ents[threadIdx.x] = P.ents[threadIdx.x]; s_tab.kstart[threadIdx.x] = P.kstart[threadIdx.x];
+    }
+    __syncthreads();
     const uint32_t lane = nr_lane();
     const int warp = threadIdx.x >> 5;
     WarpSmem &sm = smem[warp];
@@ -256,16 +347,28 @@ nr_match_filtered_kernel(const nr_filter_params P)
                         strand = slot >= nP ? 1 : 0;
                         p = p0 + slot - strand * nP;
                         if (slot_ok) W = nr_window64(sm.rdp[strand], p);
-                        mask = probe_all(P, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_MAIN>{});
-                        if (COUNT) c_probes_n += slot_ok ? NR_PROBES_MAIN : 0;
-                    } else if (item == nchunks && edge) {
+                        // Once a pair at cost b is known, only placements of cost <= b can still
+                        // matter, and prefixes of the probe table are complete for costs 0 and
+                        // <= 1 (nr_filter_core.h).  The first chunk runs the whole table and is
+                        // drained right away so that the later chunks know.
+                        if (acc.best >= 2) {
+                            mask = probe_all<true>(P, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_MAIN>{});
+                            if (COUNT) c_probes_n += slot_ok ? NR_PROBES_MAIN : 0;
+                        } else if (acc.best == 1) {
+                            mask = probe_all<false>(P, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_COST1>{});
+                            if (COUNT) c_probes_n += slot_ok ? NR_PROBES_COST1 : 0;
+                        } else {
+                            mask = probe_all<false>(P, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_COST0>{});
+                            if (COUNT) c_probes_n += slot_ok ? NR_PROBES_COST0 : 0;
+                        }
+                    } else if (item == nchunks && edge && acc.best >= 2) {
                         // one-column start overhang + interior insertion
                         if (lane < 2 * NR_PROBES_EDGE) {
                             strand = lane >= NR_PROBES_EDGE ? 1 : 0;
                             p = -1;
                             const int ti = NR_PROBES_MAIN + (int)lane - strand * NR_PROBES_EDGE;
                             W = nr_window64(sm.rdp[strand], -1);
-                            const nr_probe_t t = c_probes[ti];
+                            const nr_probe_t t = probe_unpack(s_probes[ti]);
                             const uint32_t key = nr_probe_key(W, t);
                             const uint32_t w = __ldg(P.bits[0] + (key >> 5));
                             mask = (uint64_t)((w >> (key & 31u)) & 1u) << ti;
@@ -290,7 +393,7 @@ nr_match_filtered_kernel(const nr_filter_params P)
                         }
                         const int total = __shfl_sync(0xffffffffu, incl, 31);
                         while (acc.qn + total > NR_QCAP || (item == nchunks + 1 && acc.qn > 0))
-                            drain<COUNT>(P, sm, acc, m);
+                            drain<COUNT>(P, sm, acc, m, s_probes, s_tab);
                         int pos = acc.qn + incl - mine;
                         // queue item = (probe, strand, slot position); the key, its rank and its
                         // rows are worked out in drain(), one hit per lane
@@ -302,6 +405,8 @@ nr_match_filtered_kernel(const nr_filter_params P)
                         acc.qn += total;
                         __syncwarp();
                     }
+                    if (item == 0 && nchunks > 1)
+                        while (acc.qn > 0) drain<COUNT>(P, sm, acc, m, s_probes, s_tab);
                 }
 
                 if (acc.overflow || (acc.best == 3 && P.resolve_below)) {

@@ -33,9 +33,15 @@ void pad_read(const uint32_t w[4], uint32_t rdp[NR_RDP_WORDS])
     for (int k = 0; k < 4; k++) rdp[1 + k] = w[k];
 }
 
+int g_probe_limit = 0;     // > 0: only the first g_probe_limit main probes, no edge probes
+
 }  // namespace
 
 extern "C" {
+
+// restrict the probe set to a prefix of NR_PROBES (0 = the whole table): used to check that the
+// prefixes NR_PROBES_COST0 / NR_PROBES_COST1 are complete for costs 0 / <= 1
+void nr_emul_set_probe_limit(int n) { g_probe_limit = n; }
 
 // whole-read exact scorer on one pair: returns cost (0..2, 3 = more), *umi as nr_nfa16
 int nr_emul_nfa(const uint8_t *q, int m, const uint8_t *core, int padL, int padR, int *umi)
@@ -112,6 +118,7 @@ int nr_emul_filtered(const uint32_t *wl, int64_t n, int padL, int padR, const ui
             for (int p = p0; p <= p1; p++) {
                 uint64_t W = nr_window64(rdp[s], p);
                 int nt = (p == -1) ? NR_PROBES_ALL : NR_PROBES_MAIN;
+                if (g_probe_limit > 0) nt = std::min(g_probe_limit, NR_PROBES_MAIN);
                 for (int t = 0; t < nt; t++) {
                     const nr_probe_t &pr = NR_PROBES[t];
                     if (p + nr_probe_first(pr) < 0 || p + nr_probe_end(pr) > m) continue;

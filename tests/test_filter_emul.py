@@ -181,3 +181,39 @@ def test_filter_lossless_737k(oracle, emul):
     wl = whitelists.ascii_to_strings(wl_a)
     ref, out, cnt = run_emul(emul, oracle, wl, cands, 30, 40, 1)
     assert check(ref, out, cands, wl) > 150
+
+
+@pytest.mark.parametrize("limit,max_cost", [(1, 0), (16, 1)])
+def test_probe_prefixes_complete_for_small_costs(oracle, emul, limit, max_cost):
+    """NR_PROBES_COST0 / NR_PROBES_COST1 (nr_filter_core.h): with only that prefix of the probe
+    table every candidate whose best cost is <= max_cost still gets the exact answer -- all pairs
+    at the best cost are found.  The kernel relies on this after its first chunk of slots."""
+    rng = np.random.default_rng(900 + limit)
+    emul.nr_emul_set_probe_limit(limit)
+    try:
+        total = 0
+        for pad_l, pad_r, qlen in [(30, 40, 50), (4, 17, 35), (2, 3, 30), (30, 40, 64)]:
+            wl = tie_rich_whitelist(rng, 1500)
+            cands = mixed_candidates(rng, wl, 2500, pad_l, qlen, with_n=0.0)
+            # every single-event variant of some cores, at several offsets
+            for core in wl[:40]:
+                for v in _variants(rng, core):
+                    a = int(rng.integers(0, min(pad_l + 2, 20)))
+                    cands.append((rs(rng, a) + v + rs(rng, 40))[:qlen])
+                # core hanging over the read end / the read start by one column
+                cands.append(rs(rng, 14) + core[:-1])
+                cands.append(core[1:] + rs(rng, 14))
+                cands.append(rs(rng, 10) + core)
+                cands.append(core + rs(rng, 10))
+            ref, out, _ = run_emul(emul, oracle, wl, cands, pad_l, pad_r)
+            sel = (16 - ref["best_score"] <= max_cost) & (out["took"] == 1)
+            ok = ((out["score"] == ref["best_score"]) & (out["idx"] == ref["best_idx"]) &
+                  (out["nbest"] == ref["n_best"]) & (out["strand"] == ref["strand"]) &
+                  (out["umi"] == ref["umi_q"]))
+            bad = np.flatnonzero(sel & ~ok)
+            assert len(bad) == 0, (cands[bad[0]], {k: v[bad[0]] for k, v in ref.items()},
+                                   {k: v[bad[0]] for k, v in out.items()})
+            total += int(sel.sum())
+        assert total > 1500
+    finally:
+        emul.nr_emul_set_probe_limit(0)
