@@ -193,26 +193,24 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, A
     }
 }
 
-// Probes that differ only in their FIRST kept quarter (a plain probe and the three "5-mer minus
-// one base" variants of that quarter) address the same 32-byte sector of the bitmap: the key's low
-// 8 bits are that quarter.  The plain probe of such a family brings the whole sector with one
-// 256-bit load and all four members test their bit in registers; the variants issue no load.
+// The three "5-mer minus one base" variants of a probe's FIRST kept quarter address the same
+// 32-byte sector of the bitmap (the key's low 8 bits are that quarter): the first variant brings
+// the whole sector with one 256-bit load and all three test their bit in registers.
 // (ncu: the kernel is L1TEX-bound -- l1tex throughput 73 %, ALU pipe 58 % -- and the tag stage
-// works per sector, so this removes 9 of the 34 lookups of a slot.)
-__host__ __device__ constexpr int probe_family(int T)   // first variant of the family T heads, or -1
+// works per sector.)
+__host__ __device__ constexpr bool probe_family_first(int T) { return T == 16 || T == 19 || T == 22; }
+__host__ __device__ constexpr bool probe_family_rest(int T)
 {
-    return T == 9 ? 16 : (T == 15 ? 19 : (T == 4 ? 22 : -1));
+    return T == 17 || T == 18 || T == 20 || T == 21 || T == 23 || T == 24;
 }
-__host__ __device__ constexpr bool probe_in_family(int T) { return T >= 16 && T <= 24; }
 
-static_assert(NR_PROBES[9].drop == NR_PROBES[16].drop && NR_PROBES[9].o1 == NR_PROBES[16].o1 &&
-              NR_PROBES[9].o2 == NR_PROBES[18].o2 && NR_PROBES[16].var == 0 &&
-              NR_PROBES[15].drop == NR_PROBES[19].drop && NR_PROBES[15].o1 == NR_PROBES[21].o1 &&
-              NR_PROBES[15].o2 == NR_PROBES[19].o2 && NR_PROBES[19].var == 0 &&
-              NR_PROBES[4].drop == NR_PROBES[22].drop && NR_PROBES[4].o1 == NR_PROBES[24].o1 &&
-              NR_PROBES[4].o2 == NR_PROBES[22].o2 && NR_PROBES[22].var == 0 &&
-              NR_PROBES[9].var < 0 && NR_PROBES[15].var < 0 && NR_PROBES[4].var < 0,
-              "probe families out of step with NR_PROBES");
+static_assert(NR_PROBES[16].var == 0 && NR_PROBES[16].del == 1 && NR_PROBES[18].del == 3 &&
+              NR_PROBES[16].o1 == NR_PROBES[18].o1 && NR_PROBES[16].drop == NR_PROBES[18].drop &&
+              NR_PROBES[19].var == 0 && NR_PROBES[19].del == 1 && NR_PROBES[21].del == 3 &&
+              NR_PROBES[19].o2 == NR_PROBES[21].o2 && NR_PROBES[19].drop == NR_PROBES[21].drop &&
+              NR_PROBES[22].var == 0 && NR_PROBES[22].del == 1 && NR_PROBES[24].del == 3 &&
+              NR_PROBES[22].o1 == NR_PROBES[24].o1 && NR_PROBES[22].drop == NR_PROBES[24].drop &&
+              NR_PROBES[25].var == 1, "probe families out of step with NR_PROBES");
 
 struct Sector { uint32_t v[8]; };
 
@@ -224,15 +222,14 @@ __device__ __forceinline__ uint32_t sector_bit(const Sector &s, uint32_t a)   //
 }
 
 // one probe of a slot: key from the window, one read of the key bitmap, hit bit into `mask`
-template <int T, bool WIDE>
+template <int T>
 __device__ __forceinline__ void probe_one(const nr_filter_params &P, uint64_t W, bool slot_ok,
                                           uint64_t &mask)
 {
     constexpr nr_probe_t t = NR_PROBES[T];
-    if constexpr (WIDE && probe_in_family(T)) {
-        return;                                   // tested by the head of its family
-    } else if constexpr (WIDE && probe_family(T) >= 0) {
-        constexpr int F = probe_family(T);
+    if constexpr (probe_family_rest(T)) {
+        return;                                   // tested by the first variant of its family
+    } else if constexpr (probe_family_first(T)) {
         const uint32_t key = nr_probe_key(W, t);
         Sector s;
         const uint32_t *sp = P.bits[t.drop] + ((key >> 8) << 3);
@@ -246,9 +243,8 @@ __device__ __forceinline__ void probe_one(const nr_filter_params &P, uint64_t W,
             for (int k = 0; k < 8; k++) s.v[k] = 0u;
         }
         mask |= (uint64_t)sector_bit(s, key & 255u) << T;
-        mask |= (uint64_t)sector_bit(s, nr_quarter(W, t.o0, 1)) << F;
-        mask |= (uint64_t)sector_bit(s, nr_quarter(W, t.o0, 2)) << (F + 1);
-        mask |= (uint64_t)sector_bit(s, nr_quarter(W, t.o0, 3)) << (F + 2);
+        mask |= (uint64_t)sector_bit(s, nr_quarter(W, t.o0, 2)) << (T + 1);
+        mask |= (uint64_t)sector_bit(s, nr_quarter(W, t.o0, 3)) << (T + 2);
     } else {
         const uint32_t key = nr_probe_key(W, t);
         const uint32_t w = slot_ok ? __ldg(P.bits[t.drop] + (key >> 5)) : 0u;
@@ -256,13 +252,54 @@ __device__ __forceinline__ void probe_one(const nr_filter_params &P, uint64_t W,
     }
 }
 
-template <bool WIDE, int... I>
-__device__ __forceinline__ uint64_t probe_all(const nr_filter_params &P, uint64_t W, bool slot_ok,
-                                              std::integer_sequence<int, I...>)
+// probes LO .. LO + N - 1 of a slot
+template <int LO, int... I>
+__device__ __forceinline__ uint64_t probe_range(const nr_filter_params &P, uint64_t W, bool slot_ok,
+                                                std::integer_sequence<int, I...>)
 {
     uint64_t mask = 0;
-    (probe_one<I, WIDE>(P, W, slot_ok, mask), ...);
+    (probe_one<LO + I>(P, W, slot_ok, mask), ...);
     return mask;
+}
+
+// Place the hits of one work item (per-lane probe mask at (strand, p)) in the warp's queue,
+// draining it as often as needed.
+template <bool COUNT>
+__device__ __forceinline__ void enqueue(const nr_filter_params &P, WarpSmem &sm, Acc &acc, int m,
+                                        const uint32_t *s_probes, const Tables &T4, uint64_t mask,
+                                        int strand, int p)
+{
+    const uint32_t lane = nr_lane();
+    // an item with more hits than the queue holds (dense key bitmaps: whitelists of millions of
+    // entries) is queued in four probe ranges of <= 9 x 32 hits
+    const int total_all = __reduce_add_sync(0xffffffffu, __popcll(mask));
+    if (total_all == 0) return;
+    const int nparts = total_all > NR_QCAP ? 4 : 1;
+    const uint32_t where = ((uint32_t)strand << 24) | ((uint32_t)(p + 16) << 25);
+#pragma unroll 1
+    for (int part = 0; part < nparts; part++) {
+        uint64_t pm = nparts == 1 ? mask : (mask & (0x1FFull << (9 * part)));
+        // queue positions of the hits: exclusive scan of the per-lane counts
+        const int mine = __popcll(pm);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        while (acc.qn + total > NR_QCAP) drain<COUNT>(P, sm, acc, m, s_probes, T4);
+        int pos = acc.qn + incl - mine;
+        // queue item = (probe, strand, slot position); the key, its rank and its rows are worked
+        // out in drain(), one hit per lane
+        while (pm) {
+            const int T = __ffsll((long long)pm) - 1;
+            pm &= pm - 1;
+            sm.queue[pos++] = where | ((uint32_t)T << 16);
+        }
+        acc.qn += total;
+        __syncwarp();
+    }
 }
 
 template <bool COUNT>
@@ -335,78 +372,51 @@ nr_match_filtered_kernel(const nr_filter_params P)
                 const int nslots = nP > 0 ? 2 * nP : 0;
                 const int nchunks = (nslots + 31) >> 5;
                 const bool edge = p0 <= -1 && p1 >= -1;
-                // work items: one per chunk of 32 slots, then the edge probes (slot -1 only),
-                // then a flush item that only drains
+                // Three stages over all slots, each drained before the next starts.  Prefixes of
+                // the probe table are complete for small costs (nr_filter_core.h): after stage 0
+                // (probe 0) every placement of cost 0 is known, after stage 1 (probes 1..15)
+                // every placement of cost <= 1; a candidate whose best pair is already that good
+                // needs nothing more -- only placements at the best cost count.  Stage 2 runs
+                // the variant probes and the edge probes (two cost-1 events).
 #pragma unroll 1
-                for (int item = 0; item <= nchunks + 1; item++) {
-                    uint64_t mask = 0, W = 0;
-                    int strand = 0, p = 0;
-                    if (item < nchunks) {
+                for (int stage = 0; stage < 3; stage++) {
+                    if (acc.best < stage) break;
+#pragma unroll 1
+                    for (int item = 0; item < nchunks; item++) {
                         const int slot = item * 32 + (int)lane;
                         const bool slot_ok = slot < nslots;
-                        strand = slot >= nP ? 1 : 0;
-                        p = p0 + slot - strand * nP;
-                        if (slot_ok) W = nr_window64(sm.rdp[strand], p);
-                        // Once a pair at cost b is known, only placements of cost <= b can still
-                        // matter, and prefixes of the probe table are complete for costs 0 and
-                        // <= 1 (nr_filter_core.h).  The first chunk runs the whole table and is
-                        // drained right away so that the later chunks know.
-                        if (acc.best >= 2) {
-                            mask = probe_all<true>(P, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_MAIN>{});
-                            if (COUNT) c_probes_n += slot_ok ? NR_PROBES_MAIN : 0;
-                        } else if (acc.best == 1) {
-                            mask = probe_all<false>(P, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_COST1>{});
-                            if (COUNT) c_probes_n += slot_ok ? NR_PROBES_COST1 : 0;
-                        } else {
-                            mask = probe_all<false>(P, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_COST0>{});
+                        const int strand = slot >= nP ? 1 : 0;
+                        const int p = p0 + slot - strand * nP;
+                        const uint64_t W = slot_ok ? nr_window64(sm.rdp[strand], p) : 0ull;
+                        uint64_t mask;
+                        if (stage == 0) {
+                            mask = probe_range<0>(P, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_COST0>{});
                             if (COUNT) c_probes_n += slot_ok ? NR_PROBES_COST0 : 0;
+                        } else if (stage == 1) {
+                            mask = probe_range<NR_PROBES_COST0>(P, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_COST1 - NR_PROBES_COST0>{});
+                            if (COUNT) c_probes_n += slot_ok ? NR_PROBES_COST1 - NR_PROBES_COST0 : 0;
+                        } else {
+                            mask = probe_range<NR_PROBES_COST1>(P, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_MAIN - NR_PROBES_COST1>{});
+                            if (COUNT) c_probes_n += slot_ok ? NR_PROBES_MAIN - NR_PROBES_COST1 : 0;
                         }
-                    } else if (item == nchunks && edge && acc.best >= 2) {
-                        // one-column start overhang + interior insertion
+                        enqueue<COUNT>(P, sm, acc, m, s_probes, s_tab, mask, strand, p);
+                    }
+                    if (stage == 2 && edge) {
+                        // one-column start overhang + interior insertion (slot -1 only)
+                        uint64_t mask = 0;
+                        const int strand = lane >= NR_PROBES_EDGE ? 1 : 0;
                         if (lane < 2 * NR_PROBES_EDGE) {
-                            strand = lane >= NR_PROBES_EDGE ? 1 : 0;
-                            p = -1;
                             const int ti = NR_PROBES_MAIN + (int)lane - strand * NR_PROBES_EDGE;
-                            W = nr_window64(sm.rdp[strand], -1);
+                            const uint64_t W = nr_window64(sm.rdp[strand], -1);
                             const nr_probe_t t = probe_unpack(s_probes[ti]);
                             const uint32_t key = nr_probe_key(W, t);
                             const uint32_t w = __ldg(P.bits[0] + (key >> 5));
                             mask = (uint64_t)((w >> (key & 31u)) & 1u) << ti;
                             if (COUNT) c_probes_n++;
                         }
+                        enqueue<COUNT>(P, sm, acc, m, s_probes, s_tab, mask, strand, -1);
                     }
-                    // an item with more hits than the queue holds (dense key bitmaps: whitelists
-                    // of millions of entries) is queued in four probe ranges of <= 9 x 32 hits
-                    const int total_all = __reduce_add_sync(0xffffffffu, __popcll(mask));
-                    const int nparts = total_all > NR_QCAP ? 4 : 1;
-                    const uint32_t where = ((uint32_t)strand << 24) | ((uint32_t)(p + 16) << 25);
-#pragma unroll 1
-                    for (int part = 0; part < nparts; part++) {
-                        uint64_t pm = nparts == 1 ? mask : (mask & (0x1FFull << (9 * part)));
-                        // queue positions of the hits: exclusive scan of the per-lane counts
-                        const int mine = __popcll(pm);
-                        int incl = mine;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            int v = __shfl_up_sync(0xffffffffu, incl, o);
-                            if ((int)lane >= o) incl += v;
-                        }
-                        const int total = __shfl_sync(0xffffffffu, incl, 31);
-                        while (acc.qn + total > NR_QCAP || (item == nchunks + 1 && acc.qn > 0))
-                            drain<COUNT>(P, sm, acc, m, s_probes, s_tab);
-                        int pos = acc.qn + incl - mine;
-                        // queue item = (probe, strand, slot position); the key, its rank and its
-                        // rows are worked out in drain(), one hit per lane
-                        while (pm) {
-                            const int T = __ffsll((long long)pm) - 1;
-                            pm &= pm - 1;
-                            sm.queue[pos++] = where | ((uint32_t)T << 16);
-                        }
-                        acc.qn += total;
-                        __syncwarp();
-                    }
-                    if (item == 0 && nchunks > 1)
-                        while (acc.qn > 0) drain<COUNT>(P, sm, acc, m, s_probes, s_tab);
+                    while (acc.qn > 0) drain<COUNT>(P, sm, acc, m, s_probes, s_tab);
                 }
 
                 if (acc.overflow || (acc.best == 3 && P.resolve_below)) {
