@@ -421,6 +421,26 @@ def main():
         wl.match_host(h_seqs, h_off, min_score=min_score, mode=NR_MODE_FILTERED, out=g_out)
     e2e_pageable_s = (time.perf_counter() - t0) / e2e_steps
 
+    # the exhaustive DP kernel on a bounded sample: real (executed) cell updates per second
+    from nanoranger_b200 import NR_MODE_EXHAUSTIVE
+    n_dp = min(B, 2048)
+    dp_off = d_off[:n_dp + 1].contiguous()
+    dp_bases, dp_meta, dp_nmask = wl.pack_device(d_seqs, dp_off)
+    dp_out = wl.alloc_result(n_dp, dev)
+    dp_ws = wl.workspace(n_dp, dev, NR_MODE_EXHAUSTIVE)
+    wl.match_device(dp_bases, dp_meta, dp_nmask, min_score=min_score, mode=NR_MODE_EXHAUSTIVE,
+                    out=dp_out, workspace=dp_ws)
+    torch.cuda.synchronize()
+    e0.record()
+    wl.match_device(dp_bases, dp_meta, dp_nmask, min_score=min_score, mode=NR_MODE_EXHAUSTIVE,
+                    out=dp_out, workspace=dp_ws)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_dp = e0.elapsed_time(e1)
+    dp_cells = float(dp_meta.to(torch.int64).bitwise_and(0x7F).sum().item()) * len(wl_ascii) * 16 * 2
+    dp_same = bool(torch.equal(dp_out.idx[out.assigned(min_score)[:n_dp]],
+                               out.idx[:n_dp][out.assigned(min_score)[:n_dp]]))
+
     # max over ranks
     t = torch.tensor([ms_total, ms_match, e2e_s], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(assigned)], dtype=torch.float64, device=dev)
@@ -488,6 +508,12 @@ def main():
                    "l2": "inputs larger than L2 (ASCII batch %.0f MB per GPU)" % (n_bytes_in / 1e6),
                    "index_build_s": t_index},
         "gcups_equivalent": value * n_wl * 16 * 50 / 1e9,
+        "dp_gcups": {"value": dp_cells / (ms_dp * 1e-3) / 1e9 * world, "kernel": "nr_match_exhaustive16_kernel",
+                     "sample": f"first {n_dp} candidates of the batch per GPU, both strands, every whitelist entry",
+                     "ms": ms_dp, "candidates_per_sec": world * n_dp / (ms_dp * 1e-3),
+                     "agrees_with_filtered_on_assigned": dp_same,
+                     "note": "executed cell updates of the exhaustive DP (NR_MODE_EXHAUSTIVE); "
+                             "gcups_equivalent is the filtered path's candidates/s x cells a brute force would do"},
         "assigned_per_sec": float(tot.item()) / (ms_step * 1e-3),
         "assigned_fraction": float(tot.item()) / (world * B),
         "counters_per_candidate": {k: v / B for k, v in counters.items()},

@@ -272,10 +272,23 @@ __device__ __forceinline__ void enqueue(const nr_filter_params &P, WarpSmem &sm,
     const uint32_t lane = nr_lane();
     // an item with more hits than the queue holds (dense key bitmaps: whitelists of millions of
     // entries) is queued in four probe ranges of <= 9 x 32 hits
-    const int total_all = __reduce_add_sync(0xffffffffu, __popcll(mask));
-    if (total_all == 0) return;
-    const int nparts = total_all > NR_QCAP ? 4 : 1;
     const uint32_t where = ((uint32_t)strand << 24) | ((uint32_t)(p + 16) << 25);
+    const int mine_all = __popcll(mask);
+    // common case: no lane holds more than one hit -> positions from one ballot
+    if (!__any_sync(0xffffffffu, mine_all > 1)) {
+        const uint32_t b = __ballot_sync(0xffffffffu, mine_all != 0);
+        if (b == 0u) return;
+        const int total = __popc(b);
+        while (acc.qn + total > NR_QCAP) drain<COUNT>(P, sm, acc, m, s_probes, T4);
+        if (mine_all)
+            sm.queue[acc.qn + __popc(b & ((1u << lane) - 1u))] =
+                where | ((uint32_t)(__ffsll((long long)mask) - 1) << 16);
+        acc.qn += total;
+        __syncwarp();
+        return;
+    }
+    const int total_all = __reduce_add_sync(0xffffffffu, mine_all);
+    const int nparts = total_all > NR_QCAP ? 4 : 1;
 #pragma unroll 1
     for (int part = 0; part < nparts; part++) {
         uint64_t pm = nparts == 1 ? mask : (mask & (0x1FFull << (9 * part)));

@@ -179,15 +179,32 @@ def match_records(wl: Whitelist, names, seqs, offsets, ref_names, mode=NR_MODE_A
                int(res.score[i]))
 
 
+AUTO_MODE_MAX = 200_000     # candidates up to which low-scoring reads are resolved exactly as well
+
+
 def barcode_align(input_fastq, genome_dir, out_name, threads=1, *ignored, device: int = 0,
-                  header: str = "used"):
+                  header: str = "used", mode=None):
     """scripts/barcode_align.sh <input.fa.gz> <genome_dir> <out_prefix> <threads> [ignored]:
     writes `<out_prefix>.sam`.  `threads` is accepted for call compatibility (the work runs on
-    the GPU)."""
+    the GPU).
+
+    mode: NR_MODE_AUTO resolves EVERY candidate exactly (reads below the reference's threshold go
+    through the exhaustive DP kernel, ~8e3 candidates/s against 737K barcodes), NR_MODE_FILTERED
+    resolves exactly everything the reference keeps (AS >= core length - 2) at ~2e8 candidates/s
+    and leaves the rest out of the SAM -- the only file that can tell is the low-score tail of
+    `_barcode_scores.csv`, which the reference merely plots.  Default: AUTO up to AUTO_MODE_MAX
+    candidates, FILTERED above (announced on stdout)."""
+    from ._lib import NR_MODE_FILTERED
     wl, ref_names = load_genome(genome_dir, device)
     try:
         names, seqs, offsets = fastx.read_fasta(input_fastq)
-        recs = match_records(wl, names, seqs, offsets, ref_names)
+        if mode is None:
+            mode = NR_MODE_AUTO
+            if len(names) > AUTO_MODE_MAX and wl.has_index:
+                mode = NR_MODE_FILTERED
+                print(f"nanoranger_b200: {len(names)} candidates > {AUTO_MODE_MAX}: reads scoring below "
+                      f"{wl.core_len - 2} are not resolved (pass mode=NR_MODE_AUTO to resolve them)")
+        recs = match_records(wl, names, seqs, offsets, ref_names, mode=mode)
         n = samio.write_sam(f"{out_name}.sam", ref_names, wl.pad_l + wl.core_len + wl.pad_r, recs,
                             header=header)
     finally:
