@@ -35,7 +35,8 @@
 #define NR_QCAP 480                        // queue slots per warp
 
 struct nr_filter_params {
-    const uint32_t *bits[4];      // key bitmap, 2^19 words per dropped quarter
+    const uint32_t *bits[4];      // key bitmap, 2^19 words per dropped quarter, contiguous:
+                                  // bits[j] == bits[0] + j * 2^19 (nr_whitelist.cu)
     const uint32_t *rank[4];      // distinct keys below each bitmap word
     const uint2 *ents[4];
     const uint32_t *kstart[4];
@@ -127,7 +128,7 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, A
     uint32_t start = 0, rows = 0;
     if (have && h_p + nr_probe_first(t) >= 0 && h_p + nr_probe_end(t) <= m) {
         const uint32_t key = nr_probe_key(nr_window64(sm.rdp[h_strand], h_p), t);
-        const uint32_t w = __ldg(T4.bits[d] + (key >> 5));
+        const uint32_t w = __ldg(T4.bits[0] + (((d << 24) | key) >> 5));
         const uint32_t kr = __ldg(T4.rank[d] + (key >> 5)) +
                             (uint32_t)__popc(w & ((1u << (key & 31u)) - 1u));
         const uint32_t *ks = T4.kstart[d] + kr;
@@ -221,45 +222,42 @@ __device__ __forceinline__ uint32_t sector_bit(const Sector &s, uint32_t a)   //
     return (((a & 128u) ? hi : lo) >> (a & 31u)) & 1u;
 }
 
-// one probe of a slot: key from the window, one read of the key bitmap, hit bit into `mask`
+// one probe of a slot: key from the window, one read of the key bitmap, hit bit into `mask`.
+// `bits` is the base of the four contiguous bitmaps; lanes without a slot carry W = 0 and read a
+// valid word whose result the caller discards (no predicated loads in the unrolled sequence).
 template <int T>
-__device__ __forceinline__ void probe_one(const nr_filter_params &P, uint64_t W, bool slot_ok,
-                                          uint64_t &mask)
+__device__ __forceinline__ void probe_one(const uint32_t *__restrict__ bits, uint64_t W, uint64_t &mask)
 {
     constexpr nr_probe_t t = NR_PROBES[T];
+    constexpr uint32_t table = (uint32_t)t.drop << 24;
     if constexpr (probe_family_rest(T)) {
         return;                                   // tested by the first variant of its family
     } else if constexpr (probe_family_first(T)) {
-        const uint32_t key = nr_probe_key(W, t);
+        const uint32_t key = nr_probe_key(W, t) | table;
         Sector s;
-        const uint32_t *sp = P.bits[t.drop] + ((key >> 8) << 3);
-        if (slot_ok) {
-            asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(s.v[0]), "=r"(s.v[1]), "=r"(s.v[2]), "=r"(s.v[3]), "=r"(s.v[4]),
-                           "=r"(s.v[5]), "=r"(s.v[6]), "=r"(s.v[7])
-                         : "l"(sp));
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; k++) s.v[k] = 0u;
-        }
+        const uint32_t *sp = bits + ((key >> 8) << 3);
+        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(s.v[0]), "=r"(s.v[1]), "=r"(s.v[2]), "=r"(s.v[3]), "=r"(s.v[4]),
+                       "=r"(s.v[5]), "=r"(s.v[6]), "=r"(s.v[7])
+                     : "l"(sp));
         mask |= (uint64_t)sector_bit(s, key & 255u) << T;
         mask |= (uint64_t)sector_bit(s, nr_quarter(W, t.o0, 2)) << (T + 1);
         mask |= (uint64_t)sector_bit(s, nr_quarter(W, t.o0, 3)) << (T + 2);
     } else {
-        const uint32_t key = nr_probe_key(W, t);
-        const uint32_t w = slot_ok ? __ldg(P.bits[t.drop] + (key >> 5)) : 0u;
+        const uint32_t key = nr_probe_key(W, t) | table;
+        const uint32_t w = __ldg(bits + (key >> 5));
         mask |= (uint64_t)((w >> (key & 31u)) & 1u) << T;
     }
 }
 
 // probes LO .. LO + N - 1 of a slot
 template <int LO, int... I>
-__device__ __forceinline__ uint64_t probe_range(const nr_filter_params &P, uint64_t W, bool slot_ok,
-                                                std::integer_sequence<int, I...>)
+__device__ __forceinline__ uint64_t probe_range(const uint32_t *__restrict__ bits, uint64_t W,
+                                                bool slot_ok, std::integer_sequence<int, I...>)
 {
     uint64_t mask = 0;
-    (probe_one<LO + I>(P, W, slot_ok, mask), ...);
-    return mask;
+    (probe_one<LO + I>(bits, W, mask), ...);
+    return slot_ok ? mask : 0ull;
 }
 
 // Place the hits of one work item (per-lane probe mask at (strand, p)) in the warp's queue,
@@ -332,6 +330,7 @@ nr_match_filtered_kernel(const nr_filter_params P)
     const uint32_t lane = nr_lane();
     const int warp = threadIdx.x >> 5;
     WarpSmem &sm = smem[warp];
+    const uint32_t *__restrict__ bits_all = P.bits[0];
     const uint64_t n_tiles = (P.n_cand + 31) >> 5;
     unsigned long long c_probes_n = 0, c_listed = 0;
     Acc acc;
@@ -403,13 +402,13 @@ nr_match_filtered_kernel(const nr_filter_params P)
                         const uint64_t W = slot_ok ? nr_window64(sm.rdp[strand], p) : 0ull;
                         uint64_t mask;
                         if (stage == 0) {
-                            mask = probe_range<0>(P, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_COST0>{});
+                            mask = probe_range<0>(bits_all, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_COST0>{});
                             if (COUNT) c_probes_n += slot_ok ? NR_PROBES_COST0 : 0;
                         } else if (stage == 1) {
-                            mask = probe_range<NR_PROBES_COST0>(P, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_COST1 - NR_PROBES_COST0>{});
+                            mask = probe_range<NR_PROBES_COST0>(bits_all, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_COST1 - NR_PROBES_COST0>{});
                             if (COUNT) c_probes_n += slot_ok ? NR_PROBES_COST1 - NR_PROBES_COST0 : 0;
                         } else {
-                            mask = probe_range<NR_PROBES_COST1>(P, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_MAIN - NR_PROBES_COST1>{});
+                            mask = probe_range<NR_PROBES_COST1>(bits_all, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_MAIN - NR_PROBES_COST1>{});
                             if (COUNT) c_probes_n += slot_ok ? NR_PROBES_MAIN - NR_PROBES_COST1 : 0;
                         }
                         enqueue<COUNT>(P, sm, acc, m, s_probes, s_tab, mask, strand, p);

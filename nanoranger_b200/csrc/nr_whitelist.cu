@@ -157,9 +157,18 @@ extern "C" int nr_whitelist_create(const char *cores, uint64_t n, uint32_t core_
         size_t bmb = (size_t)(NR_BM_WORDS + 1) * sizeof(uint32_t);
         uint32_t nn = (uint32_t)n;
         uint32_t blocks = (nn + 255) / 256;
+        // the four key bitmaps are one allocation, 2^19 words apart: a probe addresses bit
+        // (dropped quarter << 24 | key) from a single base pointer
+        uint32_t *bits_all = nullptr;
+        if (cudaMalloc(&bits_all, (size_t)4 * NR_BM_WORDS * sizeof(uint32_t) + 256) != cudaSuccess) {
+            cudaFree(d_keys); cudaFree(d_vals); cudaFree(d_heads);
+            nr_set_error("cudaMalloc seed index");
+            return fail(NR_ENOMEM);
+        }
+        cudaMemset(bits_all, 0, (size_t)4 * NR_BM_WORDS * sizeof(uint32_t) + 256);
+        for (int j = 0; j < 4; j++) w->d_bits[j] = bits_all + (size_t)j * NR_BM_WORDS;
         for (int j = 0; j < 4; j++) {
-            if (cudaMalloc(&w->d_bits[j], bmb) != cudaSuccess ||
-                cudaMalloc(&w->d_rank[j], bmb) != cudaSuccess ||
+            if (cudaMalloc(&w->d_rank[j], bmb) != cudaSuccess ||
                 cudaMalloc(&w->d_ents[j], n * sizeof(uint2)) != cudaSuccess ||
                 cudaMalloc(&w->d_kstart[j], (n + 1) * sizeof(uint32_t)) != cudaSuccess) {
                 cudaFree(d_keys); cudaFree(d_vals); cudaFree(d_heads);
@@ -167,7 +176,6 @@ extern "C" int nr_whitelist_create(const char *cores, uint64_t n, uint32_t core_
                 return fail(NR_ENOMEM);
             }
             w->bytes += 2 * bmb + n * sizeof(uint2) + (n + 1) * sizeof(uint32_t);
-            cudaMemset(w->d_bits[j], 0, bmb);
             nr_index_keys_kernel<<<blocks, 256>>>(w->d_lo, nn, j, d_keys, d_vals);
             thrust::stable_sort_by_key(thrust::device, thrust::device_pointer_cast(d_keys),
                                        thrust::device_pointer_cast(d_keys) + n,
@@ -206,7 +214,8 @@ extern "C" void nr_whitelist_destroy(nr_whitelist_t *w)
     cudaSetDevice(w->device);
     nr_host_ctx_destroy(w->host_ctx);
     cudaFree(w->d_lo); cudaFree(w->d_hi); cudaFree(w->d_nm);
-    for (int j = 0; j < 4; j++) { cudaFree(w->d_bits[j]); cudaFree(w->d_rank[j]); cudaFree(w->d_ents[j]); cudaFree(w->d_kstart[j]); }
+    cudaFree(w->d_bits[0]);
+    for (int j = 0; j < 4; j++) { cudaFree(w->d_rank[j]); cudaFree(w->d_ents[j]); cudaFree(w->d_kstart[j]); }
     delete w;
     if (prev >= 0) cudaSetDevice(prev);
 }
