@@ -158,6 +158,42 @@ NR_HD uint32_t nr_probe_key(uint64_t W, const nr_probe_t &t)
     return a | (b << 8) | (c << 16);
 }
 
+// ---- bitmap layouts ------------------------------------------------------------------------------
+// A 32-byte sector of a key bitmap holds the 256 keys that differ in the key's LOW byte.  The
+// device keeps every bitmap in three bit orders so that the probes of a slot that differ in one
+// kept quarter only fall into one sector whichever quarter that is (L1TEX/L2 work is per sector):
+//   layout 0: a | b << 8 | c << 16   (the index order: rank / kstart / ents use it)
+//   layout 1: b | a << 8 | c << 16
+//   layout 2: c | a << 8 | b << 16
+// Table id = layout * 4 + dropped quarter; bit address = id << 24 | permuted key.
+#define NR_BM_LAYOUTS 3
+
+NR_HD uint32_t nr_key_layout(uint32_t key, int layout)
+{
+    const uint32_t a = key & 0xFFu, b = (key >> 8) & 0xFFu, c = key >> 16;
+    if (layout == 1) return b | (a << 8) | (c << 16);
+    if (layout == 2) return c | (a << 8) | (b << 16);
+    return key;
+}
+
+// layout a main probe reads: the one in which its family (same offsets, one quarter varying
+// between the members) shares a sector
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+constexpr int nr_probe_layout_of(const nr_probe_t &t)
+{
+    if (t.var == 1) return 1;                                  // b varies between the 3 variants
+    if (t.var == 2) return 2;                                  // c varies
+    if (t.var == 0) return 0;                                  // a varies
+    // plain probes: c-varying groups (same drop, o0, o1)
+    if (t.drop == 0 && t.o0 == 4 && t.o1 == 8) return 2;       // (4,8,12) (4,8,13)
+    if (t.drop == 3 && t.o0 == 0 && t.o1 == 4) return 2;       // (0,4,8) (0,4,9) + the c variants
+    if (t.drop == 2 && t.o0 == 0 && t.o1 == 4) return 2;       // (0,4,11..14)
+    if (t.drop == 1 && t.o0 == 0 && t.o1 == 9) return 2;       // (0,9,13) (0,9,14)
+    return 0;                                                  // heads of the a-varying families, singles
+}
+
 // key of a whitelist core with quarter j removed (must agree with nr_probe_key)
 NR_HD uint32_t nr_core_key(uint32_t core, int j)
 {

@@ -194,24 +194,30 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, A
     }
 }
 
-// The three "5-mer minus one base" variants of a probe's FIRST kept quarter address the same
-// 32-byte sector of the bitmap (the key's low 8 bits are that quarter): the first variant brings
-// the whole sector with one 256-bit load and all three test their bit in registers.
+// The three "5-mer minus one base" variants of a probe differ in one kept quarter only; in the
+// bitmap layout that puts this quarter in the key's low byte (nr_filter_core.h) they address the
+// same 32-byte sector: the first variant brings the whole sector with one 256-bit load and all
+// three test their bit in registers.
 // (ncu: the kernel is L1TEX-bound -- l1tex throughput 73 %, ALU pipe 58 % -- and the tag stage
 // works per sector.)
-__host__ __device__ constexpr bool probe_family_first(int T) { return T == 16 || T == 19 || T == 22; }
+__host__ __device__ constexpr bool probe_family_first(int T)
+{
+    return T >= NR_PROBES_COST1 && T < NR_PROBES_MAIN && (T - NR_PROBES_COST1) % 3 == 0;
+}
 __host__ __device__ constexpr bool probe_family_rest(int T)
 {
-    return T == 17 || T == 18 || T == 20 || T == 21 || T == 23 || T == 24;
+    return T >= NR_PROBES_COST1 && T < NR_PROBES_MAIN && (T - NR_PROBES_COST1) % 3 != 0;
 }
-
-static_assert(NR_PROBES[16].var == 0 && NR_PROBES[16].del == 1 && NR_PROBES[18].del == 3 &&
-              NR_PROBES[16].o1 == NR_PROBES[18].o1 && NR_PROBES[16].drop == NR_PROBES[18].drop &&
-              NR_PROBES[19].var == 0 && NR_PROBES[19].del == 1 && NR_PROBES[21].del == 3 &&
-              NR_PROBES[19].o2 == NR_PROBES[21].o2 && NR_PROBES[19].drop == NR_PROBES[21].drop &&
-              NR_PROBES[22].var == 0 && NR_PROBES[22].del == 1 && NR_PROBES[24].del == 3 &&
-              NR_PROBES[22].o1 == NR_PROBES[24].o1 && NR_PROBES[22].drop == NR_PROBES[24].drop &&
-              NR_PROBES[25].var == 1, "probe families out of step with NR_PROBES");
+__host__ __device__ constexpr bool probe_family_ok(int T)   // T, T+1, T+2 = del 1, 2, 3 of one probe
+{
+    return NR_PROBES[T].var >= 0 && NR_PROBES[T].del == 1 && NR_PROBES[T + 1].del == 2 &&
+           NR_PROBES[T + 2].del == 3 && NR_PROBES[T].var == NR_PROBES[T + 2].var &&
+           NR_PROBES[T].drop == NR_PROBES[T + 2].drop && NR_PROBES[T].o0 == NR_PROBES[T + 2].o0 &&
+           NR_PROBES[T].o1 == NR_PROBES[T + 2].o1 && NR_PROBES[T].o2 == NR_PROBES[T + 2].o2;
+}
+static_assert(NR_PROBES_MAIN - NR_PROBES_COST1 == 18 && probe_family_ok(16) && probe_family_ok(19) &&
+              probe_family_ok(22) && probe_family_ok(25) && probe_family_ok(28) && probe_family_ok(31),
+              "probe families out of step with NR_PROBES");
 
 struct Sector { uint32_t v[8]; };
 
@@ -229,11 +235,13 @@ template <int T>
 __device__ __forceinline__ void probe_one(const uint32_t *__restrict__ bits, uint64_t W, uint64_t &mask)
 {
     constexpr nr_probe_t t = NR_PROBES[T];
-    constexpr uint32_t table = (uint32_t)t.drop << 24;
+    constexpr int layout = nr_probe_layout_of(t);
+    constexpr uint32_t table = (uint32_t)(layout * 4 + t.drop) << 24;
     if constexpr (probe_family_rest(T)) {
         return;                                   // tested by the first variant of its family
     } else if constexpr (probe_family_first(T)) {
-        const uint32_t key = nr_probe_key(W, t) | table;
+        const uint32_t key = nr_key_layout(nr_probe_key(W, t), layout) | table;
+        constexpr int off = t.var == 0 ? t.o0 : (t.var == 1 ? t.o1 : t.o2);   // the varying quarter
         Sector s;
         const uint32_t *sp = bits + ((key >> 8) << 3);
         asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -241,10 +249,10 @@ __device__ __forceinline__ void probe_one(const uint32_t *__restrict__ bits, uin
                        "=r"(s.v[5]), "=r"(s.v[6]), "=r"(s.v[7])
                      : "l"(sp));
         mask |= (uint64_t)sector_bit(s, key & 255u) << T;
-        mask |= (uint64_t)sector_bit(s, nr_quarter(W, t.o0, 2)) << (T + 1);
-        mask |= (uint64_t)sector_bit(s, nr_quarter(W, t.o0, 3)) << (T + 2);
+        mask |= (uint64_t)sector_bit(s, nr_quarter(W, off, 2)) << (T + 1);
+        mask |= (uint64_t)sector_bit(s, nr_quarter(W, off, 3)) << (T + 2);
     } else {
-        const uint32_t key = nr_probe_key(W, t) | table;
+        const uint32_t key = nr_key_layout(nr_probe_key(W, t), layout) | table;
         const uint32_t w = __ldg(bits + (key >> 5));
         mask |= (uint64_t)((w >> (key & 31u)) & 1u) << T;
     }

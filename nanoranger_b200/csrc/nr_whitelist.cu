@@ -50,6 +50,11 @@ __global__ void nr_index_fill_kernel(const uint32_t *__restrict__ lo, uint32_t n
     if (i < n) {
         uint32_t k = keys[i];
         atomicOr(&bits[k >> 5], 1u << (k & 31u));
+        // the same key in the other two bit orders (nr_filter_core.h: bitmap layouts)
+        for (int l = 1; l < NR_BM_LAYOUTS; l++) {
+            uint32_t kl = nr_key_layout(k, l);
+            atomicOr(&bits[(size_t)l * 4 * NR_BM_WORDS + (kl >> 5)], 1u << (kl & 31u));
+        }
         uint32_t e = vals[i];
         ents[i] = make_uint2(e, lo[e]);
         heads[i] = (i == 0 || keys[i - 1] != k) ? 1u : 0u;
@@ -157,15 +162,15 @@ extern "C" int nr_whitelist_create(const char *cores, uint64_t n, uint32_t core_
         size_t bmb = (size_t)(NR_BM_WORDS + 1) * sizeof(uint32_t);
         uint32_t nn = (uint32_t)n;
         uint32_t blocks = (nn + 255) / 256;
-        // the four key bitmaps are one allocation, 2^19 words apart: a probe addresses bit
-        // (dropped quarter << 24 | key) from a single base pointer
+        // the key bitmaps (4 dropped quarters x NR_BM_LAYOUTS bit orders) are one allocation, 2^19
+        // words apart: a probe addresses bit (table id << 24 | key) from a single base pointer
         uint32_t *bits_all = nullptr;
-        if (cudaMalloc(&bits_all, (size_t)4 * NR_BM_WORDS * sizeof(uint32_t) + 256) != cudaSuccess) {
+        if (cudaMalloc(&bits_all, (size_t)4 * NR_BM_LAYOUTS * NR_BM_WORDS * sizeof(uint32_t) + 256) != cudaSuccess) {
             cudaFree(d_keys); cudaFree(d_vals); cudaFree(d_heads);
             nr_set_error("cudaMalloc seed index");
             return fail(NR_ENOMEM);
         }
-        cudaMemset(bits_all, 0, (size_t)4 * NR_BM_WORDS * sizeof(uint32_t) + 256);
+        cudaMemset(bits_all, 0, (size_t)4 * NR_BM_LAYOUTS * NR_BM_WORDS * sizeof(uint32_t) + 256);
         for (int j = 0; j < 4; j++) w->d_bits[j] = bits_all + (size_t)j * NR_BM_WORDS;
         for (int j = 0; j < 4; j++) {
             if (cudaMalloc(&w->d_rank[j], bmb) != cudaSuccess ||
@@ -175,7 +180,7 @@ extern "C" int nr_whitelist_create(const char *cores, uint64_t n, uint32_t core_
                 nr_set_error("cudaMalloc seed index");
                 return fail(NR_ENOMEM);
             }
-            w->bytes += 2 * bmb + n * sizeof(uint2) + (n + 1) * sizeof(uint32_t);
+            w->bytes += (size_t)(1 + NR_BM_LAYOUTS) * bmb + n * sizeof(uint2) + (n + 1) * sizeof(uint32_t);
             nr_index_keys_kernel<<<blocks, 256>>>(w->d_lo, nn, j, d_keys, d_vals);
             thrust::stable_sort_by_key(thrust::device, thrust::device_pointer_cast(d_keys),
                                        thrust::device_pointer_cast(d_keys) + n,
