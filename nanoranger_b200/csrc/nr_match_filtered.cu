@@ -8,16 +8,22 @@
 // Mapping.  One warp owns a tile of 32 consecutive candidates: lane l loads candidate l's
 // 128-bit packed record (one coalesced 512 B request per warp) and stores its 8 B of results;
 // the candidates of the tile are then resolved one after another by the whole warp:
-//   probe    lane = (strand, slot position); the 34 probes of a slot are unrolled with
-//            compile-time offsets; each is one 4 B read of the L2-resident 24-bit key bitmap;
-//            the hit bits of a lane are collected in a register mask
-//   queue    one warp scan per 32 slots places the hits in a per-warp shared-memory queue
-//            (key rank = rank word + popc of the bitmap word below the key)
-//   verify   32 queued hits are expanded into the index rows sharing their keys (prefix sum over
-//            the row counts); lane = one row: reads {entry, core} and scores it with
-//            nr_verify16: a furthest-reaching-diagonal walk from the end of the core the probe
-//            pins (exact in the read interior), the 3-level shift-and automaton over the <= 27
-//            read rows around the slot where the core may hang over a read end
+//   probe    lane = (strand, slot position); the probes of a slot are unrolled with compile-time
+//            offsets; each is one read of the L2-resident key bitmaps (one base pointer, three
+//            bit orders so that probe families share a 32 B sector; 256-bit loads for the
+//            "5-mer minus one base" triples); the hit bits of a lane are collected in a mask
+//   stages   the probe table is walked in three stages over ALL slots -- probe 0 (complete for
+//            cost 0), probes 1..15 (complete for cost <= 1), the two-event probes -- and the
+//            queue is drained after each; a candidate whose best pair is already at a cost the
+//            finished stages are complete for stops there
+//   queue    one ballot (or one scan when a lane holds several hits) places the hits in a
+//            per-warp shared-memory queue as (probe, strand, slot)
+//   verify   up to 32 queued hits are expanded into the index rows sharing their keys (key rank =
+//            rank word + popc of the bitmap word below the key; prefix sum over the row counts);
+//            lane = one row: reads {entry, core} and scores it with nr_verify16: a furthest-
+//            reaching-diagonal walk from the end of the core the probe pins (exact in the read
+//            interior), the 3-level shift-and automaton over the <= 27 read rows around the
+//            slot where the core may hang over a read end
 //   merge    best cost, the distinct (entry, strand) pairs attaining it (kept one per lane),
 //            smallest UMI row per pair
 // Candidates the filter cannot take (contain N, shorter than NR_FILTER_MIN_LEN, more than 32

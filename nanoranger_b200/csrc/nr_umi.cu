@@ -35,6 +35,7 @@ struct UmiWs {
     uint32_t *rep_reads;                   // per distinct: reads of the cluster it represents
     uint32_t *rep_flag, *rep_pos;          // per distinct
     uint32_t *rep_u, *rep_c;               // per group slot: UMI / reads of the representatives found so far
+    uint32_t *htab;                        // 4 slots per distinct UMI: hash sets of representatives (huge groups)
     uint32_t *totals;                      // [0] n distinct, [1] n groups, [2] n reps
     void *cub_tmp;
     size_t cub_bytes;
@@ -52,6 +53,7 @@ size_t carve(uint8_t *base, uint64_t n, UmiWs *w, size_t cub_bytes)
                         &w->grp_first, &w->du_rank_order, &w->du_rep, &w->rep_reads,
                         &w->rep_flag, &w->rep_pos, &w->rep_u, &w->rep_c};
     for (auto p : a32) *p = (uint32_t *)take(n4);
+    w->htab = (uint32_t *)take(4 * n4);
     w->key_a = (uint64_t *)take(n8);
     w->key_b = (uint64_t *)take(n8);
     w->totals = (uint32_t *)take(256);
@@ -141,6 +143,7 @@ __global__ void k_order_keys(const uint32_t *du_first, const uint32_t *grp_id, c
 }
 
 #define NR_UMI_LARGE 96      // groups with more distinct UMIs go to the block-wide kernel
+#define NR_UMI_HUGE 2048     // ... and beyond this the representatives are found through a hash set
 
 __device__ __forceinline__ bool umi_joins(uint32_t rep_umi, uint32_t rep_cnt, uint32_t u,
                                           uint32_t cnt, int max_dist)
@@ -196,15 +199,24 @@ k_cluster_small(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__
     }
 }
 
-// one block per large group.  Same walk, 32 UMIs at a time: (1) all threads compare the chunk
-// with the representatives found so far (earliest qualifying one wins: atomicMin on its slot),
-// (2) one warp settles the chunk in walk order -- a UMI without an earlier representative may
-// still join a representative created earlier in the same chunk.
+// one block per large group.  Same walk, 32 UMIs at a time: (1) all threads look for the earliest
+// representative each chunk member can join -- by comparing the chunk with every representative
+// found so far (atomicMin on its slot), or, in huge groups, by looking the 3 * umi_len Hamming
+// neighbours of each member up in a hash set of the representatives (the work per chunk then
+// no longer grows with the group); (2) one warp settles the chunk in walk order -- a UMI without
+// an earlier representative may still join a representative created earlier in the same chunk;
+// (3) new representatives are appended (and inserted in the hash set).
+__device__ __forceinline__ uint32_t umi_hash(uint32_t u, uint32_t bits)
+{
+    return (u * 0x9E3779B1u) >> (32u - bits);
+}
+
 __global__ void __launch_bounds__(256)
 k_cluster_large(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ du_first,
                 const uint32_t *__restrict__ grp_first, const uint32_t *__restrict__ totals,
-                int max_dist, uint32_t *__restrict__ order, uint32_t *__restrict__ du_rep,
-                uint32_t *__restrict__ rep_u, uint32_t *__restrict__ rep_c)
+                int max_dist, int umi_len, uint32_t *__restrict__ order,
+                uint32_t *__restrict__ du_rep, uint32_t *__restrict__ rep_u,
+                uint32_t *__restrict__ rep_c, uint32_t *__restrict__ htab)
 {
     __shared__ uint32_t c_d[32], c_u[32], c_c[32], c_best[32];
     __shared__ uint32_t s_nrep;
@@ -215,6 +227,11 @@ k_cluster_large(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__
         const uint32_t d0 = grp_first[g], d1 = grp_first[g + 1];
         const uint32_t nd = d1 - d0;
         if (nd <= NR_UMI_LARGE) continue;
+        const bool hashed = nd > NR_UMI_HUGE;
+        // hash set of this group: the smallest power of two >= 2 nd slots out of its 4 nd
+        const uint32_t hbits = 32u - (uint32_t)__clz((int)(2u * nd - 1u));
+        const uint32_t hmask = (1u << hbits) - 1u;
+        uint32_t *tab = htab + 4ull * d0;
         __syncthreads();
         if (threadIdx.x == 0) s_nrep = 0;
         for (uint32_t r0 = 0; r0 < nd; r0 += 32) {
@@ -231,12 +248,30 @@ k_cluster_large(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__
             }
             __syncthreads();
             const uint32_t nrep = s_nrep;
-            for (uint32_t q = threadIdx.x; q < nrep; q += blockDim.x) {
-                const uint32_t ru = rep_u[d0 + q], rc = rep_c[d0 + q];
+            if (hashed) {
+                const uint32_t per = 3u * (uint32_t)umi_len;
+                for (uint32_t i = threadIdx.x; i < in_chunk * per; i += blockDim.x) {
+                    const uint32_t k = i / per, r = i - k * per;
+                    const uint32_t key = c_u[k] ^ ((r % 3u + 1u) << (2u * (r / 3u)));
+                    uint32_t slot = umi_hash(key, hbits);
+                    for (;;) {
+                        const uint32_t q = tab[slot];
+                        if (q == 0xFFFFFFFFu) break;
+                        if (rep_u[d0 + q] == key) {
+                            if (rep_c[d0 + q] + 1 >= 2 * c_c[k]) atomicMin(&c_best[k], q);
+                            break;
+                        }
+                        slot = (slot + 1u) & hmask;
+                    }
+                }
+            } else {
+                for (uint32_t q = threadIdx.x; q < nrep; q += blockDim.x) {
+                    const uint32_t ru = rep_u[d0 + q], rc = rep_c[d0 + q];
 #pragma unroll 8
-                for (uint32_t k = 0; k < 32; k++)
-                    if (k < in_chunk && umi_joins(ru, rc, c_u[k], c_c[k], max_dist))
-                        atomicMin(&c_best[k], q);
+                    for (uint32_t k = 0; k < 32; k++)
+                        if (k < in_chunk && umi_joins(ru, rc, c_u[k], c_c[k], max_dist))
+                            atomicMin(&c_best[k], q);
+                }
             }
             __syncthreads();
             if (threadIdx.x < 32) {
@@ -267,6 +302,11 @@ k_cluster_large(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__
                         const uint32_t pos = nrep + (uint32_t)__popc(R & ((1u << lane) - 1u));
                         du_rep[d] = d;
                         order[d0 + pos] = d; rep_u[d0 + pos] = u; rep_c[d0 + pos] = c;
+                        if (hashed) {
+                            uint32_t slot = umi_hash(u, hbits);
+                            while (atomicCAS(&tab[slot], 0xFFFFFFFFu, pos) != 0xFFFFFFFFu)
+                                slot = (slot + 1u) & hmask;
+                        }
                     }
                 }
                 if (lane == 0) s_nrep = nrep + (uint32_t)__popc(R);
@@ -390,10 +430,12 @@ extern "C" int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_ge
     }
     k_cluster_small<<<sms * 8, 256, 0, st>>>(w.s_umi, w.du_first, w.grp_first, w.totals, max_dist,
                                              w.du_rank_order, w.du_rep);
-    if (max_dist > 0)
+    if (max_dist > 0) {
+        NR_CHECK_CUDA(cudaMemsetAsync(w.htab, 0xFF, (size_t)(n + 1) * 16, st));
         k_cluster_large<<<sms * 4, 256, 0, st>>>(w.s_umi, w.du_first, w.grp_first, w.totals,
-                                                 max_dist, w.du_rank_order, w.du_rep, w.rep_u,
-                                                 w.rep_c);
+                                                 max_dist, umi_len, w.du_rank_order, w.du_rep,
+                                                 w.rep_u, w.rep_c, w.htab);
+    }
     NR_CHECK_CUDA(cudaMemsetAsync(w.rep_reads, 0, (size_t)(n + 1) * 4, st));
     k_rep_reads<<<sms * 8, 256, 0, st>>>(w.du_first, w.du_rep, w.totals, w.rep_reads, w.rep_flag);
     // rep_flag is defined for the first n_distinct entries only; the scan also runs over the

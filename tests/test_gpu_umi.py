@@ -150,3 +150,19 @@ def test_umi_collapse_millions_of_records(cuda_device):
     assert r["n_groups"] == len(uk)
     assert int(r["g_reads"].sum()) == n and np.array_equal(r["g_reads"], cnt.astype(np.uint32))
     assert np.array_equal(r["rep_umi"], um)
+
+
+def test_umi_collapse_huge_group_hash_path(cuda_device, oracle):
+    """one (barcode, gene) group with ~15 000 distinct 12-nt UMIs (deeply sequenced cell x highly
+    expressed gene, 40 % of the reads carrying a UMI error): the representatives are found through
+    the hash set; the answer equals the sequential walk of the oracle."""
+    rng = np.random.default_rng(21)
+    n = 60000
+    true = rng.integers(0, 1 << 24, 3000).astype(np.uint32)
+    um = true[(rng.zipf(1.2, n) % 3000)]
+    flip = rng.random(n) < 0.4
+    um = np.where(flip, um ^ (rng.integers(1, 4, n).astype(np.uint32) << (2 * rng.integers(0, 12, n)).astype(np.uint32)), um)
+    bc = np.where(rng.random(n) < 0.9, 5, rng.integers(0, 30, n)).astype(np.uint32)
+    gene = np.zeros(n, np.uint32)
+    _check(oracle, bc, gene, um.astype(np.uint32), 12, 1)
+    _check(oracle, bc, gene, um.astype(np.uint32), 12, 0)
