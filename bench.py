@@ -388,6 +388,13 @@ def main():
     torch.cuda.synchronize()
     counters = wl.counters(ws)
     assigned = int(out.assigned(min_score).sum().item())
+    # accuracy against the generator's ground truth (reported, not a parity criterion: the scoring
+    # the reference configures lets a read with barcode errors sit closer to a neighbouring entry)
+    a_np = out.assigned(min_score).cpu().numpy()
+    t_np = d["true_idx"]
+    pos = a_np & (t_np >= 0)
+    accuracy = {"assigned_to_true_barcode": float((out.idx.cpu().numpy()[pos] == t_np[pos]).mean()) if pos.any() else None,
+                "negatives_assigned": float(a_np[t_np < 0].mean()) if (t_np < 0).any() else None}
 
     # end to end through the host-buffer C-ABI call (H2D + pack + match + D2H inside the timed
     # region); inputs and outputs live in pinned host memory, as the contract asks
@@ -516,6 +523,7 @@ def main():
                              "gcups_equivalent is the filtered path's candidates/s x cells a brute force would do"},
         "assigned_per_sec": float(tot.item()) / (ms_step * 1e-3),
         "assigned_fraction": float(tot.item()) / (world * B),
+        "accuracy_rank0": accuracy,
         "counters_per_candidate": {k: v / B for k, v in counters.items()},
         "e2e": {"value": e2e_value, "unit": "candidates/s", "h2d_bytes_per_step": int(n_bytes_in),
                 "d2h_bytes_per_step": int(8 * B), "steps": e2e_steps,
