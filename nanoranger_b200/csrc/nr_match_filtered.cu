@@ -135,11 +135,13 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, A
     if (have && h_p + nr_probe_first(t) >= 0 && h_p + nr_probe_end(t) <= m) {
         const uint32_t key = nr_probe_key(nr_window64(sm.rdp[h_strand], h_p), t);
         const uint32_t w = __ldg(T4.bits[0] + (((d << 24) | key) >> 5));
-        const uint32_t kr = __ldg(T4.rank[d] + (key >> 5)) +
+        // rank / kstart / rows are touched once per hit: keep them out of L1 (L2 only) so that the
+        // bitmap sectors stay
+        const uint32_t kr = __ldcg(T4.rank[d] + (key >> 5)) +
                             (uint32_t)__popc(w & ((1u << (key & 31u)) - 1u));
         const uint32_t *ks = T4.kstart[d] + kr;
-        start = __ldg(ks);
-        rows = __ldg(ks + 1) - start;
+        start = __ldcg(ks);
+        rows = __ldcg(ks + 1) - start;
         if (COUNT) acc.c_hits++;
     }
     // exclusive prefix of the row counts
@@ -172,7 +174,7 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, A
             const uint32_t od = (uint32_t)ot.drop;
             const int strand = (int)((o_item >> 24) & 1u);
             const int p = (int)(o_item >> 25) - 16;
-            const uint2 e = __ldg(T4.ents[od] + o_start + (g - o_excl));
+            const uint2 e = __ldcg(T4.ents[od] + o_start + (g - o_excl));
             cost = nr_verify16(sm.rdp[strand], m, e.y, P.padL, P.padR, p, ot, &u);
             k = (e.x << 1) | (uint32_t)strand;
             if (COUNT) { acc.c_ver++; acc.c_pass += cost < 3; }
@@ -357,7 +359,7 @@ nr_match_filtered_kernel(const nr_filter_params P)
         {
             const uint64_t mine = tile * 32 + lane;
             uint4 b = make_uint4(0u, 0u, 0u, 0u);
-            if (mine < P.n_cand) { b = __ldg(P.bases + mine); mt = P.meta[mine]; }
+            if (mine < P.n_cand) { b = __ldcs(P.bases + mine); mt = P.meta[mine]; }
             __syncwarp();
             sm.tile[lane] = b;
             __syncwarp();
