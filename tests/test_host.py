@@ -137,3 +137,27 @@ def test_synth_is_seeded_and_shaped():
         assert q[:14] == "CGCTCTTCCGATCT" and q[14:30] == bytes(wl[clean["true_idx"][i]]).decode()
     sw = whitelists.synthetic_whitelist(5000, seed=3)
     assert len({bytes(r) for r in sw}) == 5000
+
+
+def test_sam_alignment_attributes_follow_pysam(tmp_path):
+    """extract.Aln: the pysam attributes the reference's extractors read (utils.py:112-127)."""
+    from nanoranger_b200 import extract
+    seq = "A" * 10 + "C" * 50 + "G" * 7
+    sam = ("@HD\tVN:1.6\n@SQ\tSN:T1\tLN:500\n"
+           f"r1\t0\tT1\t101\t60\t10S30=2X5I10=3D3=7S\t*\t0\t0\t{seq}\t{'I' * len(seq)}\tNM:i:10\tAS:i:77\ttp:A:P\n"
+           f"r2\t2064\tT1\t5\t60\t5H20=5H\t*\t0\t0\t{'T' * 20}\t{'#' * 20}\tAS:i:40\n"
+           "r3\t4\t*\t0\t0\t*\t*\t0\t0\tACGT\tIIII\n")
+    p = tmp_path / "x_trns.sam"
+    p.write_text(sam)
+    recs = extract.read_alignments(str(p))
+    assert [r.qname for r in recs] == ["r1", "r2"]                    # unmapped record skipped
+    a = recs[0]
+    assert (a.query_alignment_start, a.query_alignment_end, a.qlen, a.rlen) == (10, 60, 50, 67)
+    assert (a.reference_start, a.reference_end) == (100, 100 + 30 + 2 + 10 + 3 + 3)
+    assert a.get_tag("AS") == 77 and a.get_tag("tp") == "P" and a.flag == 0
+    with pytest.raises(KeyError):
+        a.get_tag("XX")
+    b = recs[1]                                                       # hard clips are not in SEQ
+    assert (b.query_alignment_start, b.query_alignment_end, b.rlen) == (0, 20, 20)
+    assert extract.rev("AACGTN") == "NACGTT"
+    assert extract._mod_coords(b) == (0, 20)
