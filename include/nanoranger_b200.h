@@ -176,6 +176,21 @@ int nr_hw_search_host(const char *text, const uint64_t *offsets, uint64_t n, con
                       int m, int k, int wildcard_n, int8_t *ed, int32_t *first, int32_t *last,
                       int32_t *nloc, int device);
 
+/* ---- SAM output (host only) -------------------------------------------------------------------
+ * Replaces the output stage of scripts/barcode_align.sh:14-41: writes `path` with one record per
+ * candidate whose best score is reached by exactly one (entry, strand) pair (STAR:
+ * --outFilterMultimapNmax 1, --outSAMunmapped None, --outSAMmode NoQS), carrying the fields
+ * utils.process_matching_* read: QNAME FLAG RNAME POS 255 CIGAR * 0 0 SEQ * NH HI AS.  POS/CIGAR
+ * are anchored so that reference column pad_l + core_len pairs with read base umi_q.
+ * names / seqs / ref_names: concatenated bytes with n + 1 (n_ref + 1) offsets.
+ * header_full != 0: one @SQ per whitelist entry (STAR's layout), else only the entries used. */
+int nr_sam_write(const char *path, int header_full, const char *names, const uint64_t *name_off,
+                 const char *seqs, const uint64_t *seq_off, uint64_t n, const int32_t *idx,
+                 const int8_t *score, const uint8_t *nbest, const uint8_t *flags,
+                 const uint8_t *umi_q, const char *ref_names, const uint64_t *ref_off,
+                 uint64_t n_ref, uint32_t pad_l, uint32_t core_len, uint32_t pad_r,
+                 uint64_t *n_written);
+
 /* ---- measurement support -------------------------------------------------------------------
  * INT-pipe roofline denominator: runs a dependent LOP3/IADD3 chain on
  * every SM for `iters` iterations and returns executed integer thread-ops per second. */

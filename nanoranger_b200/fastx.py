@@ -67,6 +67,58 @@ def read_fasta(path: str):
     return names, np.frombuffer(b"".join(chunks), np.uint8).copy(), offsets
 
 
+def read_fasta_raw(path: str):
+    """2-line FASTA(.gz) without any per-record Python work: -> (names u8 buffer, name offsets
+    u64 [n+1], seqs u8 buffer, seq offsets u64 [n+1]); names are cut at the first space.  Falls
+    back to read_fasta() for multi-line files."""
+    raw = _read_bytes(path)
+    if not raw:
+        z = np.zeros(0, np.uint8)
+        return z, np.zeros(1, np.uint64), z, np.zeros(1, np.uint64)
+    buf = np.frombuffer(raw, dtype=np.uint8)
+    if buf[-1] != 10:
+        buf = np.concatenate([buf, np.array([10], np.uint8)])
+    nl = np.flatnonzero(buf == 10)
+    starts = np.concatenate([[0], nl[:-1] + 1])
+    ends = nl.copy()
+    ends = ends - ((ends > starts) & (buf[np.maximum(ends - 1, 0)] == 13))
+    nonempty = ends > starts
+    starts, ends = starts[nonempty], ends[nonempty]
+    is_hdr = buf[starts] == ord(">")
+    if not (len(starts) % 2 == 0 and is_hdr[0::2].all() and not is_hdr[1::2].any()):
+        names, seqs, off = read_fasta(path)
+        nb, no = _pack_names(names)
+        return nb, no, seqs, off
+    hs, he = starts[0::2] + 1, ends[0::2].copy()
+    # cut names at the first space: position of the first space at or after the header start
+    sp = np.flatnonzero(buf == 32)
+    if len(sp):
+        k = np.searchsorted(sp, hs)
+        first = np.where(k < len(sp), sp[np.minimum(k, len(sp) - 1)], np.iinfo(np.int64).max)
+        he = np.minimum(he, first)
+
+    def gather(a, b):
+        lens = (b - a).astype(np.uint64)
+        off = np.zeros(len(a) + 1, np.uint64)
+        np.cumsum(lens, out=off[1:])
+        # +1 at every start, -1 at every end (starts and ends never coincide: a < b < next a)
+        keep = np.zeros(len(buf) + 1, np.int8)
+        keep[a] = 1
+        keep[b] -= 1
+        return np.ascontiguousarray(buf[np.cumsum(keep[:-1], dtype=np.int8) > 0]), off
+
+    nb, no = gather(hs, he)
+    sb, so = gather(starts[1::2], ends[1::2])
+    return nb, no, sb, so
+
+
+def _pack_names(names):
+    b = [n.encode("ascii", "replace") for n in names]
+    off = np.zeros(len(b) + 1, np.uint64)
+    np.cumsum(np.fromiter((len(x) for x in b), np.uint64, len(b)), out=off[1:])
+    return (np.frombuffer(b"".join(b), np.uint8).copy() if b else np.zeros(0, np.uint8)), off
+
+
 def write_fasta(path: str, names, seqs, gz: bool | None = None) -> None:
     gz = path.endswith(".gz") if gz is None else gz
     op = gzip.open if gz else open

@@ -102,3 +102,66 @@ def read_sam(path: str):
             out.append({"qname": t[0], "flag": int(t[1]), "rname": t[2], "pos": int(t[3]),
                         "cigar": t[5], "seq": t[9], "AS": a_s})
     return out
+
+
+def read_sam_table(path: str):
+    """Column-wise reader for large SAM files (pandas' C parser): -> dict of numpy arrays
+    qname, flag, rname, pos, cigar, seq (object / int64) and AS (int64; -1 where the tag is
+    missing).  Same content as read_sam()."""
+    import pandas as pd
+    n_hdr = 0
+    first = None
+    with open(path) as f:
+        for ln in f:
+            if ln.startswith("@"):
+                n_hdr += 1
+                continue
+            first = ln.rstrip("\n").split("\t")
+            break
+    empty = {k: np.zeros(0, object) for k in ("qname", "rname", "cigar", "seq")}
+    empty.update({k: np.zeros(0, np.int64) for k in ("flag", "pos", "AS")})
+    if first is None:
+        return empty
+    as_col = next((j for j in range(11, len(first)) if first[j].startswith("AS:i:")), None)
+    cols = [0, 1, 2, 3, 5, 9] + ([as_col] if as_col is not None else [])
+    try:
+        df = pd.read_csv(path, sep="\t", header=None, skiprows=n_hdr, usecols=cols, quoting=3,
+                         dtype={0: str, 1: np.int64, 2: str, 3: np.int64, 5: str, 9: str},
+                         na_filter=False, engine="c")
+        AS = (df[as_col].str.slice(5).astype(np.int64).to_numpy() if as_col is not None
+              else np.full(len(df), -1, np.int64))
+        if as_col is not None and not df[as_col].str.startswith("AS:i:").all():
+            raise ValueError("AS tag not in a fixed column")
+    except Exception:
+        recs = read_sam(path)                       # irregular file: record-wise reader
+        return {"qname": np.array([r["qname"] for r in recs], object),
+                "flag": np.array([r["flag"] for r in recs], np.int64),
+                "rname": np.array([r["rname"] for r in recs], object),
+                "pos": np.array([r["pos"] for r in recs], np.int64),
+                "cigar": np.array([r["cigar"] for r in recs], object),
+                "seq": np.array([r["seq"] for r in recs], object),
+                "AS": np.array([-1 if r["AS"] is None else r["AS"] for r in recs], np.int64)}
+    return {"qname": df[0].to_numpy(object), "flag": df[1].to_numpy(), "rname": df[2].to_numpy(object),
+            "pos": df[3].to_numpy(), "cigar": df[5].to_numpy(object), "seq": df[9].to_numpy(object),
+            "AS": AS}
+
+
+_SIMPLE = re.compile(r"^(?:(\d+)I)?(\d+)M(?:(\d+)I)?$")
+
+
+def query_index_at_many(pos, cigar, ref_col: int):
+    """query_index_at() for arrays; -1 where the column is not paired.  CIGARs of the anchored
+    form [aI]bM[cI] (everything this package writes) are handled without a per-record parse."""
+    out = np.full(len(pos), -1, np.int64)
+    for i, (p, c) in enumerate(zip(pos, cigar)):
+        m = _SIMPLE.match(c)
+        if m:
+            lead = int(m.group(1) or 0)
+            mid = int(m.group(2))
+            r = int(p) - 1
+            if r <= ref_col < r + mid:
+                out[i] = lead + ref_col - r
+        else:
+            q = query_index_at(int(p), c, ref_col)
+            out[i] = -1 if q is None else q
+    return out

@@ -194,19 +194,33 @@ def barcode_align(input_fastq, genome_dir, out_name, threads=1, *ignored, device
     and leaves the rest out of the SAM -- the only file that can tell is the low-score tail of
     `_barcode_scores.csv`, which the reference merely plots.  Default: AUTO up to AUTO_MODE_MAX
     candidates, FILTERED above (announced on stdout)."""
+    import ctypes as C
+    from . import _lib
     from ._lib import NR_MODE_FILTERED
     wl, ref_names = load_genome(genome_dir, device)
     try:
-        names, seqs, offsets = fastx.read_fasta(input_fastq)
+        # no per-record Python from here to the file: raw FASTA buffers -> nr_match_host ->
+        # nr_sam_write (same bytes as samio.write_sam(match_records(...)), ~50x faster)
+        nbuf, noff, seqs, offsets = fastx.read_fasta_raw(input_fastq)
+        n = len(offsets) - 1
         if mode is None:
             mode = NR_MODE_AUTO
-            if len(names) > AUTO_MODE_MAX and wl.has_index:
+            if n > AUTO_MODE_MAX and wl.has_index:
                 mode = NR_MODE_FILTERED
-                print(f"nanoranger_b200: {len(names)} candidates > {AUTO_MODE_MAX}: reads scoring below "
+                print(f"nanoranger_b200: {n} candidates > {AUTO_MODE_MAX}: reads scoring below "
                       f"{wl.core_len - 2} are not resolved (pass mode=NR_MODE_AUTO to resolve them)")
-        recs = match_records(wl, names, seqs, offsets, ref_names, mode=mode)
-        n = samio.write_sam(f"{out_name}.sam", ref_names, wl.pad_l + wl.core_len + wl.pad_r, recs,
-                            header=header)
+        res = wl.match_host(seqs, offsets, min_score=wl.core_len - 2, mode=mode)
+        rbuf, roff = fastx._pack_names(ref_names)
+        if n == 0:
+            nbuf = seqs = np.zeros(1, np.uint8)
+        written = C.c_uint64(0)
+        _lib.check(_lib.lib().nr_sam_write(
+            f"{out_name}.sam".encode(), 1 if header == "full" else 0, nbuf.ctypes.data,
+            noff.ctypes.data, seqs.ctypes.data, offsets.ctypes.data, n, res.idx.ctypes.data,
+            res.score.ctypes.data, res.nbest.ctypes.data, res.flags.ctypes.data,
+            res.umi_q.ctypes.data, rbuf.ctypes.data, roff.ctypes.data, len(ref_names), wl.pad_l,
+            wl.core_len, wl.pad_r, C.byref(written)), "nr_sam_write")
+        n = int(written.value)
     finally:
         wl.close()
     return n
@@ -217,17 +231,18 @@ def barcode_align(input_fastq, genome_dir, out_name, threads=1, *ignored, device
 def _parse_matching(sample, outdir, thr, umi_ref_col, umi_len, exact_len):
     """Common front half of process_matching_* (utils.py:697-718 and twins): AS list over all
     records, accepted (name, bc, umi) triples, short-UMI count."""
-    recs = samio.read_sam(f"{outdir}/{sample}_matching.sam")
-    all_AS = np.array([[r["AS"], r["flag"]] for r in recs], dtype=np.int64).reshape(-1, 2)
+    t = samio.read_sam_table(f"{outdir}/{sample}_matching.sam")
+    all_AS = np.stack([t["AS"], t["flag"]], axis=1).astype(np.int64).reshape(-1, 2)
+    sel = np.flatnonzero((t["AS"] >= thr) & (t["flag"] == 0))
+    q = samio.query_index_at_many(t["pos"][sel], t["cigar"][sel], umi_ref_col)
     triples, bad = [], 0
-    for r in recs:
-        if r["AS"] >= thr and r["flag"] == 0:
-            q = samio.query_index_at(r["pos"], r["cigar"], umi_ref_col)
-            umi = r["seq"][q:q + umi_len] if q is not None else "N"
-            if (len(umi) != umi_len) if exact_len else (len(umi) < umi_len):
-                bad += 1
-            else:
-                triples.append((r["qname"], r["rname"], umi))
+    for i, qi in zip(sel, q):
+        # aligned_pairs lookup failed -> the reference's `except: umi = "N"` (utils.py:709-710)
+        umi = t["seq"][i][qi:qi + umi_len] if qi >= 0 else "N"
+        if (len(umi) != umi_len) if exact_len else (len(umi) < umi_len):
+            bad += 1
+        else:
+            triples.append((t["qname"][i], t["rname"][i], umi))
     print("number of short UMI reads = ", bad)
     return all_AS, triples
 

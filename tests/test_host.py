@@ -161,3 +161,77 @@ def test_sam_alignment_attributes_follow_pysam(tmp_path):
     assert (b.query_alignment_start, b.query_alignment_end, b.rlen) == (0, 20, 20)
     assert extract.rev("AACGTN") == "NACGTT"
     assert extract._mod_coords(b) == (0, 20)
+
+
+def test_native_sam_writer_equals_python_writer(tmp_path):
+    """nr_sam_write (C++) writes the bytes samio.write_sam(match_records-style records) writes."""
+    import ctypes as C
+    from nanoranger_b200 import _lib, fastx, samio
+    from nanoranger_b200._lib import NR_FLAG_RC, NR_FLAG_TOO_LONG, NR_UMI_NONE
+    rng = np.random.default_rng(12)
+    n, n_ref, pad_l, L, pad_r = 3000, 40, 30, 16, 40
+    ref_names = ["".join("ACGT"[i] for i in rng.integers(0, 4, 16)) for _ in range(n_ref)]
+    seqs = ["".join("ACGTN"[i] for i in rng.integers(0, 5, int(rng.integers(0, 65)))) for _ in range(n)]
+    names = [f"read{i}-x_{i}_{i + 7}_0_G{i % 3}|T.1_9" for i in range(n)]
+    idx = rng.integers(0, n_ref, n).astype(np.int32)
+    score = rng.integers(-5, 17, n).astype(np.int8)
+    nbest = rng.choice([0, 1, 1, 1, 2], n).astype(np.uint8)
+    flags = (rng.choice([0, 0, 0, NR_FLAG_RC, NR_FLAG_TOO_LONG], n)).astype(np.uint8)
+    umi_q = np.where(rng.random(n) < 0.2, NR_UMI_NONE, rng.integers(0, 64, n)).astype(np.uint8)
+    recs = []
+    for i in range(n):
+        if nbest[i] == 1 and not flags[i] & NR_FLAG_TOO_LONG:
+            rc = bool(flags[i] & NR_FLAG_RC)
+            u = int(umi_q[i])
+            pos, cig = samio.anchored_alignment(len(seqs[i]), -1 if (u == NR_UMI_NONE or rc) else u, pad_l, L, pad_r)
+            s = samio.revcomp_bytes(seqs[i].encode()).decode() if rc else seqs[i]
+            recs.append((names[i], 16 if rc else 0, int(idx[i]), pos, cig, s, int(score[i])))
+    for header in ("used", "full"):
+        samio.write_sam(str(tmp_path / "py.sam"), ref_names, pad_l + L + pad_r, recs, header=header)
+        nb, no = fastx._pack_names(names)
+        sb, so = fastx._pack_names(seqs)
+        rb, ro = fastx._pack_names(ref_names)
+        w = C.c_uint64()
+        rc_ = _lib.lib().nr_sam_write(str(tmp_path / "c.sam").encode(), header == "full", nb.ctypes.data,
+                                      no.ctypes.data, sb.ctypes.data, so.ctypes.data, n, idx.ctypes.data,
+                                      score.ctypes.data, nbest.ctypes.data, flags.ctypes.data,
+                                      umi_q.ctypes.data, rb.ctypes.data, ro.ctypes.data, n_ref, pad_l, L,
+                                      pad_r, C.byref(w))
+        assert rc_ == 0 and w.value == len(recs)
+        assert (tmp_path / "c.sam").read_bytes() == (tmp_path / "py.sam").read_bytes()
+    # the raw FASTA reader agrees with the record reader
+    fa = tmp_path / "x.fa.gz"
+    with gzip.open(fa, "wt") as f:
+        for nm, s in zip(names, seqs):
+            f.write(f">{nm} trailing words\n{s}\n" if s else f">{nm}\nN\n")
+    a_names, a_seq, a_off = fastx.read_fasta(str(fa))
+    nb, no, sb, so = fastx.read_fasta_raw(str(fa))
+    assert np.array_equal(a_seq, sb) and np.array_equal(a_off, so)
+    raw = nb.tobytes().decode()
+    assert [raw[int(no[i]):int(no[i + 1])] for i in range(len(no) - 1)] == a_names
+
+
+def test_sam_table_reader_equals_record_reader(tmp_path):
+    from nanoranger_b200 import samio
+    recs = [("a_1_2_0_T", 0, 0, 17, "3I40M2I", "ACGT" * 11 + "A", 15), ("b", 16, 1, 1, "50M", "C" * 50, 14),
+            ("c x", 0, 1, 31, "12M", "G" * 12, -3)]
+    p = str(tmp_path / "m.sam")
+    samio.write_sam(p, ["BC1", "BC2"], 86, recs)
+    t = samio.read_sam_table(p)
+    r = samio.read_sam(p)
+    assert [x["qname"] for x in r] == list(t["qname"]) and [x["AS"] for x in r] == list(t["AS"])
+    assert [x["cigar"] for x in r] == list(t["cigar"]) and [x["pos"] for x in r] == list(t["pos"])
+    assert [x["seq"] for x in r] == list(t["seq"]) and [x["rname"] for x in r] == list(t["rname"])
+    for col in (0, 16, 20, 45, 46, 60):
+        many = samio.query_index_at_many(t["pos"], t["cigar"], col)
+        one = [samio.query_index_at(x["pos"], x["cigar"], col) for x in r]
+        assert list(many) == [-1 if v is None else v for v in one]
+    # STAR-style line: AS not at the same column as ours, complex CIGAR
+    with open(p, "a") as f:
+        f.write("d\t0\tBC1\t5\t255\t10M2D5M1I3M\t*\t0\t0\t" + "T" * 19 + "\t*\tAS:i:12\tnM:i:1\tMD:Z:10^AC8\n")
+    t = samio.read_sam_table(p)
+    assert list(t["AS"]) == [15, 14, -3, 12] and t["cigar"][3] == "10M2D5M1I3M"
+    assert samio.query_index_at_many(t["pos"][3:], t["cigar"][3:], 17)[0] == samio.query_index_at(5, "10M2D5M1I3M", 17)
+    empty = str(tmp_path / "e.sam")
+    samio.write_sam(empty, ["BC1"], 86, [])
+    assert len(samio.read_sam_table(empty)["AS"]) == 0
