@@ -1,5 +1,5 @@
 import os, sys, time, gzip, tempfile, cProfile, pstats
-sys.path.insert(0, os.getcwd())
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from nanoranger_b200 import synth, whitelists, utils, fastx
 n = 1000000

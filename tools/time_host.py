@@ -1,5 +1,5 @@
 import os, sys, time, gzip, tempfile
-sys.path.insert(0, os.getcwd())
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from nanoranger_b200 import synth, whitelists, utils, fastx
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
