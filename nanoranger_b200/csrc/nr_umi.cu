@@ -199,13 +199,18 @@ k_cluster_small(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__
     }
 }
 
-// one block per large group.  Same walk, 32 UMIs at a time: (1) all threads look for the earliest
-// representative each chunk member can join -- by comparing the chunk with every representative
-// found so far (atomicMin on its slot), or, in huge groups, by looking the 3 * umi_len Hamming
-// neighbours of each member up in a hash set of the representatives (the work per chunk then
-// no longer grows with the group); (2) one warp settles the chunk in walk order -- a UMI without
-// an earlier representative may still join a representative created earlier in the same chunk;
-// (3) new representatives are appended (and inserted in the hash set).
+// one block per large group.  Same walk, NR_UMI_ROUND UMIs per round:
+//  (1) all threads look for the earliest representative (among those of earlier rounds) each
+//      member can join -- by comparing the round with every such representative, or, in huge
+//      groups, by looking the 3 * umi_len Hamming neighbours of each member up in a hash set of
+//      the representatives (the work per round then no longer grows with the group);
+//  (2) the round is settled in walk order, 32 members at a time: a member without an earlier
+//      representative may still join one created earlier in the same round (compared by all
+//      threads) or earlier among its own 32 (settled by one warp with adjacency masks);
+//  (3) the new representatives are appended (and inserted in the hash set).
+// The global-memory latency of (1) and (3) is paid once per round instead of once per 32 UMIs.
+#define NR_UMI_ROUND 128
+
 __device__ __forceinline__ uint32_t umi_hash(uint32_t u, uint32_t bits)
 {
     return (u * 0x9E3779B1u) >> (32u - bits);
@@ -218,8 +223,11 @@ k_cluster_large(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__
                 uint32_t *__restrict__ du_rep, uint32_t *__restrict__ rep_u,
                 uint32_t *__restrict__ rep_c, uint32_t *__restrict__ htab)
 {
-    __shared__ uint32_t c_d[32], c_u[32], c_c[32], c_best[32];
-    __shared__ uint32_t s_nrep;
+    constexpr uint32_t NONE = 0xFFFFFFFFu;
+    __shared__ uint32_t c_d[NR_UMI_ROUND], c_u[NR_UMI_ROUND], c_c[NR_UMI_ROUND], c_best[NR_UMI_ROUND];
+    __shared__ uint32_t n_d[NR_UMI_ROUND], n_u[NR_UMI_ROUND], n_c[NR_UMI_ROUND];   // this round's new reps
+    __shared__ uint32_t c_join[32], c_adj[32];
+    __shared__ uint32_t s_nrep, s_nnew;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n_groups = totals[1];
     if (max_dist <= 0) return;
@@ -234,29 +242,32 @@ k_cluster_large(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__
         uint32_t *tab = htab + 4ull * d0;
         __syncthreads();
         if (threadIdx.x == 0) s_nrep = 0;
-        for (uint32_t r0 = 0; r0 < nd; r0 += 32) {
+        for (uint32_t r0 = 0; r0 < nd; r0 += NR_UMI_ROUND) {
             __syncthreads();
-            const uint32_t in_chunk = min(32u, nd - r0);
-            if (threadIdx.x < 32) {
+            const uint32_t in_round = min((uint32_t)NR_UMI_ROUND, nd - r0);
+            if (threadIdx.x < NR_UMI_ROUND) {
                 uint32_t d = 0, u = 0, c = 0;
-                if (lane < in_chunk) {
-                    d = order[d0 + r0 + lane];
+                if (threadIdx.x < in_round) {
+                    d = order[d0 + r0 + threadIdx.x];
                     u = s_umi[du_first[d]];
                     c = du_first[d + 1] - du_first[d];
                 }
-                c_d[lane] = d; c_u[lane] = u; c_c[lane] = c; c_best[lane] = 0xFFFFFFFFu;
+                c_d[threadIdx.x] = d; c_u[threadIdx.x] = u; c_c[threadIdx.x] = c;
+                c_best[threadIdx.x] = NONE;
             }
+            if (threadIdx.x == 0) s_nnew = 0;
             __syncthreads();
-            const uint32_t nrep = s_nrep;
+            const uint32_t nrep0 = s_nrep;
+            // (1) representatives of earlier rounds
             if (hashed) {
                 const uint32_t per = 3u * (uint32_t)umi_len;
-                for (uint32_t i = threadIdx.x; i < in_chunk * per; i += blockDim.x) {
+                for (uint32_t i = threadIdx.x; i < in_round * per; i += blockDim.x) {
                     const uint32_t k = i / per, r = i - k * per;
                     const uint32_t key = c_u[k] ^ ((r % 3u + 1u) << (2u * (r / 3u)));
                     uint32_t slot = umi_hash(key, hbits);
                     for (;;) {
                         const uint32_t q = tab[slot];
-                        if (q == 0xFFFFFFFFu) break;
+                        if (q == NONE) break;
                         if (rep_u[d0 + q] == key) {
                             if (rep_c[d0 + q] + 1 >= 2 * c_c[k]) atomicMin(&c_best[k], q);
                             break;
@@ -265,52 +276,81 @@ k_cluster_large(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__
                     }
                 }
             } else {
-                for (uint32_t q = threadIdx.x; q < nrep; q += blockDim.x) {
+                for (uint32_t q = threadIdx.x; q < nrep0; q += blockDim.x) {
                     const uint32_t ru = rep_u[d0 + q], rc = rep_c[d0 + q];
 #pragma unroll 8
-                    for (uint32_t k = 0; k < 32; k++)
-                        if (k < in_chunk && umi_joins(ru, rc, c_u[k], c_c[k], max_dist))
+                    for (uint32_t k = 0; k < NR_UMI_ROUND; k++)
+                        if (k < in_round && umi_joins(ru, rc, c_u[k], c_c[k], max_dist))
                             atomicMin(&c_best[k], q);
                 }
             }
-            __syncthreads();
-            if (threadIdx.x < 32) {
-                const bool have = lane < in_chunk;
-                const uint32_t u = c_u[lane], c = c_c[lane], d = c_d[lane];
-                // in-chunk predecessors this UMI could join if they become representatives
-                uint32_t adj = 0;
-                for (uint32_t j = 0; j < in_chunk; j++)
-                    if (j < lane && umi_joins(c_u[j], c_c[j], u, c, max_dist)) adj |= 1u << j;
-                const uint32_t best = c_best[lane];
-                uint32_t R = 0;                      // chunk members that became representatives
-                uint32_t join = 0xFFFFFFFFu;         // in-chunk representative joined
-                for (uint32_t k = 0; k < in_chunk; k++) {
-                    bool is_rep = false;
-                    if (lane == k && have && best == 0xFFFFFFFFu) {
-                        uint32_t m = adj & R;
-                        if (m) join = (uint32_t)__ffs((int)m) - 1u;
-                        else is_rep = true;
-                    }
-                    R |= __ballot_sync(0xffffffffu, is_rep);
+            // (2) settle the round, 32 members at a time
+            for (uint32_t base = 0; base < in_round; base += 32) {
+                const uint32_t cnt = min(32u, in_round - base);
+                __syncthreads();
+                if (threadIdx.x < 32) { c_join[threadIdx.x] = NONE; c_adj[threadIdx.x] = 0u; }
+                __syncthreads();
+                const uint32_t nnew = s_nnew;
+                // representatives created earlier in this round: earliest one wins
+                for (uint32_t i = threadIdx.x; i < cnt * nnew; i += blockDim.x) {
+                    const uint32_t k = i / nnew, j = i - k * nnew;
+                    if (c_best[base + k] == NONE &&
+                        umi_joins(n_u[j], n_c[j], c_u[base + k], c_c[base + k], max_dist))
+                        atomicMin(&c_join[k], j);
                 }
-                if (have) {
-                    if (best != 0xFFFFFFFFu) {
-                        du_rep[d] = order[d0 + best];
-                    } else if (join != 0xFFFFFFFFu) {
-                        du_rep[d] = c_d[join];
-                    } else {
-                        const uint32_t pos = nrep + (uint32_t)__popc(R & ((1u << lane) - 1u));
-                        du_rep[d] = d;
-                        order[d0 + pos] = d; rep_u[d0 + pos] = u; rep_c[d0 + pos] = c;
-                        if (hashed) {
-                            uint32_t slot = umi_hash(u, hbits);
-                            while (atomicCAS(&tab[slot], 0xFFFFFFFFu, pos) != 0xFFFFFFFFu)
-                                slot = (slot + 1u) & hmask;
+                // predecessors among these 32 a member could join if they become representatives
+                for (uint32_t i = threadIdx.x; i < cnt * cnt; i += blockDim.x) {
+                    const uint32_t k = i / cnt, j = i - k * cnt;
+                    if (j < k && umi_joins(c_u[base + j], c_c[base + j], c_u[base + k], c_c[base + k], max_dist))
+                        atomicOr(&c_adj[k], 1u << j);
+                }
+                __syncthreads();
+                if (threadIdx.x < 32) {
+                    const bool have = lane < cnt;
+                    const uint32_t u = c_u[base + lane], c = c_c[base + lane], d = c_d[base + lane];
+                    const uint32_t adj = c_adj[lane];
+                    const uint32_t best = c_best[base + lane], jn = c_join[lane];
+                    uint32_t R = 0;                  // members that became representatives
+                    uint32_t join = NONE;            // representative joined among these 32
+                    for (uint32_t k = 0; k < cnt; k++) {
+                        bool is_rep = false;
+                        if (lane == k && have && best == NONE && jn == NONE) {
+                            uint32_t m = adj & R;
+                            if (m) join = (uint32_t)__ffs((int)m) - 1u;
+                            else is_rep = true;
+                        }
+                        R |= __ballot_sync(0xffffffffu, is_rep);
+                    }
+                    if (have) {
+                        if (best != NONE) {
+                            du_rep[d] = order[d0 + best];
+                        } else if (jn != NONE) {
+                            du_rep[d] = n_d[jn];
+                        } else if (join != NONE) {
+                            du_rep[d] = c_d[base + join];
+                        } else {
+                            const uint32_t j = nnew + (uint32_t)__popc(R & ((1u << lane) - 1u));
+                            du_rep[d] = d;
+                            n_d[j] = d; n_u[j] = u; n_c[j] = c;
                         }
                     }
+                    if (lane == 0) s_nnew = nnew + (uint32_t)__popc(R);
                 }
-                if (lane == 0) s_nrep = nrep + (uint32_t)__popc(R);
             }
+            __syncthreads();
+            // (3) append the new representatives (walk order = creation order)
+            const uint32_t nnew = s_nnew;
+            if (threadIdx.x < nnew) {
+                const uint32_t pos = nrep0 + threadIdx.x;
+                order[d0 + pos] = n_d[threadIdx.x];
+                rep_u[d0 + pos] = n_u[threadIdx.x];
+                rep_c[d0 + pos] = n_c[threadIdx.x];
+                if (hashed) {
+                    uint32_t slot = umi_hash(n_u[threadIdx.x], hbits);
+                    while (atomicCAS(&tab[slot], NONE, pos) != NONE) slot = (slot + 1u) & hmask;
+                }
+            }
+            if (threadIdx.x == 0) s_nrep = nrep0 + nnew;
         }
     }
 }

@@ -9,7 +9,7 @@
 set -u
 TAG=${1:-r1}
 OUT=gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --batch 1048576 --no-cpu-baseline"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"   # the default workload (4 Mi candidates per step)
 mkdir -p $OUT
 $CMD > $OUT/plain_$TAG.log 2> $OUT/plain_$TAG.err || { echo "plain run failed"; tail -5 $OUT/plain_$TAG.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \

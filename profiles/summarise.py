@@ -61,7 +61,7 @@ def launches(tag):
     tot = sum(v[1] for v in agg.values())
     step_k = ("nr_pack_kernel", "nr_match_filtered_kernel<0>", "nr_match_exhaustive16_kernel")
     step_tot = sum(v[1] for k, v in agg.items() if k.startswith(step_k))
-    out = [f"# Launch list of `python bench.py --steps 2 --warmup 3 --batch 1048576 --no-cpu-baseline` ({tag})",
+    out = [f"# Launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` ({tag})",
            "", "`ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised launches:",
            "the share column is what must agree with bench.py, not the absolute times).", "",
            "The whole process is listed: index build (nr_index_*, cub), the ALU-peak probe",
@@ -131,7 +131,7 @@ def full(tag, n_cand):
 
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
-    n = int(sys.argv[2]) if len(sys.argv) > 2 else 1048576
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 22
     a = launches(tag)
     if a:
         print(open(os.path.join(ROOT, "profiles", f"{tag}_launches.md")).read())
