@@ -65,8 +65,10 @@ nr_hw_search_kernel(const uint8_t *__restrict__ text, const uint64_t *__restrict
         peq[c] = a; rpeq[c] = b;
     }
     __syncthreads();
-    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n) return;
+    // grid-stride over the windows: the two tables above are built once per block, not per 128
+    // windows
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n;
+         w += (uint64_t)gridDim.x * blockDim.x) {
     const uint8_t *t = text + offsets[w];
     const int64_t len = (int64_t)(offsets[w + 1] - offsets[w]);
     const int m = P.m;
@@ -84,7 +86,7 @@ nr_hw_search_kernel(const uint8_t *__restrict__ text, const uint64_t *__restrict
     if (len == 0 || best > P.k) {
         o_ed[w] = -1; o_nloc[w] = 0;
         o_first[2 * w] = -1; o_first[2 * w + 1] = -1; o_last[2 * w] = -1; o_last[2 * w + 1] = -1;
-        return;
+        continue;
     }
     // smallest start of an optimal alignment ending at e: reversed pattern against the reversed
     // prefix t[e], t[e-1], ...; bottom-row value == best at the farthest column
@@ -107,6 +109,7 @@ nr_hw_search_kernel(const uint8_t *__restrict__ text, const uint64_t *__restrict
     o_ed[w] = (int8_t)best; o_nloc[w] = nloc;
     o_first[2 * w] = (int32_t)starts[0]; o_first[2 * w + 1] = (int32_t)first;
     o_last[2 * w] = (int32_t)starts[1]; o_last[2 * w + 1] = (int32_t)last;
+    }
 }
 
 int check_args(const char *pattern, int m, int k)
@@ -133,7 +136,11 @@ extern "C" int nr_hw_search_device(const uint8_t *d_text, const uint64_t *d_offs
     HwParams P;
     for (int i = 0; i < 64; i++) P.pat[i] = i < m ? (uint8_t)pattern[i] : 0;
     P.m = m; P.k = k; P.wildcard = wildcard_n ? 1 : 0;
-    const uint64_t blocks = (n + 127) / 128;
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint64_t want = (n + 127) / 128, cap = (uint64_t)sms * 16;
+    const uint64_t blocks = want < cap ? want : cap;
     nr_hw_search_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(
         d_text, d_offsets, n, P, d_ed, d_first, d_last, d_nloc);
     NR_CHECK_CUDA(cudaGetLastError());
