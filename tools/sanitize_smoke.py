@@ -1,0 +1,34 @@
+"""Small run of every kernel for compute-sanitizer (memcheck / racecheck / initcheck)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from nanoranger_b200 import NR_MODE_AUTO, NR_MODE_FILTERED, NR_MODE_EXHAUSTIVE, Whitelist, synth, whitelists, pack_ascii, extract
+from nanoranger_b200 import umi as U
+wl_a = whitelists.load_737k()[::8]                       # 92K entries: quick index, same code paths
+d = synth.make_candidates(wl_a, 3000, seed=3)
+seqs = synth.to_strings(d["seqs"], d["offsets"])
+seqs[5] = seqs[5][:10] + "N" + seqs[5][11:]
+seqs += ["ACGT" * 20, "", "ACGTACGTAC"]
+wl = Whitelist(wl_a, 30, 40)
+dev = torch.device("cuda:0")
+buf, off = pack_ascii(seqs)
+d_seqs = torch.from_numpy(buf.copy()).to(dev); d_off = torch.from_numpy(off.view(np.int64).copy()).to(dev)
+bases, meta, nmask = wl.pack_device(d_seqs, d_off)
+for mode in (NR_MODE_FILTERED, NR_MODE_AUTO):
+    res = wl.match_device(bases, meta, nmask, min_score=14, mode=mode)
+res_c = wl.match_device(bases, meta, nmask, min_score=14, counted=True)
+ex = wl.match_device(bases[:40], meta[:40], nmask[:40], min_score=14, mode=NR_MODE_EXHAUSTIVE)
+h = wl.match_host(seqs, min_score=14, mode=NR_MODE_FILTERED)
+gene = torch.arange(len(seqs), dtype=torch.int32, device=dev) % 5
+rec = U.records_device(bases, meta, nmask, res, 14, 12, gene=gene)
+rows, counts = U.partition_device(rec["bc"], rec["gene"], rec["umi"], 4)
+U.unzip_device(rows)
+rng = np.random.default_rng(2)
+n = 40000
+bc = np.where(rng.random(n) < 0.6, 3, rng.integers(0, 40, n)).astype(np.uint32)
+um = rng.integers(0, 1 << 13, n).astype(np.uint32)
+for md in (0, 1):
+    U.collapse_host(bc, np.zeros(n, np.uint32), um, 12, md)
+extract.hw_search(seqs, "CGCTCTTCCGATCT" + 26 * "N" + "TTTCTTATATG", 6, True)
+torch.cuda.synchronize()
+print("sanitize_smoke ok", int(res.assigned(14).sum()), rec["n_records"])
