@@ -28,6 +28,7 @@
 //            smallest UMI row per pair
 // Candidates the filter cannot take (contain N, shorter than NR_FILTER_MIN_LEN, more than 32
 // co-optimal pairs) are appended to a device list that the exhaustive kernel resolves.
+#include <atomic>
 #include <utility>
 
 #include "nr_common.cuh"
@@ -493,7 +494,8 @@ nr_match_filtered_kernel(const nr_filter_params P)
 
 }  // namespace
 
-static int g_edge_uploaded_device = -1;
+// devices whose copy of c_probes has been written (bit per device ordinal)
+static std::atomic<unsigned long long> g_probes_uploaded{0ull};
 
 // Enqueue the filtered matcher on `stream`.  list_count must have been zeroed on the stream.
 int nr_launch_filtered(const nr_whitelist *wl, const void *d_bases, const uint8_t *d_meta,
@@ -507,10 +509,12 @@ int nr_launch_filtered(const nr_whitelist *wl, const void *d_bases, const uint8_
         nr_set_error("filtered matcher needs a 16-column N-free whitelist");
         return NR_EUNSUPPORTED;
     }
-    if (g_edge_uploaded_device != wl->device) {
+    const unsigned long long dev_bit = 1ull << (wl->device & 63);
+    if (!(g_probes_uploaded.load(std::memory_order_acquire) & dev_bit)) {
+        // a concurrent first call on the same device writes the same bytes: harmless
         NR_CHECK_CUDA(cudaMemcpyToSymbol(c_probes, &NR_PROBES[0],
                                          sizeof(nr_probe_t) * NR_PROBES_ALL));
-        g_edge_uploaded_device = wl->device;
+        g_probes_uploaded.fetch_or(dev_bit, std::memory_order_release);
     }
     nr_filter_params P;
     for (int j = 0; j < 4; j++) {
