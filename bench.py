@@ -47,6 +47,7 @@ def parse():
                          "sub-reads per read, 3' geometry, barcode match + UMI collapse")
     ap.add_argument("--max-dist", type=int, default=1, help="kinnex: UMI clustering distance")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dp-gcups", action="store_true", help="skip the exhaustive-kernel GCUPS sample")
     return ap.parse_args()
 
 
@@ -429,24 +430,31 @@ def main():
     e2e_pageable_s = (time.perf_counter() - t0) / e2e_steps
 
     # the exhaustive DP kernel on a bounded sample: real (executed) cell updates per second
-    from nanoranger_b200 import NR_MODE_EXHAUSTIVE
-    n_dp = min(B, 2048)
-    dp_off = d_off[:n_dp + 1].contiguous()
-    dp_bases, dp_meta, dp_nmask = wl.pack_device(d_seqs, dp_off)
-    dp_out = wl.alloc_result(n_dp, dev)
-    dp_ws = wl.workspace(n_dp, dev, NR_MODE_EXHAUSTIVE)
-    wl.match_device(dp_bases, dp_meta, dp_nmask, min_score=min_score, mode=NR_MODE_EXHAUSTIVE,
-                    out=dp_out, workspace=dp_ws)
-    torch.cuda.synchronize()
-    e0.record()
-    wl.match_device(dp_bases, dp_meta, dp_nmask, min_score=min_score, mode=NR_MODE_EXHAUSTIVE,
-                    out=dp_out, workspace=dp_ws)
-    e1.record()
-    torch.cuda.synchronize()
-    ms_dp = e0.elapsed_time(e1)
-    dp_cells = float(dp_meta.to(torch.int64).bitwise_and(0x7F).sum().item()) * len(wl_ascii) * 16 * 2
-    dp_same = bool(torch.equal(dp_out.idx[out.assigned(min_score)[:n_dp]],
-                               out.idx[:n_dp][out.assigned(min_score)[:n_dp]]))
+    dp = None
+    if not args.no_dp_gcups:
+        from nanoranger_b200 import NR_MODE_EXHAUSTIVE
+        n_dp = min(B, 2048)
+        dp_off = d_off[:n_dp + 1].contiguous()
+        dp_bases, dp_meta, dp_nmask = wl.pack_device(d_seqs, dp_off)
+        dp_out = wl.alloc_result(n_dp, dev)
+        dp_ws = wl.workspace(n_dp, dev, NR_MODE_EXHAUSTIVE)
+        wl.match_device(dp_bases, dp_meta, dp_nmask, min_score=min_score, mode=NR_MODE_EXHAUSTIVE,
+                        out=dp_out, workspace=dp_ws)
+        torch.cuda.synchronize()
+        e0.record()
+        wl.match_device(dp_bases, dp_meta, dp_nmask, min_score=min_score, mode=NR_MODE_EXHAUSTIVE,
+                        out=dp_out, workspace=dp_ws)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_dp = e0.elapsed_time(e1)
+        dp_cells = float(dp_meta.to(torch.int64).bitwise_and(0x7F).sum().item()) * len(wl_ascii) * 16 * 2
+        dp_mask = out.assigned(min_score)[:n_dp]
+        dp = {"value": dp_cells / (ms_dp * 1e-3) / 1e9 * world, "kernel": "nr_match_exhaustive16_kernel",
+              "sample": f"first {n_dp} candidates of the batch per GPU, both strands, every whitelist entry",
+              "ms": ms_dp, "candidates_per_sec": world * n_dp / (ms_dp * 1e-3),
+              "agrees_with_filtered_on_assigned": bool(torch.equal(dp_out.idx[dp_mask], out.idx[:n_dp][dp_mask])),
+              "note": "executed cell updates of the exhaustive DP (NR_MODE_EXHAUSTIVE); "
+                      "gcups_equivalent is the filtered path's candidates/s x cells a brute force would do"}
 
     # max over ranks
     t = torch.tensor([ms_total, ms_match, e2e_s], dtype=torch.float64, device=dev)
@@ -515,12 +523,7 @@ def main():
                    "l2": "inputs larger than L2 (ASCII batch %.0f MB per GPU)" % (n_bytes_in / 1e6),
                    "index_build_s": t_index},
         "gcups_equivalent": value * n_wl * 16 * 50 / 1e9,
-        "dp_gcups": {"value": dp_cells / (ms_dp * 1e-3) / 1e9 * world, "kernel": "nr_match_exhaustive16_kernel",
-                     "sample": f"first {n_dp} candidates of the batch per GPU, both strands, every whitelist entry",
-                     "ms": ms_dp, "candidates_per_sec": world * n_dp / (ms_dp * 1e-3),
-                     "agrees_with_filtered_on_assigned": dp_same,
-                     "note": "executed cell updates of the exhaustive DP (NR_MODE_EXHAUSTIVE); "
-                             "gcups_equivalent is the filtered path's candidates/s x cells a brute force would do"},
+        "dp_gcups": dp,
         "assigned_per_sec": float(tot.item()) / (ms_step * 1e-3),
         "assigned_fraction": float(tot.item()) / (world * B),
         "accuracy_rank0": accuracy,

@@ -61,7 +61,7 @@ def launches(tag):
     tot = sum(v[1] for v in agg.values())
     step_k = ("nr_pack_kernel", "nr_match_filtered_kernel<0>", "nr_match_exhaustive16_kernel")
     step_tot = sum(v[1] for k, v in agg.items() if k.startswith(step_k))
-    out = [f"# Launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` ({tag})",
+    out = [f"# Launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-dp-gcups` ({tag})",
            "", "`ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised launches:",
            "the share column is what must agree with bench.py, not the absolute times).", "",
            "The whole process is listed: index build (nr_index_*, cub), the ALU-peak probe",
