@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from helpers import compare, mixed_candidates, rs, tie_rich_whitelist
+from helpers import compare, mixed_candidates, mutate, rs, tie_rich_whitelist
 
 pytestmark = pytest.mark.gpu
 
@@ -167,3 +167,32 @@ def test_dense_index_3M_sized_whitelist_vs_oracle(cuda_device, oracle):
     nhi = compare(ref, res, 14, exact_below=False, label="3M filtered")
     assert nhi > 40
     assert wl.counters(ws)["hits"] > 300 * len(seqs)
+
+
+def test_adversarial_cases_vs_oracle(cuda_device, oracle):
+    """barcode at offset 0 / exactly padL / beyond the pad, homopolymer
+    and low-complexity barcodes (every probe of a slot hits), N in the candidate, lengths 1..64."""
+    from nanoranger_b200 import Whitelist, NR_MODE_AUTO, NR_MODE_FILTERED
+    rng = np.random.default_rng(77)
+    wl_strs = ["A" * 16, "C" * 16, "ACAC" * 4, "AAAAAAAACCCCCCCC", "ACGT" * 4, "A" * 15 + "C", "C" + "A" * 15,
+               "AAAACCCCGGGGTTTT", "TTTTGGGGCCCCAAAA"] + tie_rich_whitelist(rng, 400)
+    wl_strs = sorted(set(wl_strs))
+    pad_l, pad_r = 30, 40
+    seqs = []
+    for bc in wl_strs[:60]:
+        for off in (0, 1, 14, 29, 30, 31, 32, 33, 40):
+            seqs.append((rs(rng, off) + bc + rs(rng, 20))[:64])
+            seqs.append((rs(rng, off) + mutate(rng, bc, 1) + rs(rng, 20))[:64])
+        seqs.append(bc[3:] + rs(rng, 30))          # start overhang
+        seqs.append(rs(rng, 30) + bc[:13])         # end overhang
+        seqs.append("A" * 50)
+        seqs.append(("A" * 20 + bc + "A" * 20)[:64])
+        seqs.append(bc[:8] + "N" + bc[8:] + rs(rng, 20))
+    seqs += [rs(rng, n) for n in range(0, 65)]
+    wl = Whitelist(wl_strs, pad_l, pad_r)
+    ref = _oracle(oracle, wl_strs, pad_l, pad_r, seqs)
+    res, _ = _run_device(wl, seqs, 14, NR_MODE_FILTERED)
+    compare(ref, res, 14, exact_below=False, label="adversarial filtered")
+    res, _ = _run_device(wl, seqs, 14, NR_MODE_AUTO)
+    compare(ref, res, 14, exact_below=True, label="adversarial auto")
+    assert (ref["n_best"] > 32).sum() >= 0
