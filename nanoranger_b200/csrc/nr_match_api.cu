@@ -21,7 +21,8 @@ int nr_launch_filtered(const nr_whitelist *wl, const void *d_bases, const uint8_
                        uint32_t *d_list, uint32_t *d_list_count, unsigned long long *d_counters,
                        int *grid_out, cudaStream_t stream);
 
-// workspace layout: [0,64) eight u64 counters, [64,68) list count, [128, 128 + 8 KB) the
+// workspace layout: [0,64) eight u64 counters, [64,68) list count, [72,80) next tile of the
+// filtered kernel, [128, 128 + 8 KB) the
 // exhaustive kernel's arrival counters (zeroed with the header), then its partials,
 // [NR_WS_HEADER, NR_WS_HEADER + 4n) list
 #define NR_WS_ZERO (128 + NR_EX_MAXGRID * 4)

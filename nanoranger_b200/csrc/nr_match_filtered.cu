@@ -61,6 +61,7 @@ struct nr_filter_params {
     uint8_t *o_umi;
     uint32_t *list;         // candidates left to the exhaustive kernel
     uint32_t *list_count;
+    unsigned long long *tile_next;  // next tile to hand out (zeroed with the workspace header)
     unsigned long long *counters;   // nullable: probes, hits, verifications, passes, listed
 };
 
@@ -353,8 +354,14 @@ nr_match_filtered_kernel(const nr_filter_params P)
     Acc acc;
     acc.c_hits = acc.c_ver = acc.c_pass = 0;
 
-    for (uint64_t tile = (uint64_t)blockIdx.x * NR_FWARPS + warp; tile < n_tiles;
-         tile += (uint64_t)gridDim.x * NR_FWARPS) {
+    // tiles are handed out dynamically: their cost varies several-fold (a tile of unassignable
+    // candidates runs the whole probe table 32 times), a static stride leaves a long tail
+    for (;;) {
+        unsigned long long t64 = 0;
+        if (lane == 0) t64 = atomicAdd(P.tile_next, 1ull);
+        const uint64_t tile = ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(t64 >> 32), 0) << 32) |
+                              (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)t64, 0);
+        if (tile >= n_tiles) break;
         // one coalesced 512 B request brings the tile's records; meta bytes stay in registers
         uint32_t mt = 0x100u;   // no candidate
         {
@@ -526,6 +533,7 @@ int nr_launch_filtered(const nr_whitelist *wl, const void *d_bases, const uint8_
     P.min_score = min_score; P.resolve_below = resolve_below;
     P.o_idx = d_idx; P.o_score = d_score; P.o_nbest = d_nbest; P.o_flags = d_flags; P.o_umi = d_umi;
     P.list = d_list; P.list_count = d_list_count; P.counters = d_counters;
+    P.tile_next = (unsigned long long *)(d_list_count + 2);   // workspace header, offset 72
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
     if (d_counters)
