@@ -175,9 +175,9 @@ extern "C" void nr_host_free(void *p) { if (p) cudaFreeHost(p); }
 // directly; pageable buffers go through the slot's pinned staging area.
 namespace {
 
-constexpr uint64_t CHUNK_CAND = 1ull << 19;               // candidates per chunk
+constexpr uint64_t CHUNK_CAND = 1ull << 18;               // candidates per chunk
 constexpr uint64_t CHUNK_BYTES = CHUNK_CAND * 64;         // sequence bytes per chunk
-constexpr int NSLOT = 3;
+constexpr int NSLOT = 4;
 
 struct Slot {
     cudaStream_t st = nullptr;
@@ -334,11 +334,15 @@ extern "C" int nr_match_host(const nr_whitelist_t *wlc, const char *seqs, const 
     const bool out_pinned = is_pinned(idx) && is_pinned(score) && is_pinned(nbest) &&
                             is_pinned(flags) && is_pinned(umi_q);
     uint64_t c0 = 0;
-    int k = 0;
+    int k = 0, n_chunk = 0;
     int rc = NR_OK;
     while (c0 < n) {
-        // chunk = as many candidates as fit both limits
-        uint64_t c1 = std::min(n, c0 + CHUNK_CAND);
+        // chunk = as many candidates as fit both limits; the first chunks are smaller so that the
+        // GPU starts working before much of the input has crossed PCIe
+        const uint64_t want = n_chunk == 0 ? CHUNK_CAND / 8 : (n_chunk == 1 ? CHUNK_CAND / 4 :
+                              (n_chunk == 2 ? CHUNK_CAND / 2 : CHUNK_CAND));
+        n_chunk++;
+        uint64_t c1 = std::min(n, c0 + want);
         if (offsets[c1] - offsets[c0] > CHUNK_BYTES) {
             const uint64_t *hi = std::upper_bound(offsets + c0, offsets + c1 + 1,
                                                   offsets[c0] + CHUNK_BYTES);
