@@ -280,8 +280,14 @@ nr_match_exhaustive16_kernel(const uint32_t *__restrict__ wl, uint32_t n, int pa
     }
 }
 
-// ---- generic: any L <= 32, N columns in the whitelist; one entry per thread ----------------
-__global__ void __launch_bounds__(256)
+// ---- generic: any L <= 32, N columns in the whitelist; DPX s16x2, two entries per thread -----
+// The (s + 2) profile of the thread's entry pair -- 4 read bases x L columns, both entries in
+// the halves of a word -- lives in shared memory ([base][column][thread]: conflict-free), so a
+// cell pair costs one LDS + VIMNMX + VIADDMNMX like in the L = 16 kernel.  A read N scores 0
+// against everything: constant term.
+#define NR_EXG_THREADS 128
+
+__global__ void __launch_bounds__(NR_EXG_THREADS, 3)
 nr_match_exhaustive_generic_kernel(const uint32_t *__restrict__ wlo,
                                    const uint32_t *__restrict__ whi,
                                    const uint32_t *__restrict__ wnm, uint32_t n, int L, int padL,
@@ -295,16 +301,19 @@ nr_match_exhaustive_generic_kernel(const uint32_t *__restrict__ wlo,
                                    uint8_t *__restrict__ o_flags, uint8_t *__restrict__ o_umi,
                                    ExScratch sc)
 {
+    extern __shared__ uint32_t prof[];          // [4][L][NR_EXG_THREADS]
     __shared__ uint8_t cf[NR_MAX_QUERY], cr[NR_MAX_QUERY];
     __shared__ Best shb[32];
     __shared__ int sh_flag;
     uint64_t total = list ? (uint64_t)*list_count : n_cand;
+    const uint32_t npairs = (n + 1) >> 1;
     const uint32_t S = ex_slices(total, sc);
-    const uint32_t per = (n + S - 1) / S;
+    const uint32_t per = (npairs + S - 1) / S;
+    uint32_t *mine = prof + threadIdx.x;
     for (uint64_t w = blockIdx.x; w < total * S; w += gridDim.x) {
         const uint64_t it = w / S;
-        const uint32_t e_lo = (uint32_t)(w % S) * per;
-        const uint32_t e_hi = min(n, e_lo + per);
+        const uint32_t p_lo = (uint32_t)(w % S) * per;
+        const uint32_t p_hi = min(npairs, p_lo + per);
         uint64_t cand = list ? (uint64_t)list[it] : it;
         uint8_t mt = meta[cand];
         if (mt == 0xFF) {
@@ -320,47 +329,74 @@ nr_match_exhaustive_generic_kernel(const uint32_t *__restrict__ wlo,
         load_codes(bases, (mt & 0x80) ? nmask : nullptr, cand, m, cf, cr);
         __syncthreads();
         Best b; b.score = -1000; b.cnt = 0; b.key = 0xFFFFFFFFu;
-        const int aleft = -max(0, m - padL);
-        for (uint32_t e = e_lo + threadIdx.x; e < e_hi; e += blockDim.x) {
-            uint32_t lo = wlo[e], hi = whi ? whi[e] : 0u, nm = wnm ? wnm[e] : 0u;
+        const uint32_t aleft = P2(-max(0, m - padL));
+        for (uint32_t p = p_lo + threadIdx.x; p < p_hi; p += blockDim.x) {
+            const uint32_t ia = 2 * p;
+            const bool vb = ia + 1 < n;
+            const uint32_t ib = vb ? ia + 1 : ia;
+            const uint32_t la = wlo[ia], lb = wlo[ib];
+            const uint32_t ha = whi ? whi[ia] : 0u, hb = whi ? whi[ib] : 0u;
+            const uint32_t na = wnm ? wnm[ia] : 0u, nb = wnm ? wnm[ib] : 0u;
+            // profile of the pair: term = 3 match, 1 mismatch, 2 where the entry column is N
+            for (int col = 0; col < L; col++) {
+                const uint32_t ca = ((col < 16 ? la >> (2 * col) : ha >> (2 * (col - 16)))) & 3u;
+                const uint32_t cb = ((col < 16 ? lb >> (2 * col) : hb >> (2 * (col - 16)))) & 3u;
+                const bool a_n = (na >> col) & 1u, b_n = (nb >> col) & 1u;
+#pragma unroll
+                for (uint32_t q = 0; q < 4; q++) {
+                    const uint32_t ta = a_n ? 2u : (ca == q ? 3u : 1u);
+                    const uint32_t tb = b_n ? 2u : (cb == q ? 3u : 1u);
+                    mine[(q * (uint32_t)L + (uint32_t)col) * NR_EXG_THREADS] = ta | (tb << 16);
+                }
+            }
 #pragma unroll 1
             for (int strand = 0; strand < 2; strand++) {
                 const uint8_t *q = strand ? cr : cf;
-                int C[NR_MAX_CORE + 1];
+                uint32_t C[NR_MAX_CORE + 1];
 #pragma unroll
-                for (int j = 0; j <= NR_MAX_CORE; j++) C[j] = j;
-                int ar = -max(0, m - padR);
+                for (int j = 0; j <= NR_MAX_CORE; j++) C[j] = P2(j);
+                uint32_t ar = P2(-max(0, m - padR));
 #pragma unroll 1
                 for (int i = 1; i <= m; i++) {
-                    int qq = q[i - 1];
-                    int diag = C[0];
-                    C[0] = min(i, padL);
-                    // per-column s+2: match 3, mismatch 1, N 2
-                    uint32_t xl = lo ^ (uint32_t)(qq & 3) * 0x55555555u;
-                    uint32_t xh = hi ^ (uint32_t)(qq & 3) * 0x55555555u;
-                    uint32_t ml = ~(xl | (xl >> 1)) & 0x55555555u;   // bit 2c: column c matches
-                    uint32_t mh = ~(xh | (xh >> 1)) & 0x55555555u;
-                    bool qn = qq > 3;
+                    const int qq = q[i - 1];
+                    uint32_t diag = C[0];
+                    C[0] = P2(min(i, padL));
+                    if (qq < 4) {
+                        const uint32_t *pq = mine + (uint32_t)qq * (uint32_t)L * NR_EXG_THREADS;
 #pragma unroll
-                    for (int j = 1; j <= NR_MAX_CORE; j++) {
-                        int col = j - 1;
-                        uint32_t mb = col < 16 ? (ml >> (2 * col)) & 1u : (mh >> (2 * (col - 16))) & 1u;
-                        int sp = (qn || ((nm >> col) & 1u)) ? 2 : 1 + 2 * (int)mb;
-                        int t = C[j];
-                        int v = max(diag + sp, max(C[j], C[j - 1]));
-                        C[j] = (j <= L) ? v : C[j];
-                        diag = t;
+                        for (int j = 1; j <= NR_MAX_CORE; j++) {
+                            if (j <= L) {
+                                const uint32_t t = C[j];
+                                C[j] = __viaddmax_s16x2(diag, pq[(j - 1) * NR_EXG_THREADS],
+                                                        __vmaxs2(C[j], C[j - 1]));
+                                diag = t;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 1; j <= NR_MAX_CORE; j++) {
+                            if (j <= L) {
+                                const uint32_t t = C[j];
+                                C[j] = __viaddmax_s16x2(diag, 0x00020002u, __vmaxs2(C[j], C[j - 1]));
+                                diag = t;
+                            }
+                        }
                     }
-                    int cl = C[0];
+                    uint32_t cl = C[0];
 #pragma unroll
                     for (int j = 1; j <= NR_MAX_CORE; j++) if (j == L) cl = C[j];
-                    ar = max(ar, cl - (i + L + max(0, m - i - padR)));
+                    const uint32_t off = P2(i + L + max(0, m - i - padR));
+                    ar = __vmaxs2(ar, __vsub2(cl, off));
                 }
-                int ain = -1000;
+                uint32_t ain = P2(-1000);
 #pragma unroll
-                for (int j = 1; j < NR_MAX_CORE; j++) if (j < L) ain = max(ain, C[j] - (m + j));
-                int as = max(aleft, max(ain, ar));
-                best_add(b, as, (e << 1) | (uint32_t)strand);
+                for (int j = 1; j < NR_MAX_CORE; j++)
+                    if (j < L) ain = __vmaxs2(ain, __vsub2(C[j], P2(m + j)));
+                const uint32_t as2 = __vmaxs2(aleft, __vmaxs2(ain, ar));
+                const int sa = (int)(int16_t)(as2 & 0xFFFFu);
+                const int sb = (int)(int16_t)(as2 >> 16);
+                best_add(b, sa, (ia << 1) | (uint32_t)strand);
+                if (vb) best_add(b, sb, (ib << 1) | (uint32_t)strand);
             }
         }
         Best r = block_reduce_best(b, shb);
@@ -395,7 +431,10 @@ int nr_launch_exhaustive(const nr_whitelist *wl, const void *d_bases, const uint
             d_meta, d_nmask, d_list, d_list_count, n_cand, min_score, d_idx, d_score, d_nbest,
             d_flags, d_umi, sc);
     } else {
-        nr_match_exhaustive_generic_kernel<<<grid, 256, 0, stream>>>(
+        const size_t smem = (size_t)4 * wl->L * NR_EXG_THREADS * sizeof(uint32_t);
+        NR_CHECK_CUDA(cudaFuncSetAttribute(nr_match_exhaustive_generic_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nr_match_exhaustive_generic_kernel<<<grid, NR_EXG_THREADS, smem, stream>>>(
             wl->d_lo, wl->d_hi, wl->d_nm, (uint32_t)wl->n, (int)wl->L, (int)wl->pad_l,
             (int)wl->pad_r, (const uint4 *)d_bases, d_meta, d_nmask, d_list, d_list_count,
             n_cand, min_score, d_idx, d_score, d_nbest, d_flags, d_umi, sc);
