@@ -10,6 +10,8 @@
 // so one cell is one VIMNMX + one VIADDMNMX.  The L = 16 / N-free-whitelist kernel keeps two
 // entries per thread in the s16x2 halves of every register (DPX), the 4 x 16 score profile
 // of the entry pair in registers, and walks the query rows with a warp-uniform base switch.
+#include <cstdlib>
+
 #include "nr_common.cuh"
 
 namespace {
@@ -287,10 +289,11 @@ nr_match_exhaustive16_kernel(const uint32_t *__restrict__ wl, uint32_t n, int pa
 // against everything: constant term.
 #define NR_EXG_THREADS 128
 
+template <int LT>      // LT > 0: core length known at compile time (32: slide-seq); 0: runtime L
 __global__ void __launch_bounds__(NR_EXG_THREADS, 3)
 nr_match_exhaustive_generic_kernel(const uint32_t *__restrict__ wlo,
                                    const uint32_t *__restrict__ whi,
-                                   const uint32_t *__restrict__ wnm, uint32_t n, int L, int padL,
+                                   const uint32_t *__restrict__ wnm, uint32_t n, int L_rt, int padL,
                                    int padR, const uint4 *__restrict__ bases,
                                    const uint8_t *__restrict__ meta,
                                    const uint64_t *__restrict__ nmask,
@@ -302,6 +305,7 @@ nr_match_exhaustive_generic_kernel(const uint32_t *__restrict__ wlo,
                                    ExScratch sc)
 {
     extern __shared__ uint32_t prof[];          // [4][L][NR_EXG_THREADS]
+    const int L = LT ? LT : L_rt;
     __shared__ uint8_t cf[NR_MAX_QUERY], cr[NR_MAX_QUERY];
     __shared__ Best shb[32];
     __shared__ int sh_flag;
@@ -425,19 +429,36 @@ int nr_launch_exhaustive(const nr_whitelist *wl, const void *d_bases, const uint
     ExScratch sc;
     sc.done = d_scratch ? (uint32_t *)d_scratch : nullptr;
     sc.part = d_scratch ? (uint4 *)((uint8_t *)d_scratch + NR_EX_MAXGRID * sizeof(uint32_t)) : nullptr;
-    if (wl->L == 16 && !wl->has_n) {
+    static const bool force_generic = getenv("NR_FORCE_GENERIC_EXHAUSTIVE") != nullptr;   // experiments only
+    if (wl->L == 16 && !wl->has_n && !force_generic) {
         nr_match_exhaustive16_kernel<<<grid, 256, 0, stream>>>(
             wl->d_lo, (uint32_t)wl->n, (int)wl->pad_l, (int)wl->pad_r, (const uint4 *)d_bases,
             d_meta, d_nmask, d_list, d_list_count, n_cand, min_score, d_idx, d_score, d_nbest,
             d_flags, d_umi, sc);
     } else {
         const size_t smem = (size_t)4 * wl->L * NR_EXG_THREADS * sizeof(uint32_t);
-        NR_CHECK_CUDA(cudaFuncSetAttribute(nr_match_exhaustive_generic_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nr_match_exhaustive_generic_kernel<<<grid, NR_EXG_THREADS, smem, stream>>>(
-            wl->d_lo, wl->d_hi, wl->d_nm, (uint32_t)wl->n, (int)wl->L, (int)wl->pad_l,
-            (int)wl->pad_r, (const uint4 *)d_bases, d_meta, d_nmask, d_list, d_list_count,
-            n_cand, min_score, d_idx, d_score, d_nbest, d_flags, d_umi, sc);
+        if (wl->L == 32) {
+            NR_CHECK_CUDA(cudaFuncSetAttribute(nr_match_exhaustive_generic_kernel<32>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            nr_match_exhaustive_generic_kernel<32><<<grid, NR_EXG_THREADS, smem, stream>>>(
+                wl->d_lo, wl->d_hi, wl->d_nm, (uint32_t)wl->n, 32, (int)wl->pad_l,
+                (int)wl->pad_r, (const uint4 *)d_bases, d_meta, d_nmask, d_list, d_list_count,
+                n_cand, min_score, d_idx, d_score, d_nbest, d_flags, d_umi, sc);
+        } else if (wl->L == 16) {          // 16 columns with N inside some entry
+            NR_CHECK_CUDA(cudaFuncSetAttribute(nr_match_exhaustive_generic_kernel<16>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            nr_match_exhaustive_generic_kernel<16><<<grid, NR_EXG_THREADS, smem, stream>>>(
+                wl->d_lo, wl->d_hi, wl->d_nm, (uint32_t)wl->n, 16, (int)wl->pad_l,
+                (int)wl->pad_r, (const uint4 *)d_bases, d_meta, d_nmask, d_list, d_list_count,
+                n_cand, min_score, d_idx, d_score, d_nbest, d_flags, d_umi, sc);
+        } else {
+            NR_CHECK_CUDA(cudaFuncSetAttribute(nr_match_exhaustive_generic_kernel<0>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            nr_match_exhaustive_generic_kernel<0><<<grid, NR_EXG_THREADS, smem, stream>>>(
+                wl->d_lo, wl->d_hi, wl->d_nm, (uint32_t)wl->n, (int)wl->L, (int)wl->pad_l,
+                (int)wl->pad_r, (const uint4 *)d_bases, d_meta, d_nmask, d_list, d_list_count,
+                n_cand, min_score, d_idx, d_score, d_nbest, d_flags, d_umi, sc);
+        }
     }
     NR_CHECK_CUDA(cudaGetLastError());
     return NR_OK;

@@ -196,3 +196,25 @@ def test_adversarial_cases_vs_oracle(cuda_device, oracle):
     res, _ = _run_device(wl, seqs, 14, NR_MODE_AUTO)
     compare(ref, res, 14, exact_below=True, label="adversarial auto")
     assert (ref["n_best"] > 32).sum() >= 0
+
+
+@pytest.mark.parametrize("L", [16, 20, 32])
+def test_generic_kernel_core_lengths_with_n(cuda_device, oracle, L):
+    """the three instantiations of the generic exhaustive kernel (compile-time 16 and 32 columns,
+    run-time otherwise), whitelist entries with N inside"""
+    from nanoranger_b200 import Whitelist, NR_MODE_AUTO
+    rng = np.random.default_rng(300 + L)
+    cores = sorted({rs(rng, L) for _ in range(700)})
+    cores = [c if rng.random() > 0.2 else c[:5] + "N" + c[6:] for c in cores]
+    seqs = []
+    for _ in range(500):
+        c = cores[rng.integers(0, len(cores))].replace("N", "ACGT"[rng.integers(0, 4)])
+        seqs.append((rs(rng, int(rng.integers(0, 12))) + mutate(rng, c, int(rng.integers(0, 3))) + rs(rng, 25))[:64])
+    seqs += ["", "A", rs(rng, 64), "N" * 40]
+    wl = Whitelist(cores, 10, 20)
+    assert not wl.has_index
+    wlc, _ = oracle.encode_many(cores, L)
+    cc, cl = oracle.encode_many(seqs, 64)
+    ref = oracle.match(wlc, 10, 20, cc, cl)
+    res, _ = _run_device(wl, seqs, L - 2, NR_MODE_AUTO)
+    compare(ref, res, L - 2, exact_below=True, label=f"generic L={L}")
