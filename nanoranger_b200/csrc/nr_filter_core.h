@@ -373,10 +373,14 @@ NR_HD int nr_verify16(const uint32_t *rdp, int m, uint32_t core, int padL, int p
     const int pinned = fwd ? p : p + nr_probe_end(t);
     uint64_t V = nr_window64(rdp, fwd ? pinned - 1 : pinned - 19);
     if (!fwd) V = nr_rev_bases64(V) >> 24;
-    const uint64_t vm = fwd ? nr_valid_mask(1 - pinned, m - pinned + 1)
-                            : nr_valid_mask(pinned - m + 1, pinned + 1);
-    const int flags = nr_lv16(V, vm, fwd ? core : nr_rev_bases32(core));
     const int interior = fwd ? (pinned >= 0 && pinned + 18 <= m) : (pinned >= 19 && pinned <= m);
+    // every base of V[0..18] exists when the pinned end is at least one base inside the read on
+    // both sides: the mask is then all ones (the usual case; saves building it)
+    const int deep = fwd ? (pinned >= 1 && pinned + 18 <= m) : (pinned >= 19 && pinned < m);
+    const uint64_t vm = deep ? 0x5555555555555555ull
+                             : (fwd ? nr_valid_mask(1 - pinned, m - pinned + 1)
+                                    : nr_valid_mask(pinned - m + 1, pinned + 1));
+    const int flags = nr_lv16(V, vm, fwd ? core : nr_rev_bases32(core));
     if (!flags) { *umi = -1; return 3; }
     if (!interior)
         return nr_nfa16_w(nr_window64(rdp, nr_rows_first(p)), m, core, padL, padR,
