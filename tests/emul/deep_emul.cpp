@@ -1,0 +1,106 @@
+// deep_emul.cpp -- host-side emulation of the deep matcher tier (TEST INFRASTRUCTURE).
+// Compiled by tests/ with g++ from the headers the sm_100a kernel includes
+// (nr_deep_core.h: plane automaton + join; nr_deep_index.h: prefix/suffix grouping), so the
+// arithmetic is the shipped code; only the block choreography differs.  Serial and slow on
+// purpose; nothing in nanoranger_b200/ links or calls it.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../nanoranger_b200/csrc/nr_deep_core.h"
+#include "../../nanoranger_b200/csrc/nr_deep_index.h"
+
+namespace {
+
+template <int K>
+void run(const nr_deep_index_host &ix, int padL, int padR, const uint8_t *cand,
+         const uint8_t *clen, int64_t N, int32_t *idx, int8_t *score, int32_t *nbest,
+         uint8_t *strand, uint8_t *took)
+{
+    const int L = ix.L, s = ix.s;
+    std::vector<nr_deep_planes<K>> F(ix.g_pre), B(ix.g_suf);
+    std::vector<int> fmin(ix.g_pre), bmin(ix.g_suf);
+    for (int64_t c = 0; c < N; c++) {
+        const int m = clen[c];
+        took[c] = 0; idx[c] = -1; score[c] = -128; nbest[c] = 0; strand[c] = 0;
+        if (m < 1 || m > NR_DEEP_MAXM) continue;
+        int best = K + 1;
+        int64_t cnt = 0;
+        uint32_t key = 0xFFFFFFFFu;
+        for (int st = 0; st < 2; st++) {
+            uint8_t q[64];
+            for (int i = 0; i < m; i++) {
+                const uint8_t x = cand[c * 64 + (st ? m - 1 - i : i)];
+                q[i] = st ? (x > 3 ? 4 : 3 - x) : x;
+            }
+            nr_deep_rows rows;
+            nr_deep_rows_from_codes(q, m, rows);
+            int gsmin = K + 1;
+            for (uint32_t g = 0; g < ix.g_pre; g++) {
+                nr_deep_init_fwd<K>(F[g], m, padL);
+                const uint32_t lo = ix.pre_rep[4 * g], hi = ix.pre_rep[4 * g + 1], nm = ix.pre_rep[4 * g + 2];
+                for (int j = 0; j < s; j++)
+                    nr_deep_step_fwd<K>(F[g], rows, nr_core_col(lo, hi, j), (nm >> j) & 1u);
+                fmin[g] = nr_deep_min<K>(F[g]);
+            }
+            for (uint32_t h = 0; h < ix.g_suf; h++) {
+                nr_deep_init_bwd<K>(B[h], m, padR, rows.valid);
+                const uint32_t lo = ix.suf_rep[4 * h], hi = ix.suf_rep[4 * h + 1], nm = ix.suf_rep[4 * h + 2];
+                for (int j = L - 1; j >= s; j--)
+                    nr_deep_step_bwd<K>(B[h], rows, nr_core_col(lo, hi, j), (nm >> j) & 1u);
+                bmin[h] = nr_deep_min<K>(B[h]);
+                if (bmin[h] < gsmin) gsmin = bmin[h];
+            }
+            for (uint32_t g = 0; g < ix.g_pre; g++) {
+                const int bound = best > K ? K : best;
+                if (fmin[g] + gsmin > bound) continue;
+                for (uint32_t p = ix.pre_start[g]; p < ix.pre_start[g + 1]; p++) {
+                    const uint32_t h = ix.ent_suf[p];
+                    const int bnd = best > K ? K : best;
+                    const int lb = fmin[g] + bmin[h];
+                    if (lb > bnd) continue;
+                    const int t = nr_deep_join<K>(F[g].v, B[h].v, lb, bnd);
+                    if (t > K) continue;
+                    const uint32_t k = (ix.ent_idx[p] << 1) | (uint32_t)st;
+                    if (t < best) { best = t; cnt = 1; key = k; }
+                    else if (t == best) { cnt++; if (k < key) key = k; }
+                }
+            }
+        }
+        if (best <= K) {
+            took[c] = 1;
+            idx[c] = (int32_t)(key >> 1);
+            strand[c] = (uint8_t)(key & 1u);
+            score[c] = (int8_t)(L - best);
+            nbest[c] = (int32_t)cnt;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// wl_lo / wl_hi / wl_nm: packed cores (hi, nm nullable).  cand: N x 64 codes (4 = N), clen: N.
+// took[i] = 0 when no (entry, strand) pair reaches cost <= K (or the read has no / too many
+// rows): the kernel hands those to the next tier.
+int nr_emul_deep(const uint32_t *wl_lo, const uint32_t *wl_hi, const uint32_t *wl_nm, int64_t n,
+                 int L, int padL, int padR, int K, int force_s, const uint8_t *cand,
+                 const uint8_t *clen, int64_t N, int32_t *idx, int8_t *score, int32_t *nbest,
+                 uint8_t *strand, uint8_t *took, int32_t *info /* s, g_pre, g_suf */)
+{
+    if (L < 2 || L > 32) return -1;
+    nr_deep_index_host ix;
+    nr_deep_index_build(wl_lo, wl_hi, wl_nm, (uint64_t)n, L, force_s, ix);
+    if (info) { info[0] = ix.s; info[1] = (int32_t)ix.g_pre; info[2] = (int32_t)ix.g_suf; }
+    switch (K) {
+    case 2: run<2>(ix, padL, padR, cand, clen, N, idx, score, nbest, strand, took); break;
+    case 3: run<3>(ix, padL, padR, cand, clen, N, idx, score, nbest, strand, took); break;
+    case 5: run<5>(ix, padL, padR, cand, clen, N, idx, score, nbest, strand, took); break;
+    case 8: run<8>(ix, padL, padR, cand, clen, N, idx, score, nbest, strand, took); break;
+    default: return -2;
+    }
+    return 0;
+}
+
+}  // extern "C"
