@@ -47,8 +47,10 @@ extern "C" {
 #define NR_UMI_NONE 255
 
 /* matcher modes */
-#define NR_MODE_AUTO 0        /* filtered when the whitelist geometry allows it, else exhaustive */
-#define NR_MODE_EXHAUSTIVE 1  /* score every (entry, strand) pair; exact at every score          */
+#define NR_MODE_AUTO 0        /* exact at every score: seed filter where the whitelist geometry
+                                 allows it, deep tier (meet in the middle) for what it leaves,
+                                 brute-force DP for the rest                                     */
+#define NR_MODE_EXHAUSTIVE 1  /* brute-force DP over every (entry, strand) pair                  */
 #define NR_MODE_FILTERED 2    /* lossless seed filter + exact verification; exact for
                                  score >= min_score, requires L == 16, N-free whitelist and
                                  min_score >= L - 2                                              */
@@ -210,6 +212,15 @@ int nr_match_device_counted(const nr_whitelist_t *wl, const void *d_bases, const
  * c[0] index probes, c[1] bitmap hits, c[2] exact verifications, c[3] verifications that found
  * cost <= 2, c[4] candidates sent to the exhaustive kernel. */
 int nr_match_counters(const void *d_workspace, uint64_t *c5, void *stream);
+
+/* Where the candidates of the last nr_match_device / nr_match_device_counted call on this
+ * workspace were resolved: t[0] left by the seed filter (contain N, shorter than 24 nt, more than
+ * 32 co-optimal pairs, and in NR_MODE_AUTO every read below the threshold) or, on whitelists
+ * without a seed index, 0; t[1] resolved by the deep tier at cost <= 3, t[2] at cost <= 5
+ * (meet-in-the-middle over the whole whitelist, nr_match_deep.cu); t[3] left to the brute-force
+ * DP kernel.  These are the reads whose scores fill the low tail of `_barcode_scores.csv`
+ * (utils.py:698, 728-730). */
+int nr_match_tier_counts(const void *d_workspace, uint64_t *t4, void *stream);
 
 #ifdef __cplusplus
 }

@@ -36,7 +36,7 @@ SYMBOLS = (
     "nr_int_peak_dual", "nr_match_device_counted", "nr_match_counters",
     "nr_umi_records_device", "nr_umi_records_workspace_bytes", "nr_umi_partition_device",
     "nr_umi_unzip_device", "nr_hw_search_device", "nr_hw_search_host",
-    "nr_sam_write",
+    "nr_sam_write", "nr_match_tier_counts",
 )
 
 _lib = None
@@ -105,6 +105,8 @@ def lib() -> C.CDLL:
     L.nr_int_peak_dual.restype = i32
     L.nr_match_counters.argtypes = [vp, C.POINTER(u64), vp]
     L.nr_match_counters.restype = i32
+    L.nr_match_tier_counts.argtypes = [vp, C.POINTER(u64), vp]
+    L.nr_match_tier_counts.restype = i32
     _lib = L
     return L
 

@@ -42,6 +42,16 @@ struct nr_whitelist {
     uint32_t *d_rank[4];
     uint2 *d_ents[4];
     uint32_t *d_kstart[4];
+    // deep tier (nr_deep_core.h, nr_deep_index.h): entries grouped by their first deep_s columns
+    // (prefix groups, runs of the sorted order) and by their last L - deep_s (suffix groups)
+    int has_deep;
+    int deep_s;
+    uint32_t deep_gpre, deep_gsuf;
+    uint32_t *d_deep_pre_start;   // deep_gpre + 1
+    uint4 *d_deep_pre_rep;        // deep_gpre: {lo, hi, nm, 0} of the group's columns
+    uint4 *d_deep_suf_rep;        // deep_gsuf
+    uint32_t *d_deep_ent_suf;     // n: suffix group per sorted position
+    uint32_t *d_deep_ent_idx;     // n: entry index per sorted position
     size_t bytes;
     void *host_ctx;  // lazily created staging state of nr_match_host (nr_match_api.cu)
 };

@@ -152,19 +152,21 @@ NR_HD int nr_deep_min(const nr_deep_planes<K> &x)
     return r;
 }
 
-// cost of joining a prefix state with a suffix state: smallest t in [from, upto] with
-// OR_{a+b=t} F_a & B_b != 0, else K + 1 (planes are cumulative, so t is the exact cost when
-// it is <= K)
+// cost of joining a prefix state with a suffix state: smallest t with OR_{a+b=t} F_a & B_b != 0
+// (planes are cumulative, so that t is the exact cost when it is <= K), K + 1 if none.  Fully
+// unrolled with compile-time plane indices so that f and b stay in registers on the device.
 template <int K>
-NR_HD int nr_deep_join(const uint64_t *f, const uint64_t *b, int from, int upto)
+NR_HD int nr_deep_join(const uint64_t *f, const uint64_t *b)
 {
-    if (upto > K) upto = K;
-    for (int t = from < 0 ? 0 : from; t <= upto; t++) {
+    int res = K + 1;
+#pragma unroll
+    for (int t = K; t >= 0; t--) {
         uint64_t any = 0;
+#pragma unroll
         for (int a = 0; a <= t; a++) any |= f[a] & b[t - a];
-        if (any) return t;
+        if (any) res = t;
     }
-    return K + 1;
+    return res;
 }
 
 // column j of a packed core (lo: columns 0..15, hi: 16..31, nm: N columns)

@@ -21,10 +21,26 @@ int nr_launch_filtered(const nr_whitelist *wl, const void *d_bases, const uint8_
                        uint32_t *d_list, uint32_t *d_list_count, unsigned long long *d_counters,
                        int *grid_out, cudaStream_t stream);
 
-// workspace layout: [0,64) eight u64 counters, [64,68) list count, [72,80) next tile of the
-// filtered kernel, [128, 128 + 8 KB) the
-// exhaustive kernel's arrival counters (zeroed with the header), then its partials,
-// [NR_WS_HEADER, NR_WS_HEADER + 4n) list
+int nr_launch_deep(const nr_whitelist *wl, int K, const void *d_bases, const uint8_t *d_meta,
+                   const uint64_t *d_nmask, const uint32_t *d_list, const uint32_t *d_list_count,
+                   uint64_t n_cand, int min_score, int32_t *d_idx, int8_t *d_score,
+                   uint8_t *d_nbest, uint8_t *d_flags, uint8_t *d_umi, uint32_t *d_next_list,
+                   uint32_t *d_next_count, unsigned long long *d_work_next,
+                   unsigned long long *d_resolved, uint8_t *d_scratch, size_t scratch_bytes,
+                   cudaStream_t stream);
+size_t nr_deep_scratch_bytes(const nr_whitelist *wl, int K);
+int nr_deep_usable(const nr_whitelist *wl);
+
+// workspace layout (header zeroed before every call):
+//   [0,64)    eight u64 counters: probes, hits, verifications, passes, listed (counting build of
+//             the filtered kernel), candidates resolved by the deep tier at K = 3 and at K = 5
+//   [64,68)   count of list A: candidates the filtered kernel leaves (-> deep tier, K = 3)
+//   [68,72)   count of list B: left by the deep tier at K = 3 (-> K = 5)
+//   [72,80)   next tile of the filtered kernel
+//   [80,84)   count of list C: left by the deep tier at K = 5 (-> exhaustive DP kernel)
+//   [88,96)   next work item of the deep tier at K = 3, [96,104) at K = 5
+//   [128, 128 + 8 KB)  the exhaustive kernel's arrival counters, then its partials
+//   [NR_WS_HEADER, +4n) list A, then list B, list C (4n each), then the deep tier's scratch
 #define NR_WS_ZERO (128 + NR_EX_MAXGRID * 4)
 #define NR_WS_HEADER 65536
 static_assert(128 + NR_EX_SCRATCH_BYTES <= NR_WS_HEADER, "workspace header too small");
@@ -42,12 +58,50 @@ struct DeviceGuard {
     }
     ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
 };
+
+size_t lists_bytes(uint64_t n) { return (((size_t)n * sizeof(uint32_t) * 3) + 255) & ~(size_t)255; }
+
+size_t deep_scratch(const nr_whitelist *wl)
+{
+    const size_t a = nr_deep_scratch_bytes(wl, 3), b = nr_deep_scratch_bytes(wl, 5);
+    return a > b ? a : b;
+}
+
+// list A (or every candidate when from_all) -> deep tier K = 3 -> K = 5 -> exhaustive DP kernel,
+// all on the stream, counts on the device
+int resolve_chain(const nr_whitelist *wl, const void *d_bases, const uint8_t *d_meta,
+                  const uint64_t *d_nmask, uint64_t n, int min_score, bool from_all,
+                  int32_t *d_idx, int8_t *d_score, uint8_t *d_nbest, uint8_t *d_flags,
+                  uint8_t *d_umi_q, uint8_t *ws, size_t ws_bytes, int sms, cudaStream_t st)
+{
+    uint32_t *listA = (uint32_t *)(ws + NR_WS_HEADER), *listB = listA + n, *listC = listB + n;
+    uint32_t *cntA = (uint32_t *)(ws + 64), *cntB = (uint32_t *)(ws + 68), *cntC = (uint32_t *)(ws + 80);
+    unsigned long long *ctr = (unsigned long long *)ws;
+    const uint32_t *ex_list = listA, *ex_cnt = cntA;
+    if (nr_deep_usable(wl)) {
+        uint8_t *scratch = ws + NR_WS_HEADER + lists_bytes(n);
+        const size_t sb = ws_bytes - NR_WS_HEADER - lists_bytes(n);
+        int rc = nr_launch_deep(wl, 3, d_bases, d_meta, d_nmask, from_all ? nullptr : listA, cntA, n,
+                                min_score, d_idx, d_score, d_nbest, d_flags, d_umi_q, listB, cntB,
+                                (unsigned long long *)(ws + 88), ctr + 5, scratch, sb, st);
+        if (rc != NR_OK) return rc;
+        rc = nr_launch_deep(wl, 5, d_bases, d_meta, d_nmask, listB, cntB, n, min_score, d_idx,
+                            d_score, d_nbest, d_flags, d_umi_q, listC, cntC,
+                            (unsigned long long *)(ws + 96), ctr + 6, scratch, sb, st);
+        if (rc != NR_OK) return rc;
+        ex_list = listC; ex_cnt = cntC;
+    } else if (from_all) {
+        ex_list = nullptr; ex_cnt = nullptr;
+    }
+    return nr_launch_exhaustive(wl, d_bases, d_meta, d_nmask, ex_list, ex_cnt, n, min_score, d_idx,
+                                d_score, d_nbest, d_flags, d_umi_q, sms * 2, ws + 128, st);
+}
 }  // namespace
 
 extern "C" size_t nr_match_workspace_bytes(const nr_whitelist_t *wl, uint64_t n, int mode)
 {
-    (void)wl; (void)mode;
-    return NR_WS_HEADER + (size_t)n * sizeof(uint32_t);
+    (void)mode;
+    return NR_WS_HEADER + lists_bytes(n) + (wl ? deep_scratch(wl) : 0);
 }
 
 static int resolve_mode(const nr_whitelist *wl, int min_score, int mode)
@@ -85,9 +139,10 @@ extern "C" int nr_match_device(const nr_whitelist_t *wl, const void *d_bases,
     cudaStream_t st = (cudaStream_t)stream;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
-    if (eff == NR_MODE_EXHAUSTIVE) {
-        // the workspace is optional here: with one, batches smaller than the grid are split
-        // over the whitelist
+    const bool ws_ok = d_workspace && workspace_bytes >= nr_match_workspace_bytes(wl, n, mode);
+    if (eff == NR_MODE_EXHAUSTIVE && (mode == NR_MODE_EXHAUSTIVE || !nr_deep_usable(wl) || !ws_ok)) {
+        // the brute-force DP over every (entry, strand) pair.  The workspace is optional here:
+        // with one, batches smaller than the grid are split over the whitelist
         void *scratch = nullptr;
         if (d_workspace && workspace_bytes >= NR_WS_HEADER) {
             NR_CHECK_CUDA(cudaMemsetAsync(d_workspace, 0, NR_WS_ZERO, st));
@@ -96,24 +151,29 @@ extern "C" int nr_match_device(const nr_whitelist_t *wl, const void *d_bases,
         return nr_launch_exhaustive(wl, d_bases, d_meta, d_nmask, nullptr, nullptr, n, min_score,
                                     d_idx, d_score, d_nbest, d_flags, d_umi_q, sms * 2, scratch, st);
     }
-    if (!d_workspace || workspace_bytes < nr_match_workspace_bytes(wl, n, mode)) {
+    if (!ws_ok) {
         nr_set_error("nr_match_device: workspace too small (%zu < %zu)", workspace_bytes,
                      nr_match_workspace_bytes(wl, n, mode));
         return NR_EINVAL;
     }
     uint8_t *ws = (uint8_t *)d_workspace;
+    NR_CHECK_CUDA(cudaMemsetAsync(ws, 0, NR_WS_ZERO, st));
+    if (eff == NR_MODE_EXHAUSTIVE)
+        // AUTO on a whitelist without a seed index (slide-seq cores, N columns): every candidate
+        // through the deep tier, the brute-force kernel only for what it leaves
+        return resolve_chain(wl, d_bases, d_meta, d_nmask, n, min_score, true, d_idx, d_score,
+                             d_nbest, d_flags, d_umi_q, ws, workspace_bytes, sms, st);
     uint32_t *d_count = (uint32_t *)(ws + 64);
     uint32_t *d_list = (uint32_t *)(ws + NR_WS_HEADER);
-    NR_CHECK_CUDA(cudaMemsetAsync(ws, 0, NR_WS_ZERO, st));
     int grid = 0;
     int rc = nr_launch_filtered(wl, d_bases, d_meta, n, min_score, eff == NR_MODE_AUTO ? 1 : 0,
                                 d_idx, d_score, d_nbest, d_flags, d_umi_q, d_list, d_count,
                                 nullptr, &grid, st);
     if (rc != NR_OK) return rc;
     // candidates the filter left (N, short, > 32 co-optimal pairs; in AUTO also everything below
-    // cost 2) are resolved exactly, count read on the device
-    return nr_launch_exhaustive(wl, d_bases, d_meta, d_nmask, d_list, d_count, n, min_score, d_idx,
-                                d_score, d_nbest, d_flags, d_umi_q, sms * 2, ws + 128, st);
+    // cost 2) are resolved exactly, counts read on the device
+    return resolve_chain(wl, d_bases, d_meta, d_nmask, n, min_score, false, d_idx, d_score,
+                         d_nbest, d_flags, d_umi_q, ws, workspace_bytes, sms, st);
 }
 
 // Debug/bench variant: same as NR_MODE_FILTERED but with the counting kernel; fills the five
@@ -139,9 +199,8 @@ extern "C" int nr_match_device_counted(const nr_whitelist_t *wl, const void *d_b
     if (rc != NR_OK) return rc;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
-    return nr_launch_exhaustive(wl, d_bases, d_meta, d_nmask, (uint32_t *)(ws + NR_WS_HEADER),
-                                (uint32_t *)(ws + 64), n, min_score, d_idx, d_score, d_nbest,
-                                d_flags, d_umi_q, sms * 2, ws + 128, st);
+    return resolve_chain(wl, d_bases, d_meta, d_nmask, n, min_score, false, d_idx, d_score,
+                         d_nbest, d_flags, d_umi_q, ws, workspace_bytes, sms, st);
 }
 
 extern "C" int nr_match_counters(const void *d_workspace, uint64_t *c5, void *stream)
@@ -153,6 +212,20 @@ extern "C" int nr_match_counters(const void *d_workspace, uint64_t *c5, void *st
     NR_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     for (int i = 0; i < 4; i++) c5[i] = h[i];
     c5[4] = (uint32_t)(h[8] & 0xFFFFFFFFu);   // list count (candidates sent to the exhaustive kernel)
+    return NR_OK;
+}
+
+extern "C" int nr_match_tier_counts(const void *d_workspace, uint64_t *t4, void *stream)
+{
+    if (!d_workspace || !t4) { nr_set_error("nr_match_tier_counts: null pointer"); return NR_EINVAL; }
+    uint64_t h[11];
+    NR_CHECK_CUDA(cudaMemcpyAsync(h, d_workspace, sizeof(h), cudaMemcpyDeviceToHost,
+                                  (cudaStream_t)stream));
+    NR_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    t4[0] = (uint32_t)(h[8] & 0xFFFFFFFFu);     // list A count (offset 64)
+    t4[1] = h[5];
+    t4[2] = h[6];
+    t4[3] = (uint32_t)(h[10] & 0xFFFFFFFFu);    // list C count (offset 80)
     return NR_OK;
 }
 

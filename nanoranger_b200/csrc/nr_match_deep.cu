@@ -1,0 +1,323 @@
+// nr_match_deep.cu -- the deep matcher tier: exact best (entry, strand) of a candidate over the
+// WHOLE whitelist for costs up to K, by meeting in the middle (nr_deep_core.h).
+//
+// Replaces scripts/barcode_align.sh:14-41 for the reads the seed filter cannot decide -- best
+// score below core_len - 2, more than 32 co-optimal pairs, reads shorter than the filter takes,
+// whitelists without a seed index (slide-seq cores) -- so that `_barcode_scores.csv`
+// (utils.py:698, 728-730: every uniquely mapped forward read at every AS) is exact at any input
+// size.  Per candidate the work is  (G_pre * s + G_suf * (L - s)) automaton column steps plus two
+// byte loads per entry, instead of the n * L * m cells of the brute-force DP
+// (nr_match_exhaustive.cu): 737K-august-2016 has 1 920 distinct 8-column prefixes and 1 536
+// suffixes, i.e. 55 K column steps against 23.6 M DP columns.
+//
+// Mapping.  One block resolves one candidate at a time (dynamic hand-out), strand after strand:
+//   rows     the strand's row masks (which read rows carry base c / N) from two ballots
+//   phase A  thread = one prefix or suffix group: K+1 planes of 64 read rows in registers, one
+//            automaton step per core column; planes [e][group] and the group's minimum into
+//            shared memory (global scratch, L2, when the whitelist has too many groups)
+//   phase B  warp = one prefix group (handed out through a shared counter), skipped when
+//            min(prefix) + min over all suffixes exceeds the running best; lane = one entry:
+//            suffix id (coalesced), two byte minima, and only if they can still reach the best the
+//            plane join  OR_{a+b=t} F_a & B_b
+//   merge    best cost / pairs attaining it / smallest pair, per thread, then over the block
+// The winner's UMI column and flags come from the same scalar pair DP the exhaustive kernel uses.
+// Candidates without any pair at cost <= K (or with more than 63 bases) go to the next tier's list.
+#include "nr_common.cuh"
+#include "nr_deep_core.h"
+#include "nr_ex_common.cuh"
+
+#define NR_DEEP_THREADS 1024
+
+struct nr_deep_params {
+    // grouping (nr_deep_index.h)
+    const uint32_t *pre_start;
+    const uint4 *pre_rep, *suf_rep;
+    const uint32_t *ent_suf, *ent_idx;
+    uint32_t g_pre, g_suf;
+    int L, s, padL, padR;
+    // whitelist cores (result writer)
+    const uint32_t *lo, *hi, *nm;
+    // candidates
+    const uint4 *bases;
+    const uint8_t *meta;
+    const uint64_t *nmask;
+    const uint32_t *list;          // nullable: all n_cand candidates
+    const uint32_t *list_count;
+    uint64_t n_cand;
+    int min_score;
+    int32_t *o_idx;
+    int8_t *o_score;
+    uint8_t *o_nbest, *o_flags, *o_umi;
+    uint32_t *next_list;           // candidates this tier leaves
+    uint32_t *next_count;
+    unsigned long long *work_next; // next work item (zeroed with the workspace header)
+    unsigned long long *resolved;  // nullable counter
+    uint8_t *scratch;              // plane tables when they do not fit shared memory
+    size_t scratch_per_block;
+};
+
+namespace {
+
+using namespace nr_ex;
+
+template <bool SMEM>
+__device__ __forceinline__ uint64_t plane_ld(const uint64_t *p)
+{
+    if (SMEM) return *p;
+    return (uint64_t)__ldcg(reinterpret_cast<const unsigned long long *>(p));
+}
+template <bool SMEM>
+__device__ __forceinline__ void plane_st(uint64_t *p, uint64_t v)
+{
+    if (SMEM) *p = v;
+    else __stcg(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v);
+}
+
+template <int K, bool SMEM>
+__global__ void __launch_bounds__(NR_DEEP_THREADS, 1)
+nr_match_deep_kernel(const nr_deep_params P)
+{
+    extern __shared__ __align__(16) uint8_t dyn[];
+    __shared__ uint8_t cf[NR_MAX_QUERY], cr[NR_MAX_QUERY];
+    __shared__ nr_deep_rows s_rows;
+    __shared__ uint32_t s_bal[2][5];
+    __shared__ int s_bound, s_gsmin;
+    __shared__ uint32_t s_grp_next;
+    __shared__ unsigned long long s_item;
+    __shared__ int s_rc[32];
+    __shared__ uint32_t s_rn[32], s_rk[32];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t G = P.g_pre + P.g_suf;
+    uint64_t *planes;
+    uint8_t *mins;
+    if (SMEM) {
+        planes = reinterpret_cast<uint64_t *>(dyn);
+        mins = dyn + (size_t)G * (K + 1) * sizeof(uint64_t);
+    } else {
+        planes = reinterpret_cast<uint64_t *>(P.scratch + (size_t)blockIdx.x * P.scratch_per_block);
+        mins = dyn;
+    }
+    const uint64_t total = P.list ? (uint64_t)*P.list_count : P.n_cand;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(P.work_next, 1ull);
+        __syncthreads();
+        const uint64_t it = s_item;
+        if (it >= total) break;
+        const uint64_t cand = P.list ? (uint64_t)P.list[it] : it;
+        const uint8_t mt = P.meta[cand];
+        const int m = mt & 0x7F;
+        if (mt == 0xFF || m < 1 || m > NR_DEEP_MAXM) {
+            if (tid == 0) P.next_list[atomicAdd(P.next_count, 1u)] = (uint32_t)cand;
+            continue;
+        }
+        load_codes(P.bases, (mt & 0x80) ? P.nmask : nullptr, cand, m, cf, cr);
+        if (tid == 0) s_bound = K;
+        int bc = K + 1;                 // this thread's best cost / pairs / smallest pair
+        uint32_t bn = 0, bk = 0xFFFFFFFFu;
+
+#pragma unroll 1
+        for (int st = 0; st < 2; st++) {
+            __syncthreads();            // codes visible; previous strand's phase B finished
+            if (tid < 64) {
+                const int code = (st ? cr : cf)[tid];
+                const bool ok = (int)tid < m;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const uint32_t b = __ballot_sync(0xffffffffu, ok && code == c);
+                    if (lane == 0) s_bal[warp][c] = b;
+                }
+                const uint32_t bn_ = __ballot_sync(0xffffffffu, ok && code > 3);
+                if (lane == 0) s_bal[warp][4] = bn_;
+            }
+            if (tid == 0) { s_gsmin = K + 1; s_grp_next = 0; }
+            __syncthreads();
+            if (tid < 5) {
+                const uint64_t v = ((((uint64_t)s_bal[1][tid]) << 32) | (uint64_t)s_bal[0][tid]) << 1;
+                if (tid < 4) s_rows.eq[tid] = v; else s_rows.nrow = v;
+            }
+            if (tid == 5) {
+                s_rows.valid = (m >= 63) ? ~0ull : ((1ull << (m + 1)) - 1ull);
+                s_rows.edge = 1ull | (1ull << m);
+            }
+            __syncthreads();
+
+            // ---- phase A: one automaton per distinct prefix / suffix ---------------------------
+            int my_smin = K + 1;
+            for (uint32_t g = tid; g < G; g += NR_DEEP_THREADS) {
+                nr_deep_planes<K> x;
+                if (g < P.g_pre) {
+                    const uint4 rep = __ldg(P.pre_rep + g);
+                    nr_deep_init_fwd<K>(x, m, P.padL);
+#pragma unroll 1
+                    for (int j = 0; j < P.s; j++)
+                        nr_deep_step_fwd<K>(x, s_rows, nr_core_col(rep.x, rep.y, j), (rep.z >> j) & 1u);
+                } else {
+                    const uint4 rep = __ldg(P.suf_rep + (g - P.g_pre));
+                    nr_deep_init_bwd<K>(x, m, P.padR, s_rows.valid);
+#pragma unroll 1
+                    for (int j = P.L - 1; j >= P.s; j--)
+                        nr_deep_step_bwd<K>(x, s_rows, nr_core_col(rep.x, rep.y, j), (rep.z >> j) & 1u);
+                }
+                const int mn = nr_deep_min<K>(x);
+#pragma unroll
+                for (int e = 0; e <= K; e++) plane_st<SMEM>(planes + (size_t)e * G + g, x.v[e]);
+                mins[g] = (uint8_t)mn;
+                if (g >= P.g_pre) my_smin = min(my_smin, mn);
+            }
+            my_smin = __reduce_min_sync(0xffffffffu, my_smin);
+            if (lane == 0 && my_smin <= K) atomicMin(&s_gsmin, my_smin);
+            __syncthreads();
+
+            // ---- phase B: entries, prefix group by prefix group ----------------------------------
+            const int gsmin = s_gsmin;
+            for (;;) {
+                uint32_t g = 0;
+                if (lane == 0) g = atomicAdd(&s_grp_next, 1u);
+                g = __shfl_sync(0xffffffffu, g, 0);
+                if (g >= P.g_pre) break;
+                const int fm = mins[g];
+                if (fm + gsmin > *(volatile int *)&s_bound) continue;
+                uint64_t f[K + 1];
+#pragma unroll
+                for (int e = 0; e <= K; e++) f[e] = plane_ld<SMEM>(planes + (size_t)e * G + g);
+                const uint32_t p1 = __ldg(P.pre_start + g + 1);
+                for (uint32_t p = __ldg(P.pre_start + g) + lane; p < p1; p += 32) {
+                    const uint32_t h = __ldg(P.ent_suf + p);
+                    const int lb = fm + mins[P.g_pre + h];
+                    const int bound = *(volatile int *)&s_bound;
+                    if (lb <= bound) {
+                        uint64_t b[K + 1];
+#pragma unroll
+                        for (int e = 0; e <= K; e++)
+                            b[e] = plane_ld<SMEM>(planes + (size_t)e * G + P.g_pre + h);
+                        const int t = nr_deep_join<K>(f, b);
+                        if (t <= bound) {
+                            const uint32_t key = (__ldg(P.ent_idx + p) << 1) | (uint32_t)st;
+                            if (t < bc) { bc = t; bn = 1; bk = key; atomicMin(&s_bound, t); }
+                            else if (t == bc) { bn++; bk = min(bk, key); }
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- merge over the block --------------------------------------------------------------
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int c2 = __shfl_xor_sync(0xffffffffu, bc, o);
+            const uint32_t n2 = __shfl_xor_sync(0xffffffffu, bn, o);
+            const uint32_t k2 = __shfl_xor_sync(0xffffffffu, bk, o);
+            if (c2 < bc) { bc = c2; bn = n2; bk = k2; }
+            else if (c2 == bc) { bn += n2; bk = min(bk, k2); }
+        }
+        if (lane == 0) { s_rc[warp] = bc; s_rn[warp] = bn; s_rk[warp] = bk; }
+        __syncthreads();
+        if (tid == 0) {
+            int c = K + 1;
+            uint32_t n = 0, k = 0xFFFFFFFFu;
+            for (int w = 0; w < NR_DEEP_THREADS / 32; w++) {
+                if (s_rc[w] < c) { c = s_rc[w]; n = s_rn[w]; k = s_rk[w]; }
+                else if (s_rc[w] == c) { n += s_rn[w]; k = min(k, s_rk[w]); }
+            }
+            if (c <= K) {
+                Best r; r.score = P.L - c; r.cnt = n; r.key = k;
+                write_result(r, cand, m, cf, P.lo, P.hi, P.nm, P.L, P.padL, P.padR, P.min_score,
+                             P.o_idx, P.o_score, P.o_nbest, P.o_flags, P.o_umi);
+                if (P.resolved) atomicAdd(P.resolved, 1ull);
+            } else {
+                P.next_list[atomicAdd(P.next_count, 1u)] = (uint32_t)cand;
+            }
+        }
+    }
+}
+
+size_t deep_planes_bytes(const nr_whitelist *wl, int K)
+{
+    return (size_t)(wl->deep_gpre + wl->deep_gsuf) * (size_t)(K + 1) * sizeof(uint64_t);
+}
+
+constexpr size_t DEEP_SMEM_MAX = 227 * 1024 - 2048;    // dynamic budget next to ~1 KB static
+
+template <int K>
+int launch_k(const nr_whitelist *wl, nr_deep_params &P, uint8_t *d_scratch, size_t scratch_bytes,
+             cudaStream_t stream)
+{
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
+    const size_t G = (size_t)wl->deep_gpre + wl->deep_gsuf;
+    const size_t pb = deep_planes_bytes(wl, K);
+    if (pb + G <= DEEP_SMEM_MAX) {
+        const size_t smem = pb + G;
+        NR_CHECK_CUDA(cudaFuncSetAttribute(nr_match_deep_kernel<K, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nr_match_deep_kernel<K, true><<<sms, NR_DEEP_THREADS, smem, stream>>>(P);
+    } else {
+        const size_t per = (pb + 255) & ~(size_t)255;
+        size_t blocks = d_scratch ? scratch_bytes / per : 0;
+        if (blocks > (size_t)sms) blocks = (size_t)sms;
+        if (blocks == 0 || G > DEEP_SMEM_MAX) {
+            nr_set_error("deep tier: no scratch for %zu groups", G);
+            return NR_EINVAL;
+        }
+        P.scratch = d_scratch;
+        P.scratch_per_block = per;
+        NR_CHECK_CUDA(cudaFuncSetAttribute(nr_match_deep_kernel<K, false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G));
+        nr_match_deep_kernel<K, false><<<(unsigned)blocks, NR_DEEP_THREADS, G, stream>>>(P);
+    }
+    NR_CHECK_CUDA(cudaGetLastError());
+    return NR_OK;
+}
+
+}  // namespace
+
+// global scratch one launch of the deep tier needs (0 when the plane tables fit shared memory)
+size_t nr_deep_scratch_bytes(const nr_whitelist *wl, int K)
+{
+    if (!wl->has_deep) return 0;
+    const size_t G = (size_t)wl->deep_gpre + wl->deep_gsuf;
+    const size_t pb = deep_planes_bytes(wl, K);
+    if (pb + G <= DEEP_SMEM_MAX) return 0;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
+    return (size_t)sms * ((pb + 255) & ~(size_t)255);
+}
+
+// whether the tier can run at all on this whitelist (group minima must fit shared memory)
+int nr_deep_usable(const nr_whitelist *wl)
+{
+    return wl->has_deep && ((size_t)wl->deep_gpre + wl->deep_gsuf) <= DEEP_SMEM_MAX;
+}
+
+// Enqueue the deep tier (K = 3 or 5) on `stream`: candidates of (d_list, d_list_count) -- or all
+// n_cand when d_list is null -- are resolved exactly when their best cost is <= K; the others are
+// appended to (d_next_list, d_next_count).  *d_work_next must be zero.
+int nr_launch_deep(const nr_whitelist *wl, int K, const void *d_bases, const uint8_t *d_meta,
+                   const uint64_t *d_nmask, const uint32_t *d_list, const uint32_t *d_list_count,
+                   uint64_t n_cand, int min_score, int32_t *d_idx, int8_t *d_score,
+                   uint8_t *d_nbest, uint8_t *d_flags, uint8_t *d_umi, uint32_t *d_next_list,
+                   uint32_t *d_next_count, unsigned long long *d_work_next,
+                   unsigned long long *d_resolved, uint8_t *d_scratch, size_t scratch_bytes,
+                   cudaStream_t stream)
+{
+    if (!nr_deep_usable(wl)) { nr_set_error("deep tier not available for this whitelist"); return NR_EUNSUPPORTED; }
+    if (!d_list && n_cand == 0) return NR_OK;
+    nr_deep_params P;
+    P.pre_start = wl->d_deep_pre_start; P.pre_rep = wl->d_deep_pre_rep; P.suf_rep = wl->d_deep_suf_rep;
+    P.ent_suf = wl->d_deep_ent_suf; P.ent_idx = wl->d_deep_ent_idx;
+    P.g_pre = wl->deep_gpre; P.g_suf = wl->deep_gsuf;
+    P.L = (int)wl->L; P.s = wl->deep_s; P.padL = (int)wl->pad_l; P.padR = (int)wl->pad_r;
+    P.lo = wl->d_lo; P.hi = wl->d_hi; P.nm = wl->d_nm;
+    P.bases = (const uint4 *)d_bases; P.meta = d_meta; P.nmask = d_nmask;
+    P.list = d_list; P.list_count = d_list_count; P.n_cand = n_cand; P.min_score = min_score;
+    P.o_idx = d_idx; P.o_score = d_score; P.o_nbest = d_nbest; P.o_flags = d_flags; P.o_umi = d_umi;
+    P.next_list = d_next_list; P.next_count = d_next_count; P.work_next = d_work_next;
+    P.resolved = d_resolved; P.scratch = nullptr; P.scratch_per_block = 0;
+    if (K == 3) return launch_k<3>(wl, P, d_scratch, scratch_bytes, stream);
+    if (K == 5) return launch_k<5>(wl, P, d_scratch, scratch_bytes, stream);
+    nr_set_error("deep tier: K must be 3 or 5");
+    return NR_EINVAL;
+}

@@ -14,6 +14,7 @@
 
 #include "nr_common.cuh"
 #include "nr_filter_core.h"
+#include "nr_deep_index.h"
 
 static thread_local char g_err[512] = "";
 
@@ -202,6 +203,30 @@ extern "C" int nr_whitelist_create(const char *cores, uint64_t n, uint32_t core_
         }
         w->has_index = 1;
     }
+    if (core_len >= 2) {
+        // deep tier: prefix / suffix grouping (host: two sorts of n keys)
+        nr_deep_index_host ix;
+        nr_deep_index_build(lo.data(), core_len > 16 ? hi.data() : nullptr,
+                            has_n ? nmv.data() : nullptr, n, (int)core_len, 0, ix);
+        w->deep_s = ix.s; w->deep_gpre = ix.g_pre; w->deep_gsuf = ix.g_suf;
+        const size_t b_ps = (size_t)(ix.g_pre + 1) * 4, b_pr = (size_t)ix.g_pre * 16,
+                     b_sr = (size_t)ix.g_suf * 16;
+        if (cudaMalloc(&w->d_deep_pre_start, b_ps) != cudaSuccess ||
+            cudaMalloc(&w->d_deep_pre_rep, b_pr) != cudaSuccess ||
+            cudaMalloc(&w->d_deep_suf_rep, b_sr) != cudaSuccess ||
+            cudaMalloc(&w->d_deep_ent_suf, nb) != cudaSuccess ||
+            cudaMalloc(&w->d_deep_ent_idx, nb) != cudaSuccess) {
+            nr_set_error("cudaMalloc deep index");
+            return fail(NR_ENOMEM);
+        }
+        w->bytes += b_ps + b_pr + b_sr + 2 * nb;
+        cudaMemcpy(w->d_deep_pre_start, ix.pre_start.data(), b_ps, cudaMemcpyHostToDevice);
+        cudaMemcpy(w->d_deep_pre_rep, ix.pre_rep.data(), b_pr, cudaMemcpyHostToDevice);
+        cudaMemcpy(w->d_deep_suf_rep, ix.suf_rep.data(), b_sr, cudaMemcpyHostToDevice);
+        cudaMemcpy(w->d_deep_ent_suf, ix.ent_suf.data(), nb, cudaMemcpyHostToDevice);
+        cudaMemcpy(w->d_deep_ent_idx, ix.ent_idx.data(), nb, cudaMemcpyHostToDevice);
+        w->has_deep = 1;
+    }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         nr_set_error("whitelist upload failed: %s", cudaGetErrorString(e));
@@ -220,6 +245,8 @@ extern "C" void nr_whitelist_destroy(nr_whitelist_t *w)
     nr_host_ctx_destroy(w->host_ctx);
     cudaFree(w->d_lo); cudaFree(w->d_hi); cudaFree(w->d_nm);
     cudaFree(w->d_bits[0]);
+    cudaFree(w->d_deep_pre_start); cudaFree(w->d_deep_pre_rep); cudaFree(w->d_deep_suf_rep);
+    cudaFree(w->d_deep_ent_suf); cudaFree(w->d_deep_ent_idx);
     for (int j = 0; j < 4; j++) { cudaFree(w->d_rank[j]); cudaFree(w->d_ents[j]); cudaFree(w->d_kstart[j]); }
     delete w;
     if (prev >= 0) cudaSetDevice(prev);

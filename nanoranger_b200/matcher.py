@@ -172,6 +172,14 @@ class Whitelist:
         _lib.check(_lib.lib().nr_match_counters(workspace.data_ptr(), c, st), "nr_match_counters")
         return dict(zip(("probes", "hits", "verifications", "passes", "listed"), map(int, c)))
 
+    def tier_counts(self, workspace) -> dict:
+        """Where the last match_device call on `workspace` resolved its candidates."""
+        import torch
+        c = (C.c_uint64 * 4)()
+        st = torch.cuda.current_stream(workspace.device).cuda_stream
+        _lib.check(_lib.lib().nr_match_tier_counts(workspace.data_ptr(), c, st), "nr_match_tier_counts")
+        return dict(zip(("left_by_filter", "deep_k3", "deep_k5", "brute_force"), map(int, c)))
+
 
 def int_peak(device: int = 0, iters: int = 2000) -> dict:
     """ALU-pipe roofline denominator measured on this GPU (thread-ops/s)."""

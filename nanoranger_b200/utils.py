@@ -179,21 +179,18 @@ def match_records(wl: Whitelist, names, seqs, offsets, ref_names, mode=NR_MODE_A
                int(res.score[i]))
 
 
-AUTO_MODE_MAX = 200_000     # candidates up to which low-scoring reads are resolved exactly as well
-
-
 def barcode_align(input_fastq, genome_dir, out_name, threads=1, *ignored, device: int = 0,
-                  header: str = "used", mode=None):
+                  header: str = "used", mode=NR_MODE_AUTO):
     """scripts/barcode_align.sh <input.fa.gz> <genome_dir> <out_prefix> <threads> [ignored]:
     writes `<out_prefix>.sam`.  `threads` is accepted for call compatibility (the work runs on
     the GPU).
 
-    mode: NR_MODE_AUTO resolves EVERY candidate exactly (reads below the reference's threshold go
-    through the exhaustive DP kernel, ~8e3 candidates/s against 737K barcodes), NR_MODE_FILTERED
-    resolves exactly everything the reference keeps (AS >= core length - 2) at ~2e8 candidates/s
-    and leaves the rest out of the SAM -- the only file that can tell is the low-score tail of
-    `_barcode_scores.csv`, which the reference merely plots.  Default: AUTO up to AUTO_MODE_MAX
-    candidates, FILTERED above (announced on stdout)."""
+    mode: NR_MODE_AUTO (default, at any input size) resolves EVERY candidate exactly, as the
+    reference's STAR call does (--outFilterScoreMinOverLread 0): reads the seed filter cannot
+    decide go through the deep tier (exact optimum over the whole whitelist), so the low-score
+    tail of `_barcode_scores.csv` (utils.py:698, 728-730) is the oracle's.  NR_MODE_FILTERED is
+    opt-in: it resolves exactly everything the reference keeps (AS >= core length - 2) and leaves
+    the rest out of the SAM."""
     import ctypes as C
     from . import _lib
     from ._lib import NR_MODE_FILTERED
@@ -203,12 +200,6 @@ def barcode_align(input_fastq, genome_dir, out_name, threads=1, *ignored, device
         # nr_sam_write (same bytes as samio.write_sam(match_records(...)), ~50x faster)
         nbuf, noff, seqs, offsets = fastx.read_fasta_raw(input_fastq)
         n = len(offsets) - 1
-        if mode is None:
-            mode = NR_MODE_AUTO
-            if n > AUTO_MODE_MAX and wl.has_index:
-                mode = NR_MODE_FILTERED
-                print(f"nanoranger_b200: {n} candidates > {AUTO_MODE_MAX}: reads scoring below "
-                      f"{wl.core_len - 2} are not resolved (pass mode=NR_MODE_AUTO to resolve them)")
         res = wl.match_host(seqs, offsets, min_score=wl.core_len - 2, mode=mode)
         rbuf, roff = fastx._pack_names(ref_names)
         if n == 0:

@@ -59,8 +59,8 @@ void run(const nr_deep_index_host &ix, int padL, int padR, const uint8_t *cand,
                     const int bnd = best > K ? K : best;
                     const int lb = fmin[g] + bmin[h];
                     if (lb > bnd) continue;
-                    const int t = nr_deep_join<K>(F[g].v, B[h].v, lb, bnd);
-                    if (t > K) continue;
+                    const int t = nr_deep_join<K>(F[g].v, B[h].v);
+                    if (t > bnd) continue;
                     const uint32_t k = (ix.ent_idx[p] << 1) | (uint32_t)st;
                     if (t < best) { best = t; cnt = 1; key = k; }
                     else if (t == best) { cnt++; if (k < key) key = k; }

@@ -1,0 +1,82 @@
+"""Parity of the deep matcher tier (nr_match_deep.cu) through the C ABI: NR_MODE_AUTO must be
+bit-exact to the oracle at EVERY score (the reference histograms all uniquely mapped forward
+reads, utils.py:698, 728-730), and the tier -- not the brute-force kernel -- must be what
+resolved the low-scoring reads."""
+import numpy as np
+import pytest
+
+from helpers import compare, mixed_candidates, mutate, rs, tie_rich_whitelist
+from test_gpu_match import _oracle, _run_device
+
+pytestmark = pytest.mark.gpu
+
+
+def test_auto_737k_every_score_exact(cuda_device, oracle):
+    from nanoranger_b200 import NR_MODE_AUTO, Whitelist, synth, whitelists
+    wl_a = whitelists.load_737k()
+    d = synth.make_candidates(wl_a, 2500, seed=21, frac_negative=0.5, p_sub=0.04, p_ins=0.04, p_del=0.04)
+    seqs = synth.to_strings(d["seqs"], d["offsets"])
+    rng = np.random.default_rng(3)
+    seqs += [rs(rng, int(rng.integers(1, 24))) for _ in range(60)]            # shorter than the filter takes
+    seqs += [s[:k] + "N" + s[k + 1:] for s, k in zip(seqs[:80], rng.integers(0, 30, 80))]
+    seqs += ["N" * 30, "ACGT" * 16, "A" * 63, rs(rng, 64), rs(rng, 63)]
+    wl = Whitelist(wl_a, 30, 40)
+    cc, cl = oracle.encode_many(seqs, 64)
+    ref = oracle.match(oracle._CODE[wl_a], 30, 40, cc, cl)
+    res, ws = _run_device(wl, seqs, 14, NR_MODE_AUTO)
+    compare(ref, res, 14, exact_below=True, label="auto 737K")
+    t = wl.tier_counts(ws)
+    below = int((ref["best_score"] < 14).sum())
+    assert t["left_by_filter"] >= below
+    assert t["deep_k3"] + t["deep_k5"] + t["brute_force"] == t["left_by_filter"]
+    # nearly everything the filter leaves has a pair at cost <= 3 somewhere in 737K barcodes
+    assert t["deep_k3"] > 0.9 * t["left_by_filter"], t
+    assert t["brute_force"] <= 10, t
+
+
+@pytest.mark.parametrize("pad_l,pad_r,qlen", [(30, 40, 50), (4, 17, 35), (2, 3, 30), (30, 40, 63)])
+def test_auto_small_whitelists_all_tiers(cuda_device, oracle, pad_l, pad_r, qlen):
+    """small whitelists: most random reads have no pair at cost <= 3, so K = 5 and the brute-force
+    kernel get work too."""
+    from nanoranger_b200 import NR_MODE_AUTO, Whitelist
+    rng = np.random.default_rng(300 + qlen)
+    wl_strs = tie_rich_whitelist(rng, 3000)
+    seqs = mixed_candidates(rng, wl_strs, 2500, pad_l, qlen, with_n=0.1)
+    seqs += [mutate(rng, wl_strs[int(rng.integers(0, len(wl_strs)))], int(rng.integers(2, 7))) for _ in range(300)]
+    wl = Whitelist(wl_strs, pad_l, pad_r)
+    ref = _oracle(oracle, wl_strs, pad_l, pad_r, seqs)
+    res, ws = _run_device(wl, seqs, 14, NR_MODE_AUTO)
+    compare(ref, res, 14, exact_below=True, label="auto small")
+    t = wl.tier_counts(ws)
+    assert t["deep_k3"] > 0 and t["deep_k5"] > 0
+    assert t["deep_k3"] + t["deep_k5"] + t["brute_force"] == t["left_by_filter"]
+
+
+def test_auto_without_seed_index_goes_through_deep_tier(cuda_device, oracle):
+    """32-column slide-seq cores with N columns (utils.py:584-601): no seed index, AUTO = deep
+    tier over every candidate."""
+    from nanoranger_b200 import NR_MODE_AUTO, Whitelist
+    rng = np.random.default_rng(9)
+    linker = "TCTTCAGCGTTCCCGAGA"
+    bcs = set()
+    while len(bcs) < 4000:
+        b = list(rs(rng, 14))
+        if rng.random() < 0.15:
+            b[int(rng.integers(0, 14))] = "N"
+        bcs.add("".join(b))
+    wl_strs = [b[:8] + linker + b[8:] for b in sorted(bcs)]
+    seqs = []
+    for _ in range(2000):
+        core = wl_strs[int(rng.integers(0, len(wl_strs)))].replace("N", "ACGT"[int(rng.integers(0, 4))])
+        mid = mutate(rng, core, int(rng.choice([0, 0, 1, 2, 3, 5])))
+        q = (rs(rng, int(rng.integers(0, 18))) + mid + rs(rng, int(rng.integers(0, 14))))[:64]
+        if rng.random() < 0.1:
+            q = oracle.revcomp(q)
+        seqs.append(q)
+    wl = Whitelist(wl_strs, 15, 24)
+    assert not wl.has_index
+    ref = _oracle(oracle, wl_strs, 15, 24, seqs)
+    res, ws = _run_device(wl, seqs, 30, NR_MODE_AUTO)
+    compare(ref, res, 30, exact_below=True, label="auto slide-seq")
+    t = wl.tier_counts(ws)
+    assert t["deep_k3"] > 1000, t
