@@ -221,8 +221,9 @@ NR_HD int nr_rows_last(int p, int m) { return p + 24 < m ? p + 24 : m; }
 // the best placement inside those rows, 3 if none; *umi = smallest row at which a best
 // placement leaves the core (the query index aligned to reference column padL+16,
 // utils.py:705-708), -1 if the best placement ends inside the core.
-// NR_NFA16_BODY(BASE_AT) is the body; BASE_AT(i) yields base i of Q.
-#define NR_NFA16_BODY(BASE_AT)                                                                \
+// NR_NFA16_BODY(BASE_AT, ISN_AT) is the body; BASE_AT(i) yields base i of Q, ISN_AT(i) whether it
+// is N: an N row scores 0 against every column (cost 1 on the diagonal instead of 0 / 2).
+#define NR_NFA16_BODY(BASE_AT, ISN_AT)                                                        \
     const uint32_t KEEP = 0x15555555u; /* states 1..15 */                                     \
     const uint32_t FIN = 0x40000000u;  /* state 16 */                                         \
     uint32_t R0 = 0, R1, R2;                                                                  \
@@ -232,14 +233,15 @@ NR_HD int nr_rows_last(int p, int m) { return p + 24 < m ? p + 24 : m; }
     for (int i = r0; i < r1; i++) {                                                           \
         uint32_t c = (uint32_t)(BASE_AT(i));                                                  \
         uint32_t x = core ^ (c * 0x55555555u);                                                \
-        uint32_t M = ~(x | (x >> 1)) & 0x55555555u;                                           \
+        const uint32_t nrow = (ISN_AT(i)) ? 0xFFFFFFFFu : 0u;                                 \
+        uint32_t M = ~(x | (x >> 1)) & 0x55555555u & ~nrow;                                   \
         int z = i - padL; /* cost of state 0 at row i when positive */                        \
         uint32_t S0 = (R0 << 2) | (z <= 0 ? 1u : 0u);                                         \
         uint32_t S1 = (R1 << 2) | (z <= 1 ? 1u : 0u);                                         \
         uint32_t S2 = (R2 << 2) | (z <= 2 ? 1u : 0u);                                         \
         uint32_t A0 = S0 & M;                                                                 \
-        uint32_t A1 = (S1 & M) | (R0 & KEEP) | A0;                                            \
-        uint32_t A2 = (S2 & M) | (R1 & KEEP) | S0 | A1;                                       \
+        uint32_t A1 = (S1 & M) | (R0 & KEEP) | A0 | (S0 & nrow);                              \
+        uint32_t A2 = (S2 & M) | (R1 & KEEP) | S0 | A1 | (S1 & nrow);                         \
         A2 |= (A0 << 2) | (z + 1 <= 0 ? 1u : 0u); /* one deleted column, cost 2 */            \
         R0 = A0; R1 = A1; R2 = A2;                                                            \
         if (R2 & FIN) {                                                                       \
@@ -263,8 +265,10 @@ NR_HD int nr_nfa16(const uint32_t *rdp, int m, uint32_t core, int padL, int padR
                    int *umi)
 {
 #define NR_BASE_AT(i) nr_read_base(rdp, (i))
-    NR_NFA16_BODY(NR_BASE_AT)
+#define NR_ISN_AT(i) 0
+    NR_NFA16_BODY(NR_BASE_AT, NR_ISN_AT)
 #undef NR_BASE_AT
+#undef NR_ISN_AT
 }
 
 // at most 32 rows, bases r0.. held in Wn = nr_window64(rdp, r0)
@@ -272,8 +276,75 @@ NR_HD int nr_nfa16_w(uint64_t Wn, int m, uint32_t core, int padL, int padR, int 
                      int *umi)
 {
 #define NR_BASE_AT(i) ((uint32_t)(Wn >> (2 * ((i) - r0))) & 3u)
-    NR_NFA16_BODY(NR_BASE_AT)
+#define NR_ISN_AT(i) 0
+    NR_NFA16_BODY(NR_BASE_AT, NR_ISN_AT)
 #undef NR_BASE_AT
+#undef NR_ISN_AT
+}
+
+// reads with N: nm has bit i set where base i of Q is N (its 2-bit code is then ignored)
+NR_HD int nr_nfa16n(const uint32_t *rdp, uint64_t nm, int m, uint32_t core, int padL, int padR,
+                    int r0, int r1, int *umi)
+{
+#define NR_BASE_AT(i) nr_read_base(rdp, (i))
+#define NR_ISN_AT(i) ((nm >> (i)) & 1ull)
+    NR_NFA16_BODY(NR_BASE_AT, NR_ISN_AT)
+#undef NR_BASE_AT
+#undef NR_ISN_AT
+}
+
+// at most 32 rows; nmw = nm >> r0
+NR_HD int nr_nfa16n_w(uint64_t Wn, uint32_t nmw, int m, uint32_t core, int padL, int padR, int r0,
+                      int r1, int *umi)
+{
+#define NR_BASE_AT(i) ((uint32_t)(Wn >> (2 * ((i) - r0))) & 3u)
+#define NR_ISN_AT(i) ((nmw >> ((i) - r0)) & 1u)
+    NR_NFA16_BODY(NR_BASE_AT, NR_ISN_AT)
+#undef NR_BASE_AT
+#undef NR_ISN_AT
+}
+
+// ---- reads with one or two N ----------------------------------------------------------------
+// A read N scores 0 against any core column: cost 1, no shift -- an event the probe table does
+// not enumerate (two damaged quarters are only covered for insertions / overhangs).  Instead the
+// N is SUBSTITUTED: variant v of the read carries base (v & 3) at the first N and ((v >> 2) & 3)
+// at the second.  A placement of true cost c that aligns a set A of the N's to core columns has
+// cost c - |A| in the variant that carries those columns' bases (and base 0 at the other N's),
+// and the key of the probe that finds a placement only depends on read bases that match the
+// core, so:
+//   - a variant with z non-zero substitutions is only needed for placements with |A| >= z, and
+//     there only the probe stages complete for cost <= 2 - z;
+//   - in round r (after which every placement of true cost <= r must be known) variant v runs
+//     stage r - z(v);
+//   - slots whose probes cannot reach a substituted N read the same keys as the variant with
+//     that substitution zeroed, which runs the same or a later stage: they are skipped.
+// Nominated (entry, strand) pairs are scored against the ORIGINAL read by nr_nfa16n_w.
+NR_HD int nr_nvar_count(int n_n) { return n_n == 1 ? 4 : 16; }
+NR_HD int nr_nvar_nonzero(int v) { return ((v & 3) != 0) + ((v >> 2) != 0); }
+// read positions a probe at slot p may use: p .. p + 18; one base of margin on both sides
+NR_HD bool nr_slot_reaches(int p, int pos) { return pos >= p - 1 && pos <= p + 20; }
+NR_HD bool nr_nvar_slot_needed(int v, int p, int n0s, int n1s)   // N positions on the slot's strand
+{
+    if ((v & 3) != 0 && !nr_slot_reaches(p, n0s)) return false;
+    if ((v >> 2) != 0 && !nr_slot_reaches(p, n1s)) return false;
+    return true;
+}
+// the four packed words of variant v (n1 < 0: one N)
+NR_HD void nr_nvar_apply(const uint32_t in[4], int n0, int n1, int v, uint32_t out[4])
+{
+    for (int k = 0; k < 4; k++) out[k] = in[k];
+    out[n0 >> 4] = (out[n0 >> 4] & ~(3u << ((n0 & 15) * 2))) | ((uint32_t)(v & 3) << ((n0 & 15) * 2));
+    if (n1 >= 0)
+        out[n1 >> 4] = (out[n1 >> 4] & ~(3u << ((n1 & 15) * 2))) |
+                       ((uint32_t)((v >> 2) & 3) << ((n1 & 15) * 2));
+}
+// N mask of the reverse-complement strand
+NR_HD uint64_t nr_rev_mask(uint64_t nm, int m)
+{
+    uint64_t r = 0;
+    for (int k = 0; k < m; k++)
+        if ((nm >> k) & 1ull) r |= 1ull << (m - 1 - k);
+    return r;
 }
 
 // ---- interior scorer: furthest-reaching diagonals ------------------------------------------------

@@ -16,10 +16,12 @@ int nr_launch_exhaustive(const nr_whitelist *wl, const void *d_bases, const uint
                          int32_t *d_idx, int8_t *d_score, uint8_t *d_nbest, uint8_t *d_flags,
                          uint8_t *d_umi, int grid_cap, void *d_scratch, cudaStream_t stream);
 int nr_launch_filtered(const nr_whitelist *wl, const void *d_bases, const uint8_t *d_meta,
-                       uint64_t n_cand, int min_score, int resolve_below, int32_t *d_idx,
-                       int8_t *d_score, uint8_t *d_nbest, uint8_t *d_flags, uint8_t *d_umi,
-                       uint32_t *d_list, uint32_t *d_list_count, unsigned long long *d_counters,
-                       int *grid_out, cudaStream_t stream);
+                       const uint64_t *d_nmask, uint64_t n_cand, int min_score, int resolve_below,
+                       int32_t *d_idx, int8_t *d_score, uint8_t *d_nbest, uint8_t *d_flags,
+                       uint8_t *d_umi, uint32_t *d_list, uint32_t *d_list_count,
+                       uint32_t *d_list_n, uint32_t *d_list_n_count,
+                       unsigned long long *d_tile_next, unsigned long long *d_tile_next_n,
+                       unsigned long long *d_counters, int *grid_out, cudaStream_t stream);
 
 int nr_launch_deep(const nr_whitelist *wl, int K, const void *d_bases, const uint8_t *d_meta,
                    const uint64_t *d_nmask, const uint32_t *d_list, const uint32_t *d_list_count,
@@ -38,9 +40,11 @@ int nr_deep_usable(const nr_whitelist *wl);
 //   [68,72)   count of list B: left by the deep tier at K = 3 (-> K = 5)
 //   [72,80)   next tile of the filtered kernel
 //   [80,84)   count of list C: left by the deep tier at K = 5 (-> exhaustive DP kernel)
+//   [84,88)   count of list N: reads with N the filter's main pass hands to its N pass
 //   [88,96)   next work item of the deep tier at K = 3, [96,104) at K = 5
+//   [104,112) next tile of the filtered kernel's N pass
 //   [128, 128 + 8 KB)  the exhaustive kernel's arrival counters, then its partials
-//   [NR_WS_HEADER, +4n) list A, then list B, list C (4n each), then the deep tier's scratch
+//   [NR_WS_HEADER, +4n) list A, then list B, list C, list N (4n each), then the deep tier's scratch
 #define NR_WS_ZERO (128 + NR_EX_MAXGRID * 4)
 #define NR_WS_HEADER 65536
 static_assert(128 + NR_EX_SCRATCH_BYTES <= NR_WS_HEADER, "workspace header too small");
@@ -59,7 +63,7 @@ struct DeviceGuard {
     ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
 };
 
-size_t lists_bytes(uint64_t n) { return (((size_t)n * sizeof(uint32_t) * 3) + 255) & ~(size_t)255; }
+size_t lists_bytes(uint64_t n) { return (((size_t)n * sizeof(uint32_t) * 4) + 255) & ~(size_t)255; }
 
 size_t deep_scratch(const nr_whitelist *wl)
 {
@@ -166,8 +170,10 @@ extern "C" int nr_match_device(const nr_whitelist_t *wl, const void *d_bases,
     uint32_t *d_count = (uint32_t *)(ws + 64);
     uint32_t *d_list = (uint32_t *)(ws + NR_WS_HEADER);
     int grid = 0;
-    int rc = nr_launch_filtered(wl, d_bases, d_meta, n, min_score, eff == NR_MODE_AUTO ? 1 : 0,
-                                d_idx, d_score, d_nbest, d_flags, d_umi_q, d_list, d_count,
+    int rc = nr_launch_filtered(wl, d_bases, d_meta, d_nmask, n, min_score,
+                                eff == NR_MODE_AUTO ? 1 : 0, d_idx, d_score, d_nbest, d_flags,
+                                d_umi_q, d_list, d_count, d_list + 3 * n, (uint32_t *)(ws + 84),
+                                (unsigned long long *)(ws + 72), (unsigned long long *)(ws + 104),
                                 nullptr, &grid, st);
     if (rc != NR_OK) return rc;
     // candidates the filter left (N, short, > 32 co-optimal pairs; in AUTO also everything below
@@ -193,9 +199,12 @@ extern "C" int nr_match_device_counted(const nr_whitelist_t *wl, const void *d_b
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t *ws = (uint8_t *)d_workspace;
     NR_CHECK_CUDA(cudaMemsetAsync(ws, 0, NR_WS_ZERO, st));
-    int rc = nr_launch_filtered(wl, d_bases, d_meta, n, min_score, 0, d_idx, d_score, d_nbest,
-                                d_flags, d_umi_q, (uint32_t *)(ws + NR_WS_HEADER),
-                                (uint32_t *)(ws + 64), (unsigned long long *)ws, nullptr, st);
+    uint32_t *listA = (uint32_t *)(ws + NR_WS_HEADER);
+    int rc = nr_launch_filtered(wl, d_bases, d_meta, d_nmask, n, min_score, 0, d_idx, d_score,
+                                d_nbest, d_flags, d_umi_q, listA, (uint32_t *)(ws + 64),
+                                listA + 3 * n, (uint32_t *)(ws + 84),
+                                (unsigned long long *)(ws + 72), (unsigned long long *)(ws + 104),
+                                (unsigned long long *)ws, nullptr, st);
     if (rc != NR_OK) return rc;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);

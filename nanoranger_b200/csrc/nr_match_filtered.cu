@@ -59,8 +59,11 @@ struct nr_filter_params {
     uint8_t *o_nbest;
     uint8_t *o_flags;
     uint8_t *o_umi;
-    uint32_t *list;         // candidates left to the exhaustive kernel
+    uint32_t *list;         // candidates left to the next tier (deep / exhaustive)
     uint32_t *list_count;
+    uint32_t *list_n;       // main pass: candidates with N, handed to the N pass (nullable)
+    uint32_t *list_n_count;
+    const uint64_t *nmask;  // N pass: per-candidate N masks
     unsigned long long *tile_next;  // next tile to hand out (zeroed with the workspace header)
     unsigned long long *counters;   // nullable: probes, hits, verifications, passes, listed
 };
@@ -97,6 +100,7 @@ struct WarpSmem {
     uint4 tile[32];                  // packed records of the warp's 32 candidates
     uint32_t rdp[2][NR_RDP_WORDS];   // candidate in flight: forward / reverse complement, padded
     uint32_t queue[NR_QCAP];         // bitmap hits waiting for verification: probe | strand | slot
+    uint64_t nm[2];                  // N pass: N mask of the candidate in flight, per strand
 };
 
 struct Acc {                 // running answer of the candidate in flight (warp-uniform unless noted)
@@ -116,7 +120,7 @@ __device__ __forceinline__ int merge_umi(int a, int b) { return a < 0 ? b : (b <
 
 // Take up to 32 queued bitmap hits, expand each into the index rows that share its key
 // (kstart gives first row and count), and verify the rows 32 at a time, one row per lane.
-template <bool COUNT>
+template <bool COUNT, bool NMODE>
 __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, Acc &acc, int m,
                                       const uint32_t *s_probes, const Tables &T4)
 {
@@ -177,7 +181,15 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, A
             const int strand = (int)((o_item >> 24) & 1u);
             const int p = (int)(o_item >> 25) - 16;
             const uint2 e = __ldcg(T4.ents[od] + o_start + (g - o_excl));
-            cost = nr_verify16(sm.rdp[strand], m, e.y, P.padL, P.padR, p, ot, &u);
+            if (NMODE) {
+                // reads with N: the automaton over the rows around the slot, N rows at cost 1
+                // (sm.rdp holds a substituted variant; the N rows ignore their base)
+                const int r0 = nr_rows_first(p);
+                cost = nr_nfa16n_w(nr_window64(sm.rdp[strand], r0), (uint32_t)(sm.nm[strand] >> r0),
+                                   m, e.y, P.padL, P.padR, r0, nr_rows_last(p, m), &u);
+            } else {
+                cost = nr_verify16(sm.rdp[strand], m, e.y, P.padL, P.padR, p, ot, &u);
+            }
             k = (e.x << 1) | (uint32_t)strand;
             if (COUNT) { acc.c_ver++; acc.c_pass += cost < 3; }
         }
@@ -280,7 +292,7 @@ __device__ __forceinline__ uint64_t probe_range(const uint32_t *__restrict__ bit
 
 // Place the hits of one work item (per-lane probe mask at (strand, p)) in the warp's queue,
 // draining it as often as needed.
-template <bool COUNT>
+template <bool COUNT, bool NMODE>
 __device__ __forceinline__ void enqueue(const nr_filter_params &P, WarpSmem &sm, Acc &acc, int m,
                                         const uint32_t *s_probes, const Tables &T4, uint64_t mask,
                                         int strand, int p)
@@ -295,7 +307,7 @@ __device__ __forceinline__ void enqueue(const nr_filter_params &P, WarpSmem &sm,
         const uint32_t b = __ballot_sync(0xffffffffu, mine_all != 0);
         if (b == 0u) return;
         const int total = __popc(b);
-        while (acc.qn + total > NR_QCAP) drain<COUNT>(P, sm, acc, m, s_probes, T4);
+        while (acc.qn + total > NR_QCAP) drain<COUNT, NMODE>(P, sm, acc, m, s_probes, T4);
         if (mine_all)
             sm.queue[acc.qn + __popc(b & ((1u << lane) - 1u))] =
                 where | ((uint32_t)(__ffsll((long long)mask) - 1) << 16);
@@ -317,7 +329,7 @@ __device__ __forceinline__ void enqueue(const nr_filter_params &P, WarpSmem &sm,
             if ((int)lane >= o) incl += v;
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
-        while (acc.qn + total > NR_QCAP) drain<COUNT>(P, sm, acc, m, s_probes, T4);
+        while (acc.qn + total > NR_QCAP) drain<COUNT, NMODE>(P, sm, acc, m, s_probes, T4);
         int pos = acc.qn + incl - mine;
         // queue item = (probe, strand, slot position); the key, its rank and its rows are worked
         // out in drain(), one hit per lane
@@ -331,7 +343,82 @@ __device__ __forceinline__ void enqueue(const nr_filter_params &P, WarpSmem &sm,
     }
 }
 
-template <bool COUNT>
+// One probe stage (0: probe 0; 1: probes 1..15; 2: the two-event probes + the edge probes at slot
+// -1) over all slots of both strands of the read staged in sm.rdp, drained at the end.
+// NMODE: the staged read is substituted variant `v`; slots that cannot reach a substituted N
+// position are skipped (nr_filter_core.h).
+template <bool COUNT, bool NMODE>
+__device__ __forceinline__ void run_stage(const nr_filter_params &P, WarpSmem &sm, Acc &acc, int m,
+                                          const uint32_t *s_probes, const Tables &s_tab,
+                                          const uint32_t *__restrict__ bits_all, int stage, int p0,
+                                          int nP, bool edge, int v, int n0, int n1,
+                                          unsigned long long &c_probes_n)
+{
+    const uint32_t lane = nr_lane();
+    const int nslots = nP > 0 ? 2 * nP : 0;
+    const int nchunks = (nslots + 31) >> 5;
+#pragma unroll 1
+    for (int item = 0; item < nchunks; item++) {
+        const int slot = item * 32 + (int)lane;
+        bool slot_ok = slot < nslots;
+        const int strand = slot >= nP ? 1 : 0;
+        const int p = p0 + slot - strand * nP;
+        if (NMODE && v != 0)
+            slot_ok = slot_ok && nr_nvar_slot_needed(v, p, strand ? m - 1 - n0 : n0,
+                                                     n1 < 0 ? -100 : (strand ? m - 1 - n1 : n1));
+        if (NMODE && !__any_sync(0xffffffffu, slot_ok)) continue;
+        const uint64_t W = slot_ok ? nr_window64(sm.rdp[strand], p) : 0ull;
+        uint64_t mask;
+        if (stage == 0) {
+            mask = probe_range<0>(bits_all, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_COST0>{});
+            if (COUNT) c_probes_n += slot_ok ? NR_PROBES_COST0 : 0;
+        } else if (stage == 1) {
+            mask = probe_range<NR_PROBES_COST0>(bits_all, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_COST1 - NR_PROBES_COST0>{});
+            if (COUNT) c_probes_n += slot_ok ? NR_PROBES_COST1 - NR_PROBES_COST0 : 0;
+        } else {
+            mask = probe_range<NR_PROBES_COST1>(bits_all, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_MAIN - NR_PROBES_COST1>{});
+            if (COUNT) c_probes_n += slot_ok ? NR_PROBES_MAIN - NR_PROBES_COST1 : 0;
+        }
+        enqueue<COUNT, NMODE>(P, sm, acc, m, s_probes, s_tab, mask, strand, p);
+    }
+    if (stage == 2 && edge) {
+        // one-column start overhang + interior insertion (slot -1 only)
+        uint64_t mask = 0;
+        const int strand = lane >= NR_PROBES_EDGE ? 1 : 0;
+        if (lane < 2 * NR_PROBES_EDGE) {
+            const int ti = NR_PROBES_MAIN + (int)lane - strand * NR_PROBES_EDGE;
+            const uint64_t W = nr_window64(sm.rdp[strand], -1);
+            const nr_probe_t t = probe_unpack(s_probes[ti]);
+            const uint32_t key = nr_probe_key(W, t);
+            const uint32_t w = __ldg(P.bits[0] + (key >> 5));
+            mask = (uint64_t)((w >> (key & 31u)) & 1u) << ti;
+            if (COUNT) c_probes_n++;
+        }
+        enqueue<COUNT, NMODE>(P, sm, acc, m, s_probes, s_tab, mask, strand, -1);
+    }
+    while (acc.qn > 0) drain<COUNT, NMODE>(P, sm, acc, m, s_probes, s_tab);
+}
+
+// stage both strands of the packed read w4, padded, in shared memory
+__device__ __forceinline__ void stage_read(WarpSmem &sm, const uint32_t w4[4], int m)
+{
+    const uint32_t lane = nr_lane();
+    uint32_t rc[4];
+    nr_revcomp4(w4, m, rc);
+    uint32_t vf = 0, vr = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if ((int)lane == k + 1) { vf = w4[k]; vr = rc[k]; }
+    __syncwarp();
+    if (lane < NR_RDP_WORDS) { sm.rdp[0][lane] = vf; sm.rdp[1][lane] = vr; }
+    __syncwarp();
+}
+
+// NMODE = false: the main pass over all n_cand candidates; reads with N (and at least
+// NR_FILTER_MIN_LEN bases) are handed to the N pass through list_n when there is one.
+// NMODE = true: the N pass over list_n -- reads with one or two N as substituted variants
+// (nr_filter_core.h), reads with more N on to the next tier.
+template <bool COUNT, bool NMODE>
 __global__ void __launch_bounds__(NR_FWARPS * 32, NR_FBLOCKS)
 nr_match_filtered_kernel(const nr_filter_params P)
 {
@@ -349,7 +436,8 @@ nr_match_filtered_kernel(const nr_filter_params P)
     const int warp = threadIdx.x >> 5;
     WarpSmem &sm = smem[warp];
     const uint32_t *__restrict__ bits_all = P.bits[0];
-    const uint64_t n_tiles = (P.n_cand + 31) >> 5;
+    const uint64_t n_items = NMODE ? (uint64_t)*P.list_n_count : P.n_cand;
+    const uint64_t n_tiles = (n_items + 31) >> 5;
     unsigned long long c_probes_n = 0, c_listed = 0;
     Acc acc;
     acc.c_hits = acc.c_ver = acc.c_pass = 0;
@@ -364,20 +452,31 @@ nr_match_filtered_kernel(const nr_filter_params P)
         if (tile >= n_tiles) break;
         // one coalesced 512 B request brings the tile's records; meta bytes stay in registers
         uint32_t mt = 0x100u;   // no candidate
+        uint32_t cidx = 0;      // N pass: the candidate this lane loaded
+        uint32_t nm_lo = 0, nm_hi = 0;
         {
             const uint64_t mine = tile * 32 + lane;
             uint4 b = make_uint4(0u, 0u, 0u, 0u);
-            if (mine < P.n_cand) { b = __ldcs(P.bases + mine); mt = P.meta[mine]; }
+            if (mine < n_items) {
+                if (NMODE) {
+                    cidx = P.list_n[mine];
+                    b = __ldg(P.bases + cidx); mt = P.meta[cidx];
+                    const uint64_t nm = P.nmask[cidx];
+                    nm_lo = (uint32_t)nm; nm_hi = (uint32_t)(nm >> 32);
+                } else {
+                    b = __ldcs(P.bases + mine); mt = P.meta[mine];
+                }
+            }
             __syncwarp();
             sm.tile[lane] = b;
             __syncwarp();
         }
-        const int in_tile = (int)min((uint64_t)32, P.n_cand - tile * 32);
+        const int in_tile = (int)min((uint64_t)32, n_items - tile * 32);
 
 #pragma unroll 1
         for (int c = 0; c < in_tile; c++) {
             const uint32_t cmt = __shfl_sync(0xffffffffu, mt, c);
-            const uint64_t cand = tile * 32 + c;
+            const uint64_t cand = NMODE ? (uint64_t)__shfl_sync(0xffffffffu, cidx, c) : tile * 32 + c;
             if (cmt == 0xFFu) {          // longer than NR_MAX_QUERY: not scored
                 if (lane == 0) {
                     P.o_idx[cand] = -1; P.o_score[cand] = NR_SCORE_BELOW; P.o_nbest[cand] = 0;
@@ -387,72 +486,60 @@ nr_match_filtered_kernel(const nr_filter_params P)
                 continue;
             }
             const int m = (int)(cmt & 0x7Fu);
-            bool to_list = (cmt & 0x80u) || m < NR_FILTER_MIN_LEN;
-            if (!to_list) {
-                // stage both strands, padded, in shared memory
-                {
-                    uint4 t4 = sm.tile[c];
-                    uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w}, rc[4];
-                    nr_revcomp4(w4, m, rc);
-                    uint32_t vf = 0, vr = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if ((int)lane == k + 1) { vf = w4[k]; vr = rc[k]; }
-                    __syncwarp();
-                    if (lane < NR_RDP_WORDS) { sm.rdp[0][lane] = vf; sm.rdp[1][lane] = vr; }
-                    __syncwarp();
-                }
+            bool to_list = m < NR_FILTER_MIN_LEN;
+            bool to_nlist = false;
+            uint64_t nm = 0;
+            int n_n = 0;
+            if (NMODE) {
+                nm = ((uint64_t)__shfl_sync(0xffffffffu, nm_hi, c) << 32) |
+                     (uint64_t)__shfl_sync(0xffffffffu, nm_lo, c);
+                n_n = __popcll(nm);
+                if (n_n < 1 || n_n > 2) to_list = true;
+            } else if (cmt & 0x80u) {
+                if (P.list_n && !to_list) to_nlist = true; else to_list = true;
+            }
+            if (!to_list && !to_nlist) {
                 acc.best = 3; acc.nb = 0; acc.key = 0; acc.umi = -1; acc.overflow = 0; acc.qn = 0;
                 const int p0 = nr_slot_first(m, P.padR), p1 = nr_slot_last(m, P.padL);
                 const int nP = p1 - p0 + 1;
-                const int nslots = nP > 0 ? 2 * nP : 0;
-                const int nchunks = (nslots + 31) >> 5;
                 const bool edge = p0 <= -1 && p1 >= -1;
-                // Three stages over all slots, each drained before the next starts.  Prefixes of
-                // the probe table are complete for small costs (nr_filter_core.h): after stage 0
-                // (probe 0) every placement of cost 0 is known, after stage 1 (probes 1..15)
-                // every placement of cost <= 1; a candidate whose best pair is already that good
-                // needs nothing more -- only placements at the best cost count.  Stage 2 runs
-                // the variant probes and the edge probes (two cost-1 events).
+                const uint4 t4 = sm.tile[c];
+                const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
+                if (!NMODE) {
+                    stage_read(sm, w4, m);
+                    // Three stages over all slots, each drained before the next starts.  Prefixes of
+                    // the probe table are complete for small costs (nr_filter_core.h): after stage 0
+                    // (probe 0) every placement of cost 0 is known, after stage 1 (probes 1..15)
+                    // every placement of cost <= 1; a candidate whose best pair is already that good
+                    // needs nothing more -- only placements at the best cost count.  Stage 2 runs
+                    // the variant probes and the edge probes (two cost-1 events).
 #pragma unroll 1
-                for (int stage = 0; stage < 3; stage++) {
-                    if (acc.best < stage) break;
+                    for (int stage = 0; stage < 3; stage++) {
+                        if (acc.best < stage) break;
+                        run_stage<COUNT, false>(P, sm, acc, m, s_probes, s_tab, bits_all, stage, p0,
+                                                nP, edge, 0, 0, -1, c_probes_n);
+                    }
+                } else {
+                    // rounds: after round r every placement of true cost <= r is known; variant v
+                    // (z non-zero substitutions) runs probe stage r - z
+                    const int n0 = __ffsll((long long)nm) - 1;
+                    const int n1 = n_n == 2 ? 63 - __clzll((long long)nm) : -1;
+                    if (lane == 0) { sm.nm[0] = nm; sm.nm[1] = __brevll(nm) >> (64 - m); }
+                    const int nvar = nr_nvar_count(n_n);
 #pragma unroll 1
-                    for (int item = 0; item < nchunks; item++) {
-                        const int slot = item * 32 + (int)lane;
-                        const bool slot_ok = slot < nslots;
-                        const int strand = slot >= nP ? 1 : 0;
-                        const int p = p0 + slot - strand * nP;
-                        const uint64_t W = slot_ok ? nr_window64(sm.rdp[strand], p) : 0ull;
-                        uint64_t mask;
-                        if (stage == 0) {
-                            mask = probe_range<0>(bits_all, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_COST0>{});
-                            if (COUNT) c_probes_n += slot_ok ? NR_PROBES_COST0 : 0;
-                        } else if (stage == 1) {
-                            mask = probe_range<NR_PROBES_COST0>(bits_all, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_COST1 - NR_PROBES_COST0>{});
-                            if (COUNT) c_probes_n += slot_ok ? NR_PROBES_COST1 - NR_PROBES_COST0 : 0;
-                        } else {
-                            mask = probe_range<NR_PROBES_COST1>(bits_all, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_MAIN - NR_PROBES_COST1>{});
-                            if (COUNT) c_probes_n += slot_ok ? NR_PROBES_MAIN - NR_PROBES_COST1 : 0;
+                    for (int round = 0; round < 3; round++) {
+                        if (acc.best < round) break;
+#pragma unroll 1
+                        for (int v = 0; v < nvar; v++) {
+                            const int stage = round - nr_nvar_nonzero(v);
+                            if (stage < 0) continue;
+                            uint32_t wv[4];
+                            nr_nvar_apply(w4, n0, n1, v, wv);
+                            stage_read(sm, wv, m);
+                            run_stage<COUNT, true>(P, sm, acc, m, s_probes, s_tab, bits_all, stage, p0,
+                                                   nP, edge, v, n0, n1, c_probes_n);
                         }
-                        enqueue<COUNT>(P, sm, acc, m, s_probes, s_tab, mask, strand, p);
                     }
-                    if (stage == 2 && edge) {
-                        // one-column start overhang + interior insertion (slot -1 only)
-                        uint64_t mask = 0;
-                        const int strand = lane >= NR_PROBES_EDGE ? 1 : 0;
-                        if (lane < 2 * NR_PROBES_EDGE) {
-                            const int ti = NR_PROBES_MAIN + (int)lane - strand * NR_PROBES_EDGE;
-                            const uint64_t W = nr_window64(sm.rdp[strand], -1);
-                            const nr_probe_t t = probe_unpack(s_probes[ti]);
-                            const uint32_t key = nr_probe_key(W, t);
-                            const uint32_t w = __ldg(P.bits[0] + (key >> 5));
-                            mask = (uint64_t)((w >> (key & 31u)) & 1u) << ti;
-                            if (COUNT) c_probes_n++;
-                        }
-                        enqueue<COUNT>(P, sm, acc, m, s_probes, s_tab, mask, strand, -1);
-                    }
-                    while (acc.qn > 0) drain<COUNT>(P, sm, acc, m, s_probes, s_tab);
                 }
 
                 if (acc.overflow || (acc.best == 3 && P.resolve_below)) {
@@ -481,7 +568,9 @@ nr_match_filtered_kernel(const nr_filter_params P)
                     }
                 }
             }
-            if (to_list) {
+            if (to_nlist) {
+                if (lane == 0) P.list_n[atomicAdd(P.list_n_count, 1u)] = (uint32_t)cand;
+            } else if (to_list) {
                 if (lane == 0) {
                     uint32_t at = atomicAdd(P.list_count, 1u);
                     P.list[at] = (uint32_t)cand;
@@ -504,12 +593,16 @@ nr_match_filtered_kernel(const nr_filter_params P)
 // devices whose copy of c_probes has been written (bit per device ordinal)
 static std::atomic<unsigned long long> g_probes_uploaded{0ull};
 
-// Enqueue the filtered matcher on `stream`.  list_count must have been zeroed on the stream.
+// Enqueue the filtered matcher on `stream`: the main pass over all candidates, then (when
+// d_list_n is given) the N pass over the reads with N the main pass set aside.  The workspace
+// header (list counts, tile counters) must have been zeroed on the stream.
 int nr_launch_filtered(const nr_whitelist *wl, const void *d_bases, const uint8_t *d_meta,
-                       uint64_t n_cand, int min_score, int resolve_below, int32_t *d_idx,
-                       int8_t *d_score, uint8_t *d_nbest, uint8_t *d_flags, uint8_t *d_umi,
-                       uint32_t *d_list, uint32_t *d_list_count, unsigned long long *d_counters,
-                       int *grid_out, cudaStream_t stream)
+                       const uint64_t *d_nmask, uint64_t n_cand, int min_score, int resolve_below,
+                       int32_t *d_idx, int8_t *d_score, uint8_t *d_nbest, uint8_t *d_flags,
+                       uint8_t *d_umi, uint32_t *d_list, uint32_t *d_list_count,
+                       uint32_t *d_list_n, uint32_t *d_list_n_count,
+                       unsigned long long *d_tile_next, unsigned long long *d_tile_next_n,
+                       unsigned long long *d_counters, int *grid_out, cudaStream_t stream)
 {
     if (n_cand == 0) return NR_OK;
     if (!wl->has_index) {
@@ -533,14 +626,15 @@ int nr_launch_filtered(const nr_whitelist *wl, const void *d_bases, const uint8_
     P.min_score = min_score; P.resolve_below = resolve_below;
     P.o_idx = d_idx; P.o_score = d_score; P.o_nbest = d_nbest; P.o_flags = d_flags; P.o_umi = d_umi;
     P.list = d_list; P.list_count = d_list_count; P.counters = d_counters;
-    P.tile_next = (unsigned long long *)(d_list_count + 2);   // workspace header, offset 72
+    P.list_n = d_list_n; P.list_n_count = d_list_n_count; P.nmask = d_nmask;
+    P.tile_next = d_tile_next;
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
     if (d_counters)
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nr_match_filtered_kernel<true>,
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nr_match_filtered_kernel<true, false>,
                                                       NR_FWARPS * 32, 0);
     else
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nr_match_filtered_kernel<false>,
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nr_match_filtered_kernel<false, false>,
                                                       NR_FWARPS * 32, 0);
     if (per_sm < 1) per_sm = 1;
     uint64_t tiles = (n_cand + 31) / 32;
@@ -549,9 +643,21 @@ int nr_launch_filtered(const nr_whitelist *wl, const void *d_bases, const uint8_
     unsigned grid = (unsigned)(want < cap ? want : cap);
     if (grid_out) *grid_out = (int)grid;
     if (d_counters)
-        nr_match_filtered_kernel<true><<<grid, NR_FWARPS * 32, 0, stream>>>(P);
+        nr_match_filtered_kernel<true, false><<<grid, NR_FWARPS * 32, 0, stream>>>(P);
     else
-        nr_match_filtered_kernel<false><<<grid, NR_FWARPS * 32, 0, stream>>>(P);
+        nr_match_filtered_kernel<false, false><<<grid, NR_FWARPS * 32, 0, stream>>>(P);
     NR_CHECK_CUDA(cudaGetLastError());
+    if (d_list_n) {
+        // the N pass: how many reads it gets is only known on the device; a grid sized for one
+        // read in eight (far more than any real rate of N) exits at once where there is no tile
+        P.tile_next = d_tile_next_n;
+        uint64_t want_n = (want + 7) / 8;
+        unsigned grid_n = (unsigned)(want_n < cap ? (want_n ? want_n : 1) : cap);
+        if (d_counters)
+            nr_match_filtered_kernel<true, true><<<grid_n, NR_FWARPS * 32, 0, stream>>>(P);
+        else
+            nr_match_filtered_kernel<false, true><<<grid_n, NR_FWARPS * 32, 0, stream>>>(P);
+        NR_CHECK_CUDA(cudaGetLastError());
+    }
     return NR_OK;
 }

@@ -22,9 +22,11 @@ TSO_5P = b"TTTCTTATAT"
 def make_candidates(whitelist_ascii: np.ndarray, n: int, seed: int = 2, geometry: str = "5p",
                     umi_len: int = 12, p_sub: float = 0.02, p_ins: float = 0.02,
                     p_del: float = 0.02, frac_negative: float = 0.10, max_len: int = 64,
-                    cell_idx: np.ndarray | None = None, umi_codes: np.ndarray | None = None):
+                    cell_idx: np.ndarray | None = None, umi_codes: np.ndarray | None = None,
+                    p_n: float = 0.0):
     """-> dict(seqs u8 buffer, offsets u64 [n+1], true_idx int64 [n] (-1 for negatives),
-    umi [n, umi_len] codes)."""
+    umi [n, umi_len] codes).  p_n: per-base probability that the basecaller emitted N (drawn
+    last, so p_n = 0 reproduces the earlier streams)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     n_wl = len(whitelist_ascii)
     if cell_idx is None:
@@ -68,6 +70,8 @@ def make_candidates(whitelist_ascii: np.ndarray, n: int, seed: int = 2, geometry
     pos_base = start + is_ins
     ok = (~is_del) & (pos_base < max_len)
     out[(row0 + pos_base)[ok]] = _ASCII[base[ok]]
+    if p_n > 0:
+        out[rng.random(out.shape[0]) < p_n] = ord("N")
     true_idx = np.where(neg, -1, cell_idx).astype(np.int64)
     return {"seqs": out, "offsets": offsets, "true_idx": true_idx, "umi": umi_codes,
             "lens": lens_c}

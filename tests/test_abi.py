@@ -53,7 +53,7 @@ def test_argument_errors_without_gpu(built):
     assert L.nr_whitelist_create(b"A" * 40, 1, 40, 1, 1, 0, C.byref(h)) == -1       # core too long
     assert b"bad arguments" in L.nr_last_error()
     assert L.nr_match_host(None, None, None, 5, 14, 0, None, None, None, None, None) == -1
-    assert L.nr_match_workspace_bytes(None, 1000, 0) == 65536 + 12032          # header + three lists
+    assert L.nr_match_workspace_bytes(None, 1000, 0) == 65536 + 16128          # header + four lists
     assert L.nr_umi_records_workspace_bytes(0) > 0
     assert L.nr_umi_partition_device(None, None, None, None, 5, 0, None, None, None, None) == -1   # world 0
 

@@ -217,3 +217,102 @@ def test_probe_prefixes_complete_for_small_costs(oracle, emul, limit, max_cost):
         assert total > 1500
     finally:
         emul.nr_emul_set_probe_limit(0)
+
+
+# ---- reads with one or two N: substituted variants + N-aware automaton --------------------------
+
+def test_automaton_with_n_rows_equals_oracle_pair(oracle, emul):
+    O = oracle
+    rng = np.random.default_rng(11)
+    n_low = 0
+    for _ in range(8000):
+        pad_l = int(rng.choice([30, 4, 16, 0, 2]))
+        pad_r = int(rng.choice([40, 17, 28, 0, 3]))
+        core = rs(rng, 16)
+        mid = mutate(rng, core, int(rng.integers(0, 3)))
+        pre, suf = rs(rng, int(rng.integers(0, 36))), rs(rng, int(rng.integers(0, 30)))
+        mode = rng.integers(0, 6)
+        q = (mid[int(rng.integers(1, 4)):] + suf) if mode == 0 else \
+            (pre + mid[:-int(rng.integers(1, 4))]) if mode == 1 else (pre + mid + suf)
+        q = list(q[:64])
+        if not q:
+            continue
+        for _k in range(int(rng.integers(1, 3))):
+            # N mostly inside / next to the core
+            j = int(np.clip(len(pre) + rng.integers(-2, 19), 0, len(q) - 1)) if mode >= 2 else int(rng.integers(0, len(q)))
+            q[j] = "N"
+        q = "".join(q)
+        a1, u1 = O.pair(q, core, pad_l, pad_r)
+        qc, cc = np.ascontiguousarray(O.encode(q)), np.ascontiguousarray(O.encode(core))
+        u = C.c_int(-9)
+        cost = emul.nr_emul_nfa_n(P(qc, C.c_uint8), len(qc), P(cc, C.c_uint8), pad_l, pad_r, C.byref(u))
+        if 16 - a1 <= 2:
+            n_low += 1
+            assert (cost, u.value) == (16 - a1, u1), (q, core, pad_l, pad_r)
+        else:
+            assert cost == 3, (q, core, pad_l, pad_r, a1)
+    assert n_low > 600
+
+
+def run_emul_n(E, O, wl, cands, pad_l, pad_r):
+    wlc, _ = O.encode_many(wl, 16)
+    cc, cl = O.encode_many(cands, 64)
+    lo = np.zeros(len(wl), np.uint32)
+    for j in range(16):
+        lo |= wlc[:, j].astype(np.uint32) << np.uint32(2 * j)
+    n = len(cands)
+    out = dict(idx=np.zeros(n, np.int32), score=np.zeros(n, np.int8), nbest=np.zeros(n, np.int32),
+               strand=np.zeros(n, np.uint8), umi=np.zeros(n, np.int16), took=np.zeros(n, np.uint8))
+    cnt = np.zeros(2, np.int64)
+    rc = E.nr_emul_filtered_n(P(lo, C.c_uint32), C.c_int64(len(wl)), pad_l, pad_r, P(cc, C.c_uint8),
+                              P(cl.astype(np.uint8), C.c_uint8), C.c_int64(n), 24,
+                              P(out["idx"], C.c_int32), P(out["score"], C.c_int8),
+                              P(out["nbest"], C.c_int32), P(out["strand"], C.c_uint8),
+                              P(out["umi"], C.c_int16), P(out["took"], C.c_uint8), P(cnt, C.c_int64))
+    assert rc == 0
+    ref = O.match(wlc, pad_l, pad_r, cc, cl)
+    return ref, out, cnt
+
+
+def _with_n(rng, q, k, lo, hi):
+    q = list(q)
+    for j in rng.choice(np.arange(max(0, lo), min(len(q), hi)), size=k, replace=False):
+        q[int(j)] = "N"
+    return "".join(q)
+
+
+@pytest.mark.parametrize("pad_l,pad_r,qlen", [(30, 40, 50), (4, 17, 35), (16, 28, 41), (30, 40, 64)])
+def test_filter_n_reads_lossless_random(oracle, emul, pad_l, pad_r, qlen):
+    rng = np.random.default_rng(700 + qlen)
+    wl = tie_rich_whitelist(rng, 2500)
+    base = mixed_candidates(rng, wl, 2500, pad_l, qlen, with_n=0.0)
+    cands = []
+    for q in base:
+        if len(q) < 2:
+            continue
+        k = int(rng.choice([1, 1, 2]))
+        cands.append(_with_n(rng, q, k, 0, len(q)))
+    ref, out, cnt = run_emul_n(emul, oracle, wl, cands, pad_l, pad_r)
+    assert check(ref, out, cands, wl) > 200
+
+
+def test_filter_n_reads_all_small_cost_variants(oracle, emul):
+    """every <= 1-edit variant of a few cores, one or two N placed in / around the core, interior
+    and at both read ends: all placements of true cost <= 2 must be found."""
+    rng = np.random.default_rng(8)
+    wl = tie_rich_whitelist(rng, 400)
+    n_hi = 0
+    for rep in range(3):
+        core = wl[int(rng.integers(0, len(wl)))]
+        cands = []
+        for v in _variants(rng, core):
+            for where in range(3):
+                pre = rs(rng, [14, 0, 30][where])
+                suf = rs(rng, [20, 25, 0][where])
+                q = (pre + v + suf)[:64]
+                a = len(pre)
+                for k in (1, 2):
+                    cands.append(_with_n(rng, q, k, a - 1, a + len(v) + 1))
+        ref, out, cnt = run_emul_n(emul, oracle, wl, cands, 30, 40)
+        n_hi += check(ref, out, cands, wl)
+    assert n_hi > 500
