@@ -45,13 +45,18 @@ struct nr_whitelist {
     // deep tier (nr_deep_core.h, nr_deep_index.h): entries grouped by their first deep_s columns
     // (prefix groups, runs of the sorted order) and by their last L - deep_s (suffix groups)
     int has_deep;
-    int deep_s;
-    uint32_t deep_gpre, deep_gsuf;
+    int deep_s, deep_s1, deep_u1;     // split column; columns shared inside each half (mid groups)
+    uint32_t deep_gpre, deep_gsuf, deep_gpmid, deep_gsmid;
     uint32_t *d_deep_pre_start;   // deep_gpre + 1
     uint4 *d_deep_pre_rep;        // deep_gpre: {lo, hi, nm, 0} of the group's columns
     uint4 *d_deep_suf_rep;        // deep_gsuf
     uint32_t *d_deep_ent_suf;     // n: suffix group per sorted position
     uint32_t *d_deep_ent_idx;     // n: entry index per sorted position
+    uint32_t *d_deep_suf_start;   // deep_gsuf + 1: the same entries in suffix-group order
+    uint32_t *d_deep_sent_pre;    // n: prefix group per suffix-sorted position
+    uint32_t *d_deep_sent_idx;    // n: entry index per suffix-sorted position
+    uint4 *d_deep_pmid_rep;       // deep_gpmid: mid groups of the prefix side (pre_rep.w = parent)
+    uint4 *d_deep_smid_rep;       // deep_gsmid
     size_t bytes;
     void *host_ctx;  // lazily created staging state of nr_match_host (nr_match_api.cu)
 };

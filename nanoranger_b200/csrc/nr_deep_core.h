@@ -91,18 +91,19 @@ NR_HD void nr_deep_init_bwd(nr_deep_planes<K> &b, int m, int padR, uint64_t vali
     }
 }
 
-// consume one more core column (code c, col_n: the column is N) on the prefix side
-template <int K>
+// consume one more core column (code c, col_n: the column is N) on the prefix side.
+// NTERM = false drops the N terms: for callers that know neither the read nor the column has N.
+template <int K, bool NTERM = true>
 NR_HD void nr_deep_step_fwd(nr_deep_planes<K> &x, const nr_deep_rows &r, int c, bool col_n)
 {
-    const uint64_t eq = col_n ? 0ull : r.eq[c];
-    const uint64_t nr = col_n ? (r.valid & ~1ull) : r.nrow;
+    const uint64_t eq = (NTERM && col_n) ? 0ull : r.eq[c];
+    const uint64_t nr = !NTERM ? 0ull : (col_n ? (r.valid & ~1ull) : r.nrow);
     nr_deep_planes<K> y;
 #pragma unroll
     for (int e = 0; e <= K; e++) {
         uint64_t v = (x.v[e] << 1) & eq;                               // match
         if (e >= 1) {
-            v |= (x.v[e - 1] << 1) & nr;                               // N on either side: 1
+            if (NTERM) v |= (x.v[e - 1] << 1) & nr;                    // N on either side: 1
             v |= x.v[e - 1] & r.edge;                                  // column over a read end: 1
             v |= (y.v[e - 1] << 1);                                    // extra read base: 1
         }
@@ -117,17 +118,17 @@ NR_HD void nr_deep_step_fwd(nr_deep_planes<K> &x, const nr_deep_rows &r, int c, 
 }
 
 // the mirror image: prepend one core column on the suffix side
-template <int K>
+template <int K, bool NTERM = true>
 NR_HD void nr_deep_step_bwd(nr_deep_planes<K> &x, const nr_deep_rows &r, int c, bool col_n)
 {
-    const uint64_t eq = (col_n ? 0ull : r.eq[c]) >> 1;                 // bit i: base of row i+1
-    const uint64_t nr = (col_n ? (r.valid & ~1ull) : r.nrow) >> 1;
+    const uint64_t eq = ((NTERM && col_n) ? 0ull : r.eq[c]) >> 1;      // bit i: base of row i+1
+    const uint64_t nr = !NTERM ? 0ull : ((col_n ? (r.valid & ~1ull) : r.nrow) >> 1);
     nr_deep_planes<K> y;
 #pragma unroll
     for (int e = 0; e <= K; e++) {
         uint64_t v = (x.v[e] >> 1) & eq;
         if (e >= 1) {
-            v |= (x.v[e - 1] >> 1) & nr;
+            if (NTERM) v |= (x.v[e - 1] >> 1) & nr;
             v |= x.v[e - 1] & r.edge;
             v |= (y.v[e - 1] >> 1);
         }

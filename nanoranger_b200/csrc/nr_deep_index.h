@@ -15,10 +15,21 @@ struct nr_deep_index_host {
     int L = 0, s = 0;
     uint32_t g_pre = 0, g_suf = 0;
     std::vector<uint32_t> pre_start;    // g_pre + 1: first sorted position of every prefix group
-    std::vector<uint32_t> pre_rep;      // g_pre x 4: lo, hi, nm of the group's columns, 0
-    std::vector<uint32_t> suf_rep;      // g_suf x 4
+    std::vector<uint32_t> pre_rep;      // g_pre x 4: lo, hi, nm of the group's columns, parent
+    std::vector<uint32_t> suf_rep;      // g_suf x 4: lo, hi, nm, parent
     std::vector<uint32_t> ent_suf;      // n: suffix group of the entry at each sorted position
     std::vector<uint32_t> ent_idx;      // n: its index in the caller's whitelist
+    // the same entries ordered by suffix group (the deep tier scans whichever side is rarer)
+    std::vector<uint32_t> suf_start;    // g_suf + 1
+    std::vector<uint32_t> sent_pre;     // n: prefix group of the entry at each suffix-sorted position
+    std::vector<uint32_t> sent_idx;     // n: its index in the caller's whitelist
+    // one level of sharing inside each half: "mid" groups = distinct first s1 columns (parents of
+    // the prefix groups) and distinct last u1 columns (parents of the suffix groups); the automaton
+    // runs the shared columns once per mid group.  s1 = 0 / u1 = 0: no sharing on that side.
+    int s1 = 0, u1 = 0;
+    uint32_t g_pmid = 0, g_smid = 0;
+    std::vector<uint32_t> pmid_rep;     // g_pmid x 4: lo, hi, nm, 0
+    std::vector<uint32_t> smid_rep;     // g_smid x 4
 };
 
 namespace nr_deep_detail {
@@ -103,34 +114,65 @@ inline void nr_deep_index_build(const uint32_t *lo, const uint32_t *hi, const ui
     }
     out.L = L;
     out.s = s;
-    // suffix group ids
+    // shared columns inside each half: s1 of the prefix's s, u1 of the suffix's L - s
+    const uint64_t gpre = groups(hf, s), gsuf = groups(hb, L - s);
+    int s1 = 0, u1 = 0;
+    {
+        uint64_t best = gpre * (uint64_t)s;
+        for (int c = 1; c < s; c++) {
+            const uint64_t cost = groups(hf, c) * (uint64_t)c + gpre * (uint64_t)(s - c);
+            if (cost < best) { best = cost; s1 = c; }
+        }
+        best = gsuf * (uint64_t)(L - s);
+        for (int c = 1; c < L - s; c++) {
+            const uint64_t cost = groups(hb, c) * (uint64_t)c + gsuf * (uint64_t)(L - s - c);
+            if (cost < best) { best = cost; u1 = c; }
+        }
+    }
+    out.s1 = s1; out.u1 = u1;
+    auto push_rep = [&](std::vector<uint32_t> &v, uint32_t i, uint32_t parent) {
+        v.push_back(lo[i]); v.push_back(hi ? hi[i] : 0u); v.push_back(nm ? nm[i] : 0u);
+        v.push_back(parent);
+    };
+    // suffix groups (runs of the suffix-sorted order) and their parents
     std::vector<uint32_t> suf_of((size_t)n);
-    out.suf_rep.clear();
-    uint32_t gs = 0;
+    out.suf_rep.clear(); out.smid_rep.clear(); out.suf_start.clear();
+    out.sent_idx.resize((size_t)n);
+    uint32_t gs = 0, gsm = 0;
     for (uint64_t e = 0; e < n; e++) {
-        if (e == 0 || key_lcp(bw[(size_t)e - 1], bw[(size_t)e]) < L - s) {
-            const uint32_t i = bw[(size_t)e].idx;
-            out.suf_rep.push_back(lo[i]); out.suf_rep.push_back(hi ? hi[i] : 0u);
-            out.suf_rep.push_back(nm ? nm[i] : 0u); out.suf_rep.push_back(0u);
+        const int lcp = e == 0 ? -1 : key_lcp(bw[(size_t)e - 1], bw[(size_t)e]);
+        const uint32_t i = bw[(size_t)e].idx;
+        if (u1 > 0 && lcp < u1) { push_rep(out.smid_rep, i, 0u); gsm++; }
+        if (lcp < L - s) {
+            push_rep(out.suf_rep, i, u1 > 0 ? gsm - 1 : 0u);
+            out.suf_start.push_back((uint32_t)e);
             gs++;
         }
-        suf_of[bw[(size_t)e].idx] = gs - 1;
+        suf_of[i] = gs - 1;
+        out.sent_idx[(size_t)e] = i;
     }
-    out.g_suf = gs;
-    out.pre_start.clear(); out.pre_rep.clear();
+    out.suf_start.push_back((uint32_t)n);
+    out.g_suf = gs; out.g_smid = gsm;
+    // prefix groups
+    std::vector<uint32_t> pre_of((size_t)n);
+    out.pre_start.clear(); out.pre_rep.clear(); out.pmid_rep.clear();
     out.ent_suf.resize((size_t)n); out.ent_idx.resize((size_t)n);
-    uint32_t gp = 0;
+    uint32_t gp = 0, gpm = 0;
     for (uint64_t e = 0; e < n; e++) {
+        const int lcp = e == 0 ? -1 : key_lcp(fw[(size_t)e - 1], fw[(size_t)e]);
         const uint32_t i = fw[(size_t)e].idx;
-        if (e == 0 || key_lcp(fw[(size_t)e - 1], fw[(size_t)e]) < s) {
+        if (s1 > 0 && lcp < s1) { push_rep(out.pmid_rep, i, 0u); gpm++; }
+        if (lcp < s) {
             out.pre_start.push_back((uint32_t)e);
-            out.pre_rep.push_back(lo[i]); out.pre_rep.push_back(hi ? hi[i] : 0u);
-            out.pre_rep.push_back(nm ? nm[i] : 0u); out.pre_rep.push_back(0u);
+            push_rep(out.pre_rep, i, s1 > 0 ? gpm - 1 : 0u);
             gp++;
         }
+        pre_of[i] = gp - 1;
         out.ent_suf[(size_t)e] = suf_of[i];
         out.ent_idx[(size_t)e] = i;
     }
     out.pre_start.push_back((uint32_t)n);
-    out.g_pre = gp;
+    out.g_pre = gp; out.g_pmid = gpm;
+    out.sent_pre.resize((size_t)n);
+    for (uint64_t e = 0; e < n; e++) out.sent_pre[(size_t)e] = pre_of[out.sent_idx[(size_t)e]];
 }

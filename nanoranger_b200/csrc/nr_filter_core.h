@@ -471,3 +471,55 @@ NR_HD int nr_verify16(const uint32_t *rdp, int m, uint32_t core, int padL, int p
     *umi = arg;
     return best;
 }
+
+// bit t of x -> bit 2t (t < 32)
+NR_HD uint64_t nr_spread_even(uint32_t x)
+{
+    uint64_t v = x;
+    v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+    v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+    v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+}
+
+NR_HD uint64_t nr_rev_bits64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __brevll(x);
+#else
+    x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+    x = ((x >> 8) & 0x00FF00FF00FF00FFull) | ((x & 0x00FF00FF00FF00FFull) << 8);
+    x = ((x >> 16) & 0x0000FFFF0000FFFFull) | ((x & 0x0000FFFF0000FFFFull) << 16);
+    return (x >> 32) | (x << 32);
+#endif
+}
+
+// Verification of one nominated (entry, strand) for a read with N (nm: N mask of the strand,
+// rdp: any substituted variant).  The diagonal walk of nr_verify16 runs with the N rows counted
+// as matches -- a lower bound on the true cost, so "nothing within cost 2" is exact -- and
+// whatever survives is scored by the N-aware automaton over the rows around the slot.
+NR_HD int nr_verify16n(const uint32_t *rdp, uint64_t nm, int m, uint32_t core, int padL, int padR,
+                       int p, const nr_probe_t &t, int *umi)
+{
+    const int fwd = t.drop != 0;
+    const int pinned = fwd ? p : p + nr_probe_end(t);
+    uint64_t V = nr_window64(rdp, fwd ? pinned - 1 : pinned - 19);
+    if (!fwd) V = nr_rev_bases64(V) >> 24;
+    uint64_t vm = fwd ? nr_valid_mask(1 - pinned, m - pinned + 1)
+                      : nr_valid_mask(pinned - m + 1, pinned + 1);
+    // N rows as seen from the pinned end: base t of V is read[pinned - 1 + t] (forward) or
+    // read[pinned - t] (backward)
+    uint32_t nt;
+    if (fwd) nt = (uint32_t)(pinned >= 1 ? nm >> (pinned - 1) : nm << (1 - pinned));
+    else nt = (pinned >= 0 && pinned <= 63) ? (uint32_t)(nr_rev_bits64(nm) >> (63 - pinned))
+                                            : (uint32_t)(nr_rev_bits64(nm) << (pinned - 63));
+    vm &= ~nr_spread_even(nt);
+    if (!nr_lv16(V, vm, fwd ? core : nr_rev_bases32(core))) { *umi = -1; return 3; }
+    const int r0 = nr_rows_first(p);
+    return nr_nfa16n_w(nr_window64(rdp, r0), (uint32_t)(nm >> r0), m, core, padL, padR, r0,
+                       nr_rows_last(p, m), umi);
+}

@@ -13,11 +13,16 @@
 // Mapping.  One block resolves one candidate at a time (dynamic hand-out), strand after strand:
 //   rows     the strand's row masks (which read rows carry base c / N) from two ballots
 //   phase A  thread = one prefix or suffix group: K+1 planes of 64 read rows in registers, one
-//            automaton step per core column; planes [e][group] and the group's minimum into
-//            shared memory (global scratch, L2, when the whitelist has too many groups)
-//   phase B  warp = one prefix group (handed out through a shared counter), skipped when
-//            min(prefix) + min over all suffixes exceeds the running best; lane = one entry:
-//            suffix id (coalesced), two byte minima, and only if they can still reach the best the
+//            automaton step per core column.  A0 runs the columns shared inside each half once
+//            per "mid" group (distinct first s1 / last u1 columns), A1 continues every group from
+//            its parent's planes.  Planes [e][group] and the group's minimum go to shared memory
+//            (global scratch, L2, when the whitelist has too many groups)
+//   phase B  two-sided: a pair (prefix group, suffix group) can only reach cost <= K if the
+//            prefix minimum is <= K/2 or the suffix minimum is <= K - 1 - K/2, and groups that
+//            close to the read are rare (a handful out of thousands).  Warps scan the entries of
+//            those groups only -- prefix-sorted order for the hot prefix groups, suffix-sorted
+//            order for the hot suffix groups (minus what the prefix side already saw) -- lane =
+//            one entry: two byte minima, and only if they can still reach the running best the
 //            plane join  OR_{a+b=t} F_a & B_b
 //   merge    best cost / pairs attaining it / smallest pair, per thread, then over the block
 // The winner's UMI column and flags come from the same scalar pair DP the exhaustive kernel uses.
@@ -26,15 +31,15 @@
 #include "nr_deep_core.h"
 #include "nr_ex_common.cuh"
 
-#define NR_DEEP_THREADS 1024
+#define NR_DEEP_MAXTHREADS 1024
 
 struct nr_deep_params {
     // grouping (nr_deep_index.h)
-    const uint32_t *pre_start;
-    const uint4 *pre_rep, *suf_rep;
-    const uint32_t *ent_suf, *ent_idx;
-    uint32_t g_pre, g_suf;
-    int L, s, padL, padR;
+    const uint32_t *pre_start, *suf_start;
+    const uint4 *pre_rep, *suf_rep, *pmid_rep, *smid_rep;
+    const uint32_t *ent_suf, *ent_idx, *sent_pre, *sent_idx;
+    uint32_t g_pre, g_suf, g_pmid, g_smid;
+    int L, s, s1, u1, padL, padR;
     // whitelist cores (result writer)
     const uint32_t *lo, *hi, *nm;
     // candidates
@@ -73,29 +78,102 @@ __device__ __forceinline__ void plane_st(uint64_t *p, uint64_t v)
     else __stcg(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v);
 }
 
-template <int K, bool SMEM>
-__global__ void __launch_bounds__(NR_DEEP_THREADS, 1)
+// phase A for one strand; NTERM = false when neither the read nor the whitelist has N
+template <int K, bool SMEM, bool NTERM>
+__device__ __forceinline__ void phase_a(const nr_deep_params &P, const nr_deep_rows &rows, int m,
+                                        uint64_t *planes, uint64_t *mid, uint8_t *mins,
+                                        int *s_gmin /* [0] prefixes, [1] suffixes */)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t G = P.g_pre + P.g_suf, GM = P.g_pmid + P.g_smid;
+    // A0: shared columns, once per mid group
+    for (uint32_t g = tid; g < GM; g += blockDim.x) {
+        nr_deep_planes<K> x;
+        if (g < P.g_pmid) {
+            const uint4 rep = __ldg(P.pmid_rep + g);
+            nr_deep_init_fwd<K>(x, m, P.padL);
+#pragma unroll 1
+            for (int j = 0; j < P.s1; j++)
+                nr_deep_step_fwd<K, NTERM>(x, rows, nr_core_col(rep.x, rep.y, j), (rep.z >> j) & 1u);
+        } else {
+            const uint4 rep = __ldg(P.smid_rep + (g - P.g_pmid));
+            nr_deep_init_bwd<K>(x, m, P.padR, rows.valid);
+#pragma unroll 1
+            for (int j = P.L - 1; j >= P.L - P.u1; j--)
+                nr_deep_step_bwd<K, NTERM>(x, rows, nr_core_col(rep.x, rep.y, j), (rep.z >> j) & 1u);
+        }
+#pragma unroll
+        for (int e = 0; e <= K; e++) plane_st<SMEM>(mid + (size_t)e * GM + g, x.v[e]);
+    }
+    if (GM) __syncthreads();
+    // A1: the rest of each half, from the parent's planes
+    int my_fmin = K + 1, my_smin = K + 1;
+    for (uint32_t g = tid; g < G; g += blockDim.x) {
+        nr_deep_planes<K> x;
+        if (g < P.g_pre) {
+            const uint4 rep = __ldg(P.pre_rep + g);
+            if (P.s1 > 0) {
+#pragma unroll
+                for (int e = 0; e <= K; e++) x.v[e] = plane_ld<SMEM>(mid + (size_t)e * GM + rep.w);
+            } else {
+                nr_deep_init_fwd<K>(x, m, P.padL);
+            }
+#pragma unroll 1
+            for (int j = P.s1; j < P.s; j++)
+                nr_deep_step_fwd<K, NTERM>(x, rows, nr_core_col(rep.x, rep.y, j), (rep.z >> j) & 1u);
+        } else {
+            const uint4 rep = __ldg(P.suf_rep + (g - P.g_pre));
+            if (P.u1 > 0) {
+#pragma unroll
+                for (int e = 0; e <= K; e++)
+                    x.v[e] = plane_ld<SMEM>(mid + (size_t)e * GM + P.g_pmid + rep.w);
+            } else {
+                nr_deep_init_bwd<K>(x, m, P.padR, rows.valid);
+            }
+#pragma unroll 1
+            for (int j = P.L - 1 - P.u1; j >= P.s; j--)
+                nr_deep_step_bwd<K, NTERM>(x, rows, nr_core_col(rep.x, rep.y, j), (rep.z >> j) & 1u);
+        }
+        const int mn = nr_deep_min<K>(x);
+#pragma unroll
+        for (int e = 0; e <= K; e++) plane_st<SMEM>(planes + (size_t)e * G + g, x.v[e]);
+        mins[g] = (uint8_t)mn;
+        if (g < P.g_pre) my_fmin = min(my_fmin, mn); else my_smin = min(my_smin, mn);
+    }
+    my_fmin = __reduce_min_sync(0xffffffffu, my_fmin);
+    my_smin = __reduce_min_sync(0xffffffffu, my_smin);
+    if (lane == 0) {
+        if (my_fmin <= K) atomicMin(&s_gmin[0], my_fmin);
+        if (my_smin <= K) atomicMin(&s_gmin[1], my_smin);
+    }
+}
+
+template <int K, bool SMEM, bool WLN>
+__global__ void __launch_bounds__(NR_DEEP_MAXTHREADS, 1)
 nr_match_deep_kernel(const nr_deep_params P)
 {
     extern __shared__ __align__(16) uint8_t dyn[];
     __shared__ uint8_t cf[NR_MAX_QUERY], cr[NR_MAX_QUERY];
     __shared__ nr_deep_rows s_rows;
     __shared__ uint32_t s_bal[2][5];
-    __shared__ int s_bound, s_gsmin;
+    __shared__ int s_bound, s_gmin[2];
     __shared__ uint32_t s_grp_next;
     __shared__ unsigned long long s_item;
     __shared__ int s_rc[32];
     __shared__ uint32_t s_rn[32], s_rk[32];
 
+    constexpr int A = K / 2, B_ = K - 1 - K / 2;     // which side scans a pair (see header)
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t G = P.g_pre + P.g_suf;
-    uint64_t *planes;
+    const uint32_t G = P.g_pre + P.g_suf, GM = P.g_pmid + P.g_smid;
+    uint64_t *planes, *mid;
     uint8_t *mins;
     if (SMEM) {
         planes = reinterpret_cast<uint64_t *>(dyn);
-        mins = dyn + (size_t)G * (K + 1) * sizeof(uint64_t);
+        mid = planes + (size_t)G * (K + 1);
+        mins = reinterpret_cast<uint8_t *>(mid + (size_t)GM * (K + 1));
     } else {
         planes = reinterpret_cast<uint64_t *>(P.scratch + (size_t)blockIdx.x * P.scratch_per_block);
+        mid = planes + (size_t)G * (K + 1);
         mins = dyn;
     }
     const uint64_t total = P.list ? (uint64_t)*P.list_count : P.n_cand;
@@ -132,7 +210,7 @@ nr_match_deep_kernel(const nr_deep_params P)
                 const uint32_t bn_ = __ballot_sync(0xffffffffu, ok && code > 3);
                 if (lane == 0) s_bal[warp][4] = bn_;
             }
-            if (tid == 0) { s_gsmin = K + 1; s_grp_next = 0; }
+            if (tid == 64) { s_gmin[0] = K + 1; s_gmin[1] = K + 1; s_grp_next = 0; }
             __syncthreads();
             if (tid < 5) {
                 const uint64_t v = ((((uint64_t)s_bal[1][tid]) << 32) | (uint64_t)s_bal[0][tid]) << 1;
@@ -144,60 +222,67 @@ nr_match_deep_kernel(const nr_deep_params P)
             }
             __syncthreads();
 
-            // ---- phase A: one automaton per distinct prefix / suffix ---------------------------
-            int my_smin = K + 1;
-            for (uint32_t g = tid; g < G; g += NR_DEEP_THREADS) {
-                nr_deep_planes<K> x;
-                if (g < P.g_pre) {
-                    const uint4 rep = __ldg(P.pre_rep + g);
-                    nr_deep_init_fwd<K>(x, m, P.padL);
-#pragma unroll 1
-                    for (int j = 0; j < P.s; j++)
-                        nr_deep_step_fwd<K>(x, s_rows, nr_core_col(rep.x, rep.y, j), (rep.z >> j) & 1u);
-                } else {
-                    const uint4 rep = __ldg(P.suf_rep + (g - P.g_pre));
-                    nr_deep_init_bwd<K>(x, m, P.padR, s_rows.valid);
-#pragma unroll 1
-                    for (int j = P.L - 1; j >= P.s; j--)
-                        nr_deep_step_bwd<K>(x, s_rows, nr_core_col(rep.x, rep.y, j), (rep.z >> j) & 1u);
-                }
-                const int mn = nr_deep_min<K>(x);
-#pragma unroll
-                for (int e = 0; e <= K; e++) plane_st<SMEM>(planes + (size_t)e * G + g, x.v[e]);
-                mins[g] = (uint8_t)mn;
-                if (g >= P.g_pre) my_smin = min(my_smin, mn);
-            }
-            my_smin = __reduce_min_sync(0xffffffffu, my_smin);
-            if (lane == 0 && my_smin <= K) atomicMin(&s_gsmin, my_smin);
+            if (!WLN && !(mt & 0x80)) phase_a<K, SMEM, false>(P, s_rows, m, planes, mid, mins, s_gmin);
+            else phase_a<K, SMEM, true>(P, s_rows, m, planes, mid, mins, s_gmin);
             __syncthreads();
 
-            // ---- phase B: entries, prefix group by prefix group ----------------------------------
-            const int gsmin = s_gsmin;
+            // ---- phase B: the entries of the groups close to the read ---------------------------
+            const int gfmin = s_gmin[0], gsmin = s_gmin[1];
+            const uint32_t n_chunks = (G + 31) >> 5;
             for (;;) {
-                uint32_t g = 0;
-                if (lane == 0) g = atomicAdd(&s_grp_next, 1u);
-                g = __shfl_sync(0xffffffffu, g, 0);
-                if (g >= P.g_pre) break;
-                const int fm = mins[g];
-                if (fm + gsmin > *(volatile int *)&s_bound) continue;
-                uint64_t f[K + 1];
+                uint32_t chunk = 0;
+                if (lane == 0) chunk = atomicAdd(&s_grp_next, 1u);
+                chunk = __shfl_sync(0xffffffffu, chunk, 0);
+                if (chunk >= n_chunks) break;
+                const uint32_t gl = chunk * 32 + lane;
+                const int mn = gl < G ? (int)mins[gl] : K + 1;
+                const bool hot = gl < P.g_pre ? (mn <= A && mn + gsmin <= K)
+                                              : (gl < G && mn <= B_ && mn + gfmin <= K);
+                uint32_t hm = __ballot_sync(0xffffffffu, hot);
+                while (hm) {
+                    const int src = __ffs(hm) - 1;
+                    hm &= hm - 1;
+                    const uint32_t gg = chunk * 32 + (uint32_t)src;
+                    const int gmn = __shfl_sync(0xffffffffu, mn, src);
+                    uint64_t own[K + 1];
 #pragma unroll
-                for (int e = 0; e <= K; e++) f[e] = plane_ld<SMEM>(planes + (size_t)e * G + g);
-                const uint32_t p1 = __ldg(P.pre_start + g + 1);
-                for (uint32_t p = __ldg(P.pre_start + g) + lane; p < p1; p += 32) {
-                    const uint32_t h = __ldg(P.ent_suf + p);
-                    const int lb = fm + mins[P.g_pre + h];
-                    const int bound = *(volatile int *)&s_bound;
-                    if (lb <= bound) {
-                        uint64_t b[K + 1];
+                    for (int e = 0; e <= K; e++) own[e] = plane_ld<SMEM>(planes + (size_t)e * G + gg);
+                    if (gg < P.g_pre) {
+                        if (gmn + gsmin > *(volatile int *)&s_bound) continue;
+                        const uint32_t p1 = __ldg(P.pre_start + gg + 1);
+                        for (uint32_t p = __ldg(P.pre_start + gg) + lane; p < p1; p += 32) {
+                            const uint32_t h = __ldg(P.ent_suf + p);
+                            const int bound = *(volatile int *)&s_bound;
+                            if (gmn + (int)mins[P.g_pre + h] > bound) continue;
+                            uint64_t b[K + 1];
 #pragma unroll
-                        for (int e = 0; e <= K; e++)
-                            b[e] = plane_ld<SMEM>(planes + (size_t)e * G + P.g_pre + h);
-                        const int t = nr_deep_join<K>(f, b);
-                        if (t <= bound) {
-                            const uint32_t key = (__ldg(P.ent_idx + p) << 1) | (uint32_t)st;
-                            if (t < bc) { bc = t; bn = 1; bk = key; atomicMin(&s_bound, t); }
-                            else if (t == bc) { bn++; bk = min(bk, key); }
+                            for (int e = 0; e <= K; e++)
+                                b[e] = plane_ld<SMEM>(planes + (size_t)e * G + P.g_pre + h);
+                            const int t = nr_deep_join<K>(own, b);
+                            if (t <= bound) {
+                                const uint32_t key = (__ldg(P.ent_idx + p) << 1) | (uint32_t)st;
+                                if (t < bc) { bc = t; bn = 1; bk = key; atomicMin(&s_bound, t); }
+                                else if (t == bc) { bn++; bk = min(bk, key); }
+                            }
+                        }
+                    } else {
+                        const uint32_t h = gg - P.g_pre;
+                        if (gmn + gfmin > *(volatile int *)&s_bound) continue;
+                        const uint32_t p1 = __ldg(P.suf_start + h + 1);
+                        for (uint32_t p = __ldg(P.suf_start + h) + lane; p < p1; p += 32) {
+                            const uint32_t g = __ldg(P.sent_pre + p);
+                            const int fm = mins[g];
+                            const int bound = *(volatile int *)&s_bound;
+                            if (fm <= A || fm + gmn > bound) continue;   // fm <= A: the prefix side has it
+                            uint64_t f[K + 1];
+#pragma unroll
+                            for (int e = 0; e <= K; e++) f[e] = plane_ld<SMEM>(planes + (size_t)e * G + g);
+                            const int t = nr_deep_join<K>(f, own);
+                            if (t <= bound) {
+                                const uint32_t key = (__ldg(P.sent_idx + p) << 1) | (uint32_t)st;
+                                if (t < bc) { bc = t; bn = 1; bk = key; atomicMin(&s_bound, t); }
+                                else if (t == bc) { bn++; bk = min(bk, key); }
+                            }
                         }
                     }
                 }
@@ -218,7 +303,7 @@ nr_match_deep_kernel(const nr_deep_params P)
         if (tid == 0) {
             int c = K + 1;
             uint32_t n = 0, k = 0xFFFFFFFFu;
-            for (int w = 0; w < NR_DEEP_THREADS / 32; w++) {
+            for (uint32_t w = 0; w < (blockDim.x >> 5); w++) {
                 if (s_rc[w] < c) { c = s_rc[w]; n = s_rn[w]; k = s_rk[w]; }
                 else if (s_rc[w] == c) { n += s_rn[w]; k = min(k, s_rk[w]); }
             }
@@ -236,24 +321,36 @@ nr_match_deep_kernel(const nr_deep_params P)
 
 size_t deep_planes_bytes(const nr_whitelist *wl, int K)
 {
-    return (size_t)(wl->deep_gpre + wl->deep_gsuf) * (size_t)(K + 1) * sizeof(uint64_t);
+    return (size_t)(wl->deep_gpre + wl->deep_gsuf + wl->deep_gpmid + wl->deep_gsmid) *
+           (size_t)(K + 1) * sizeof(uint64_t);
 }
 
 constexpr size_t DEEP_SMEM_MAX = 227 * 1024 - 2048;    // dynamic budget next to ~1 KB static
 
-template <int K>
-int launch_k(const nr_whitelist *wl, nr_deep_params &P, uint8_t *d_scratch, size_t scratch_bytes,
-             cudaStream_t stream)
+// threads per block: every thread gets the same number of phase-A groups (to within one warp)
+unsigned deep_threads(size_t G)
+{
+    const size_t rounds = (G + NR_DEEP_MAXTHREADS - 1) / NR_DEEP_MAXTHREADS;
+    size_t t = ((G + rounds - 1) / rounds + 31) & ~(size_t)31;
+    if (t < 256) t = 256;
+    if (t > NR_DEEP_MAXTHREADS) t = NR_DEEP_MAXTHREADS;
+    return (unsigned)t;
+}
+
+template <int K, bool WLN>
+int launch_kw(const nr_whitelist *wl, nr_deep_params &P, uint8_t *d_scratch, size_t scratch_bytes,
+              cudaStream_t stream)
 {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
     const size_t G = (size_t)wl->deep_gpre + wl->deep_gsuf;
     const size_t pb = deep_planes_bytes(wl, K);
+    const unsigned threads = deep_threads(G);
     if (pb + G <= DEEP_SMEM_MAX) {
         const size_t smem = pb + G;
-        NR_CHECK_CUDA(cudaFuncSetAttribute(nr_match_deep_kernel<K, true>,
+        NR_CHECK_CUDA(cudaFuncSetAttribute(nr_match_deep_kernel<K, true, WLN>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nr_match_deep_kernel<K, true><<<sms, NR_DEEP_THREADS, smem, stream>>>(P);
+        nr_match_deep_kernel<K, true, WLN><<<sms, threads, smem, stream>>>(P);
     } else {
         const size_t per = (pb + 255) & ~(size_t)255;
         size_t blocks = d_scratch ? scratch_bytes / per : 0;
@@ -264,12 +361,20 @@ int launch_k(const nr_whitelist *wl, nr_deep_params &P, uint8_t *d_scratch, size
         }
         P.scratch = d_scratch;
         P.scratch_per_block = per;
-        NR_CHECK_CUDA(cudaFuncSetAttribute(nr_match_deep_kernel<K, false>,
+        NR_CHECK_CUDA(cudaFuncSetAttribute(nr_match_deep_kernel<K, false, WLN>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G));
-        nr_match_deep_kernel<K, false><<<(unsigned)blocks, NR_DEEP_THREADS, G, stream>>>(P);
+        nr_match_deep_kernel<K, false, WLN><<<(unsigned)blocks, threads, G, stream>>>(P);
     }
     NR_CHECK_CUDA(cudaGetLastError());
     return NR_OK;
+}
+
+template <int K>
+int launch_k(const nr_whitelist *wl, nr_deep_params &P, uint8_t *d_scratch, size_t scratch_bytes,
+             cudaStream_t stream)
+{
+    return wl->has_n ? launch_kw<K, true>(wl, P, d_scratch, scratch_bytes, stream)
+                     : launch_kw<K, false>(wl, P, d_scratch, scratch_bytes, stream);
 }
 
 }  // namespace
@@ -308,8 +413,11 @@ int nr_launch_deep(const nr_whitelist *wl, int K, const void *d_bases, const uin
     nr_deep_params P;
     P.pre_start = wl->d_deep_pre_start; P.pre_rep = wl->d_deep_pre_rep; P.suf_rep = wl->d_deep_suf_rep;
     P.ent_suf = wl->d_deep_ent_suf; P.ent_idx = wl->d_deep_ent_idx;
-    P.g_pre = wl->deep_gpre; P.g_suf = wl->deep_gsuf;
-    P.L = (int)wl->L; P.s = wl->deep_s; P.padL = (int)wl->pad_l; P.padR = (int)wl->pad_r;
+    P.suf_start = wl->d_deep_suf_start; P.sent_pre = wl->d_deep_sent_pre; P.sent_idx = wl->d_deep_sent_idx;
+    P.pmid_rep = wl->d_deep_pmid_rep; P.smid_rep = wl->d_deep_smid_rep;
+    P.g_pre = wl->deep_gpre; P.g_suf = wl->deep_gsuf; P.g_pmid = wl->deep_gpmid; P.g_smid = wl->deep_gsmid;
+    P.L = (int)wl->L; P.s = wl->deep_s; P.s1 = wl->deep_s1; P.u1 = wl->deep_u1;
+    P.padL = (int)wl->pad_l; P.padR = (int)wl->pad_r;
     P.lo = wl->d_lo; P.hi = wl->d_hi; P.nm = wl->d_nm;
     P.bases = (const uint4 *)d_bases; P.meta = d_meta; P.nmask = d_nmask;
     P.list = d_list; P.list_count = d_list_count; P.n_cand = n_cand; P.min_score = min_score;

@@ -182,11 +182,9 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, A
             const int p = (int)(o_item >> 25) - 16;
             const uint2 e = __ldcg(T4.ents[od] + o_start + (g - o_excl));
             if (NMODE) {
-                // reads with N: the automaton over the rows around the slot, N rows at cost 1
-                // (sm.rdp holds a substituted variant; the N rows ignore their base)
-                const int r0 = nr_rows_first(p);
-                cost = nr_nfa16n_w(nr_window64(sm.rdp[strand], r0), (uint32_t)(sm.nm[strand] >> r0),
-                                   m, e.y, P.padL, P.padR, r0, nr_rows_last(p, m), &u);
+                // reads with N: diagonal walk with the N rows as wildcards, then the N-aware
+                // automaton (sm.rdp holds a substituted variant; the N rows ignore their base)
+                cost = nr_verify16n(sm.rdp[strand], sm.nm[strand], m, e.y, P.padL, P.padR, p, ot, &u);
             } else {
                 cost = nr_verify16(sm.rdp[strand], m, e.y, P.padL, P.padR, p, ot, &u);
             }
@@ -436,8 +434,11 @@ nr_match_filtered_kernel(const nr_filter_params P)
     const int warp = threadIdx.x >> 5;
     WarpSmem &sm = smem[warp];
     const uint32_t *__restrict__ bits_all = P.bits[0];
+    // candidates per tile: the N pass gets few reads (a few per cent of the batch), each several
+    // times dearer than a plain read: small tiles keep its tail short
+    constexpr uint32_t TS = NMODE ? 4u : 32u;
     const uint64_t n_items = NMODE ? (uint64_t)*P.list_n_count : P.n_cand;
-    const uint64_t n_tiles = (n_items + 31) >> 5;
+    const uint64_t n_tiles = (n_items + TS - 1) / TS;
     unsigned long long c_probes_n = 0, c_listed = 0;
     Acc acc;
     acc.c_hits = acc.c_ver = acc.c_pass = 0;
@@ -455,9 +456,9 @@ nr_match_filtered_kernel(const nr_filter_params P)
         uint32_t cidx = 0;      // N pass: the candidate this lane loaded
         uint32_t nm_lo = 0, nm_hi = 0;
         {
-            const uint64_t mine = tile * 32 + lane;
+            const uint64_t mine = tile * TS + lane;
             uint4 b = make_uint4(0u, 0u, 0u, 0u);
-            if (mine < n_items) {
+            if (lane < TS && mine < n_items) {
                 if (NMODE) {
                     cidx = P.list_n[mine];
                     b = __ldg(P.bases + cidx); mt = P.meta[cidx];
@@ -471,12 +472,12 @@ nr_match_filtered_kernel(const nr_filter_params P)
             sm.tile[lane] = b;
             __syncwarp();
         }
-        const int in_tile = (int)min((uint64_t)32, n_items - tile * 32);
+        const int in_tile = (int)min((uint64_t)TS, n_items - tile * TS);
 
 #pragma unroll 1
         for (int c = 0; c < in_tile; c++) {
             const uint32_t cmt = __shfl_sync(0xffffffffu, mt, c);
-            const uint64_t cand = NMODE ? (uint64_t)__shfl_sync(0xffffffffu, cidx, c) : tile * 32 + c;
+            const uint64_t cand = NMODE ? (uint64_t)__shfl_sync(0xffffffffu, cidx, c) : tile * TS + c;
             if (cmt == 0xFFu) {          // longer than NR_MAX_QUERY: not scored
                 if (lane == 0) {
                     P.o_idx[cand] = -1; P.o_score[cand] = NR_SCORE_BELOW; P.o_nbest[cand] = 0;

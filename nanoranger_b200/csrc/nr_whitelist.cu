@@ -208,23 +208,38 @@ extern "C" int nr_whitelist_create(const char *cores, uint64_t n, uint32_t core_
         nr_deep_index_host ix;
         nr_deep_index_build(lo.data(), core_len > 16 ? hi.data() : nullptr,
                             has_n ? nmv.data() : nullptr, n, (int)core_len, 0, ix);
-        w->deep_s = ix.s; w->deep_gpre = ix.g_pre; w->deep_gsuf = ix.g_suf;
+        w->deep_s = ix.s; w->deep_s1 = ix.s1; w->deep_u1 = ix.u1;
+        w->deep_gpre = ix.g_pre; w->deep_gsuf = ix.g_suf;
+        w->deep_gpmid = ix.g_pmid; w->deep_gsmid = ix.g_smid;
         const size_t b_ps = (size_t)(ix.g_pre + 1) * 4, b_pr = (size_t)ix.g_pre * 16,
-                     b_sr = (size_t)ix.g_suf * 16;
+                     b_ss = (size_t)(ix.g_suf + 1) * 4, b_sr = (size_t)ix.g_suf * 16,
+                     b_pm = (size_t)ix.g_pmid * 16 + 16, b_sm = (size_t)ix.g_smid * 16 + 16;
         if (cudaMalloc(&w->d_deep_pre_start, b_ps) != cudaSuccess ||
             cudaMalloc(&w->d_deep_pre_rep, b_pr) != cudaSuccess ||
+            cudaMalloc(&w->d_deep_suf_start, b_ss) != cudaSuccess ||
             cudaMalloc(&w->d_deep_suf_rep, b_sr) != cudaSuccess ||
+            cudaMalloc(&w->d_deep_pmid_rep, b_pm) != cudaSuccess ||
+            cudaMalloc(&w->d_deep_smid_rep, b_sm) != cudaSuccess ||
             cudaMalloc(&w->d_deep_ent_suf, nb) != cudaSuccess ||
-            cudaMalloc(&w->d_deep_ent_idx, nb) != cudaSuccess) {
+            cudaMalloc(&w->d_deep_ent_idx, nb) != cudaSuccess ||
+            cudaMalloc(&w->d_deep_sent_pre, nb) != cudaSuccess ||
+            cudaMalloc(&w->d_deep_sent_idx, nb) != cudaSuccess) {
             nr_set_error("cudaMalloc deep index");
             return fail(NR_ENOMEM);
         }
-        w->bytes += b_ps + b_pr + b_sr + 2 * nb;
+        w->bytes += b_ps + b_pr + b_ss + b_sr + b_pm + b_sm + 4 * nb;
         cudaMemcpy(w->d_deep_pre_start, ix.pre_start.data(), b_ps, cudaMemcpyHostToDevice);
         cudaMemcpy(w->d_deep_pre_rep, ix.pre_rep.data(), b_pr, cudaMemcpyHostToDevice);
+        cudaMemcpy(w->d_deep_suf_start, ix.suf_start.data(), b_ss, cudaMemcpyHostToDevice);
         cudaMemcpy(w->d_deep_suf_rep, ix.suf_rep.data(), b_sr, cudaMemcpyHostToDevice);
+        if (ix.g_pmid)
+            cudaMemcpy(w->d_deep_pmid_rep, ix.pmid_rep.data(), (size_t)ix.g_pmid * 16, cudaMemcpyHostToDevice);
+        if (ix.g_smid)
+            cudaMemcpy(w->d_deep_smid_rep, ix.smid_rep.data(), (size_t)ix.g_smid * 16, cudaMemcpyHostToDevice);
         cudaMemcpy(w->d_deep_ent_suf, ix.ent_suf.data(), nb, cudaMemcpyHostToDevice);
         cudaMemcpy(w->d_deep_ent_idx, ix.ent_idx.data(), nb, cudaMemcpyHostToDevice);
+        cudaMemcpy(w->d_deep_sent_pre, ix.sent_pre.data(), nb, cudaMemcpyHostToDevice);
+        cudaMemcpy(w->d_deep_sent_idx, ix.sent_idx.data(), nb, cudaMemcpyHostToDevice);
         w->has_deep = 1;
     }
     cudaError_t e = cudaDeviceSynchronize();
@@ -247,6 +262,8 @@ extern "C" void nr_whitelist_destroy(nr_whitelist_t *w)
     cudaFree(w->d_bits[0]);
     cudaFree(w->d_deep_pre_start); cudaFree(w->d_deep_pre_rep); cudaFree(w->d_deep_suf_rep);
     cudaFree(w->d_deep_ent_suf); cudaFree(w->d_deep_ent_idx);
+    cudaFree(w->d_deep_suf_start); cudaFree(w->d_deep_sent_pre); cudaFree(w->d_deep_sent_idx);
+    cudaFree(w->d_deep_pmid_rep); cudaFree(w->d_deep_smid_rep);
     for (int j = 0; j < 4; j++) { cudaFree(w->d_rank[j]); cudaFree(w->d_ents[j]); cudaFree(w->d_kstart[j]); }
     delete w;
     if (prev >= 0) cudaSetDevice(prev);

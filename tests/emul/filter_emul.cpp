@@ -252,10 +252,8 @@ int nr_emul_filtered_n(const uint32_t *wl, int64_t n, int padL, int padR, const 
                                                   (size_t)nr_popc32(bw & ((1u << (key & 31u)) - 1u));
                                 for (size_t r = ix.kstart[pr.drop][kr]; r < ix.kstart[pr.drop][kr + 1]; r++) {
                                     const uint32_t e = ix.rows[pr.drop][r].second;
-                                    const int r0 = nr_rows_first(p), r1 = nr_rows_last(p, m);
                                     int u;
-                                    const int cost = nr_nfa16n_w(nr_window64(rdp[s], r0), (uint32_t)(nms[s] >> r0),
-                                                                 m, wl[e], padL, padR, r0, r1, &u);
+                                    const int cost = nr_verify16n(rdp[s], nms[s], m, wl[e], padL, padR, p, pr, &u);
                                     counters[1]++;
                                     if (cost > 2) continue;
                                     if (cost < best) best = cost;

@@ -60,7 +60,7 @@ def run_emul(E, O, wl, cands, pad_l, pad_r, K, force_s=0):
     n = len(cands)
     out = dict(idx=np.zeros(n, np.int32), score=np.zeros(n, np.int8), nbest=np.zeros(n, np.int32),
                strand=np.zeros(n, np.uint8), took=np.zeros(n, np.uint8))
-    info = np.zeros(3, np.int32)
+    info = np.zeros(7, np.int32)
     rc = E.nr_emul_deep(P(lo, C.c_uint32), P(hi, C.c_uint32), P(nm, C.c_uint32), C.c_int64(len(wl)),
                         L, pad_l, pad_r, K, force_s, P(cc, C.c_uint8), P(cl.astype(np.uint8), C.c_uint8),
                         C.c_int64(n), P(out["idx"], C.c_int32), P(out["score"], C.c_int8),
@@ -141,3 +141,4 @@ def test_deep_real_737k_sample(oracle, emul):
     ref, out, info, cl = run_emul(emul, oracle, wl, cands, 30, 40, 5)
     assert check(ref, out, cl, 16, 5, cands, wl) > 350
     assert info[1] < len(wl) and info[2] < len(wl)
+    assert 0 < info[3] < info[0] and 0 < info[5] < info[1], info      # prefix side shares columns
