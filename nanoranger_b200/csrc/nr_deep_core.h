@@ -175,3 +175,35 @@ NR_HD int nr_core_col(uint32_t lo, uint32_t hi, int j)
 {
     return (int)(((j < 16) ? (lo >> (2 * j)) : (hi >> (2 * (j - 16)))) & 3u);
 }
+
+// UMI column of one (candidate, entry) pair whose cost c <= K is known: the smallest read row i at
+// which an optimal alignment leaves the core, i.e. the smallest i with
+//     T0[i][L] + max(0, m - i - padR) == c,
+// where T0 is T without the "column hangs over the read END" rule (an alignment that ends inside
+// the core never reaches reference column padL+L: utils.py:705-710 then finds no query index).
+// Returns -1 when no row qualifies.  rows.edge must be 1 (bit 0 only) for this automaton.
+template <int K>
+NR_HD int nr_deep_umi_row(const nr_deep_rows &rows0, uint32_t lo, uint32_t hi, uint32_t nm, int L,
+                          int m, int padL, int padR, int c)
+{
+    nr_deep_planes<K> x;
+    nr_deep_init_fwd<K>(x, m, padL);
+    for (int j = 0; j < L; j++) nr_deep_step_fwd<K>(x, rows0, nr_core_col(lo, hi, j), (nm >> j) & 1u);
+    int best = 64;
+#pragma unroll
+    for (int e = 0; e <= K; e++) {
+        if (e > c) continue;
+        int from = m - padR - (c - e);                  // rows with suffix excess <= c - e
+        if (from < 0) from = 0;
+        const uint64_t s = x.v[e] & ~((1ull << from) - 1ull);
+        if (s) {
+#if defined(__CUDA_ARCH__)
+            const int i = __ffsll((long long)s) - 1;
+#else
+            const int i = __builtin_ctzll(s);
+#endif
+            if (i < best) best = i;
+        }
+    }
+    return best == 64 ? -1 : best;
+}

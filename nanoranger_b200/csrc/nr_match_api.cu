@@ -30,6 +30,11 @@ int nr_launch_deep(const nr_whitelist *wl, int K, const void *d_bases, const uin
                    uint32_t *d_next_count, unsigned long long *d_work_next,
                    unsigned long long *d_resolved, uint8_t *d_scratch, size_t scratch_bytes,
                    cudaStream_t stream);
+int nr_launch_deep_finalize(const nr_whitelist *wl, const void *d_bases, const uint8_t *d_meta,
+                            const uint64_t *d_nmask, const uint32_t *d_list,
+                            const uint32_t *d_list_count, uint64_t n_cand, const int32_t *d_idx,
+                            const int8_t *d_score, uint8_t *d_flags, uint8_t *d_umi,
+                            cudaStream_t stream);
 size_t nr_deep_scratch_bytes(const nr_whitelist *wl, int K);
 int nr_deep_usable(const nr_whitelist *wl);
 
@@ -92,6 +97,9 @@ int resolve_chain(const nr_whitelist *wl, const void *d_bases, const uint8_t *d_
         rc = nr_launch_deep(wl, 5, d_bases, d_meta, d_nmask, listB, cntB, n, min_score, d_idx,
                             d_score, d_nbest, d_flags, d_umi_q, listC, cntC,
                             (unsigned long long *)(ws + 96), ctr + 6, scratch, sb, st);
+        if (rc != NR_OK) return rc;
+        rc = nr_launch_deep_finalize(wl, d_bases, d_meta, d_nmask, from_all ? nullptr : listA, cntA,
+                                     n, d_idx, d_score, d_flags, d_umi_q, st);
         if (rc != NR_OK) return rc;
         ex_list = listC; ex_cnt = cntC;
     } else if (from_all) {

@@ -32,6 +32,9 @@
 #include "nr_ex_common.cuh"
 
 #define NR_DEEP_MAXTHREADS 1024
+#define NR_DEEP_HCAP 2048          // groups per phase-B window (= capacity of the hot list)
+#define NR_DEEP_ITEM 128           // entries per phase-B work item (4 per lane, loads issued together)
+#define NR_UMI_PENDING 254         // umi_q placeholder between the resolver and the finaliser
 
 struct nr_deep_params {
     // grouping (nr_deep_index.h)
@@ -157,7 +160,8 @@ nr_match_deep_kernel(const nr_deep_params P)
     __shared__ nr_deep_rows s_rows;
     __shared__ uint32_t s_bal[2][5];
     __shared__ int s_bound, s_gmin[2];
-    __shared__ uint32_t s_grp_next;
+    __shared__ uint32_t s_nhot, s_item_next;
+    __shared__ uint32_t s_hot[NR_DEEP_HCAP], s_hpre[NR_DEEP_HCAP + 1];
     __shared__ unsigned long long s_item;
     __shared__ int s_rc[32];
     __shared__ uint32_t s_rn[32], s_rk[32];
@@ -210,7 +214,7 @@ nr_match_deep_kernel(const nr_deep_params P)
                 const uint32_t bn_ = __ballot_sync(0xffffffffu, ok && code > 3);
                 if (lane == 0) s_bal[warp][4] = bn_;
             }
-            if (tid == 64) { s_gmin[0] = K + 1; s_gmin[1] = K + 1; s_grp_next = 0; }
+            if (tid == 64) { s_gmin[0] = K + 1; s_gmin[1] = K + 1; }
             __syncthreads();
             if (tid < 5) {
                 const uint64_t v = ((((uint64_t)s_bal[1][tid]) << 32) | (uint64_t)s_bal[0][tid]) << 1;
@@ -227,65 +231,111 @@ nr_match_deep_kernel(const nr_deep_params P)
             __syncthreads();
 
             // ---- phase B: the entries of the groups close to the read ---------------------------
+            // Per window of NR_DEEP_HCAP groups: list the hot groups, cut their entries into items
+            // of NR_DEEP_ITEM, hand the items to the warps (a hot group has hundreds of entries and
+            // there are only a few dozen of them: one warp per group would leave most warps idle).
             const int gfmin = s_gmin[0], gsmin = s_gmin[1];
-            const uint32_t n_chunks = (G + 31) >> 5;
-            for (;;) {
-                uint32_t chunk = 0;
-                if (lane == 0) chunk = atomicAdd(&s_grp_next, 1u);
-                chunk = __shfl_sync(0xffffffffu, chunk, 0);
-                if (chunk >= n_chunks) break;
-                const uint32_t gl = chunk * 32 + lane;
-                const int mn = gl < G ? (int)mins[gl] : K + 1;
-                const bool hot = gl < P.g_pre ? (mn <= A && mn + gsmin <= K)
-                                              : (gl < G && mn <= B_ && mn + gfmin <= K);
-                uint32_t hm = __ballot_sync(0xffffffffu, hot);
-                while (hm) {
-                    const int src = __ffs(hm) - 1;
-                    hm &= hm - 1;
-                    const uint32_t gg = chunk * 32 + (uint32_t)src;
-                    const int gmn = __shfl_sync(0xffffffffu, mn, src);
+            for (uint32_t w0 = 0; w0 < G; w0 += NR_DEEP_HCAP) {
+                if (tid == 0) { s_nhot = 0; s_item_next = 0; }
+                __syncthreads();
+                const uint32_t w1 = min(G, w0 + NR_DEEP_HCAP);
+                for (uint32_t g = w0 + tid; g < w1; g += blockDim.x) {
+                    const int mn = mins[g];
+                    const bool hot = g < P.g_pre ? (mn <= A && mn + gsmin <= K)
+                                                 : (mn <= B_ && mn + gfmin <= K);
+                    if (hot) s_hot[atomicAdd(&s_nhot, 1u)] = g;
+                }
+                __syncthreads();
+                const uint32_t nh = s_nhot;
+                if (warp == 0) {
+                    uint32_t running = 0;
+                    for (uint32_t base = 0; base < nh; base += 32) {
+                        const uint32_t i = base + lane;
+                        uint32_t cnt = 0;
+                        if (i < nh) {
+                            const uint32_t g = s_hot[i];
+                            const uint32_t *st_ = g < P.g_pre ? P.pre_start + g : P.suf_start + (g - P.g_pre);
+                            cnt = (__ldg(st_ + 1) - __ldg(st_) + NR_DEEP_ITEM - 1) / NR_DEEP_ITEM;
+                        }
+                        uint32_t incl = cnt;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                            if ((int)lane >= o) incl += v;
+                        }
+                        if (i < nh) s_hpre[i] = running + incl - cnt;
+                        running += __shfl_sync(0xffffffffu, incl, 31);
+                    }
+                    if (lane == 0) s_hpre[nh] = running;
+                }
+                __syncthreads();
+                const uint32_t n_items = s_hpre[nh];
+                for (;;) {
+                    uint32_t item = 0;
+                    if (lane == 0) item = atomicAdd(&s_item_next, 1u);
+                    item = __shfl_sync(0xffffffffu, item, 0);
+                    if (item >= n_items) break;
+                    uint32_t lo_ = 0, hi_ = nh;                 // largest k with s_hpre[k] <= item
+                    while (hi_ - lo_ > 1) {
+                        const uint32_t md = (lo_ + hi_) >> 1;
+                        if (s_hpre[md] <= item) lo_ = md; else hi_ = md;
+                    }
+                    const uint32_t gg = s_hot[lo_];
+                    const uint32_t off = (item - s_hpre[lo_]) * NR_DEEP_ITEM + lane;
+                    const int gmn = mins[gg];
                     uint64_t own[K + 1];
 #pragma unroll
                     for (int e = 0; e <= K; e++) own[e] = plane_ld<SMEM>(planes + (size_t)e * G + gg);
                     if (gg < P.g_pre) {
                         if (gmn + gsmin > *(volatile int *)&s_bound) continue;
-                        const uint32_t p1 = __ldg(P.pre_start + gg + 1);
-                        for (uint32_t p = __ldg(P.pre_start + gg) + lane; p < p1; p += 32) {
-                            const uint32_t h = __ldg(P.ent_suf + p);
+                        const uint32_t p0 = __ldg(P.pre_start + gg) + off, p1 = __ldg(P.pre_start + gg + 1);
+                        uint32_t h[NR_DEEP_ITEM / 32];
+#pragma unroll
+                        for (int u = 0; u < NR_DEEP_ITEM / 32; u++)
+                            h[u] = p0 + 32 * u < p1 ? __ldg(P.ent_suf + p0 + 32 * u) : 0xFFFFFFFFu;
+#pragma unroll
+                        for (int u = 0; u < NR_DEEP_ITEM / 32; u++) {
+                            if (h[u] == 0xFFFFFFFFu) continue;
                             const int bound = *(volatile int *)&s_bound;
-                            if (gmn + (int)mins[P.g_pre + h] > bound) continue;
+                            if (gmn + (int)mins[P.g_pre + h[u]] > bound) continue;
                             uint64_t b[K + 1];
 #pragma unroll
                             for (int e = 0; e <= K; e++)
-                                b[e] = plane_ld<SMEM>(planes + (size_t)e * G + P.g_pre + h);
+                                b[e] = plane_ld<SMEM>(planes + (size_t)e * G + P.g_pre + h[u]);
                             const int t = nr_deep_join<K>(own, b);
                             if (t <= bound) {
-                                const uint32_t key = (__ldg(P.ent_idx + p) << 1) | (uint32_t)st;
+                                const uint32_t key = (__ldg(P.ent_idx + p0 + 32 * u) << 1) | (uint32_t)st;
                                 if (t < bc) { bc = t; bn = 1; bk = key; atomicMin(&s_bound, t); }
                                 else if (t == bc) { bn++; bk = min(bk, key); }
                             }
                         }
                     } else {
-                        const uint32_t h = gg - P.g_pre;
+                        const uint32_t hh = gg - P.g_pre;
                         if (gmn + gfmin > *(volatile int *)&s_bound) continue;
-                        const uint32_t p1 = __ldg(P.suf_start + h + 1);
-                        for (uint32_t p = __ldg(P.suf_start + h) + lane; p < p1; p += 32) {
-                            const uint32_t g = __ldg(P.sent_pre + p);
-                            const int fm = mins[g];
+                        const uint32_t p0 = __ldg(P.suf_start + hh) + off, p1 = __ldg(P.suf_start + hh + 1);
+                        uint32_t gq[NR_DEEP_ITEM / 32];
+#pragma unroll
+                        for (int u = 0; u < NR_DEEP_ITEM / 32; u++)
+                            gq[u] = p0 + 32 * u < p1 ? __ldg(P.sent_pre + p0 + 32 * u) : 0xFFFFFFFFu;
+#pragma unroll
+                        for (int u = 0; u < NR_DEEP_ITEM / 32; u++) {
+                            if (gq[u] == 0xFFFFFFFFu) continue;
+                            const int fm = mins[gq[u]];
                             const int bound = *(volatile int *)&s_bound;
                             if (fm <= A || fm + gmn > bound) continue;   // fm <= A: the prefix side has it
                             uint64_t f[K + 1];
 #pragma unroll
-                            for (int e = 0; e <= K; e++) f[e] = plane_ld<SMEM>(planes + (size_t)e * G + g);
+                            for (int e = 0; e <= K; e++) f[e] = plane_ld<SMEM>(planes + (size_t)e * G + gq[u]);
                             const int t = nr_deep_join<K>(f, own);
                             if (t <= bound) {
-                                const uint32_t key = (__ldg(P.sent_idx + p) << 1) | (uint32_t)st;
+                                const uint32_t key = (__ldg(P.sent_idx + p0 + 32 * u) << 1) | (uint32_t)st;
                                 if (t < bc) { bc = t; bn = 1; bk = key; atomicMin(&s_bound, t); }
                                 else if (t == bc) { bn++; bk = min(bk, key); }
                             }
                         }
                     }
                 }
+                __syncthreads();        // every warp is done with this window's list and counters
             }
         }
 
@@ -308,14 +358,74 @@ nr_match_deep_kernel(const nr_deep_params P)
                 else if (s_rc[w] == c) { n += s_rn[w]; k = min(k, s_rk[w]); }
             }
             if (c <= K) {
-                Best r; r.score = P.L - c; r.cnt = n; r.key = k;
-                write_result(r, cand, m, cf, P.lo, P.hi, P.nm, P.L, P.padL, P.padR, P.min_score,
-                             P.o_idx, P.o_score, P.o_nbest, P.o_flags, P.o_umi);
+                // the UMI column of a forward-strand winner is left to nr_deep_finalize_kernel (one
+                // thread per candidate): a scalar pair DP here would hold the whole block
+                const int score = P.L - c;
+                const int strand = (int)(k & 1u);
+                uint8_t fl = NR_FLAG_EXHAUSTIVE;
+                if (n > 1) fl |= NR_FLAG_TIE;
+                if (strand) fl |= NR_FLAG_RC | NR_FLAG_NO_UMI;
+                if (score < P.min_score) fl |= NR_FLAG_BELOW;
+                P.o_idx[cand] = (int32_t)(k >> 1);
+                P.o_score[cand] = (int8_t)score;
+                P.o_nbest[cand] = (uint8_t)min(n, 255u);
+                P.o_flags[cand] = fl;
+                P.o_umi[cand] = strand ? NR_UMI_NONE : NR_UMI_PENDING;
                 if (P.resolved) atomicAdd(P.resolved, 1ull);
             } else {
                 P.next_list[atomicAdd(P.next_count, 1u)] = (uint32_t)cand;
             }
         }
+    }
+}
+
+// UMI columns of the candidates the deep tier resolved on the forward strand: thread = candidate,
+// the plane automaton over the winner's L columns (nr_deep_umi_row), K = 5 planes cover every cost
+// the tier reports.
+__global__ void __launch_bounds__(256)
+nr_deep_finalize_kernel(const uint4 *__restrict__ bases, const uint8_t *__restrict__ meta,
+                        const uint64_t *__restrict__ nmask, const uint32_t *__restrict__ list,
+                        const uint32_t *__restrict__ list_count, uint64_t n_cand,
+                        const uint32_t *__restrict__ lo, const uint32_t *__restrict__ hi,
+                        const uint32_t *__restrict__ nm, int L, int padL, int padR,
+                        const int32_t *__restrict__ o_idx, const int8_t *__restrict__ o_score,
+                        uint8_t *__restrict__ o_flags, uint8_t *__restrict__ o_umi)
+{
+    const uint64_t total = list ? (uint64_t)*list_count : n_cand;
+    for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
+         it += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t cand = list ? (uint64_t)list[it] : it;
+        if (o_umi[cand] != NR_UMI_PENDING) continue;
+        const uint8_t mt = meta[cand];
+        const int m = mt & 0x7F;
+        const uint4 b4 = __ldg(bases + cand);
+        const uint32_t w[4] = {b4.x, b4.y, b4.z, b4.w};
+        const uint64_t len_mask = (1ull << m) - 1ull;                 // m <= 63 here
+        const uint64_t nmk = (mt & 0x80) ? (nmask[cand] & len_mask) : 0ull;
+        nr_deep_rows rows;
+#pragma unroll
+        for (uint32_t c = 0; c < 4; c++) {
+            uint64_t eq = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t x = ~(w[k] ^ (c * 0x55555555u));
+                uint32_t t = x & (x >> 1) & 0x55555555u;              // bit 2i: base i equals c
+                t = (t | (t >> 1)) & 0x33333333u;
+                t = (t | (t >> 2)) & 0x0F0F0F0Fu;
+                t = (t | (t >> 4)) & 0x00FF00FFu;
+                t = (t | (t >> 8)) & 0x0000FFFFu;
+                eq |= (uint64_t)t << (16 * k);
+            }
+            rows.eq[c] = (eq & len_mask & ~nmk) << 1;
+        }
+        rows.nrow = nmk << 1;
+        rows.valid = (m >= 63) ? ~0ull : ((1ull << (m + 1)) - 1ull);
+        rows.edge = 1ull;                                             // no end-overhang rule (T0)
+        const int32_t idx = o_idx[cand];
+        const int u = nr_deep_umi_row<5>(rows, lo[idx], hi ? hi[idx] : 0u, nm ? nm[idx] : 0u, L, m,
+                                         padL, padR, L - (int)o_score[cand]);
+        if (u < 0) { o_flags[cand] |= NR_FLAG_NO_UMI; o_umi[cand] = NR_UMI_NONE; }
+        else o_umi[cand] = (uint8_t)u;
     }
 }
 
@@ -325,7 +435,7 @@ size_t deep_planes_bytes(const nr_whitelist *wl, int K)
            (size_t)(K + 1) * sizeof(uint64_t);
 }
 
-constexpr size_t DEEP_SMEM_MAX = 227 * 1024 - 2048;    // dynamic budget next to ~1 KB static
+constexpr size_t DEEP_SMEM_MAX = 227 * 1024 - 18 * 1024;    // dynamic budget next to ~17 KB static
 
 // threads per block: every thread gets the same number of phase-A groups (to within one warp)
 unsigned deep_threads(size_t G)
@@ -428,4 +538,24 @@ int nr_launch_deep(const nr_whitelist *wl, int K, const void *d_bases, const uin
     if (K == 5) return launch_k<5>(wl, P, d_scratch, scratch_bytes, stream);
     nr_set_error("deep tier: K must be 3 or 5");
     return NR_EINVAL;
+}
+
+// UMI columns for everything the deep tier resolved among (d_list, d_list_count) -- or among all
+// n_cand candidates when d_list is null.  Runs after the last deep launch of a call.
+int nr_launch_deep_finalize(const nr_whitelist *wl, const void *d_bases, const uint8_t *d_meta,
+                            const uint64_t *d_nmask, const uint32_t *d_list,
+                            const uint32_t *d_list_count, uint64_t n_cand, const int32_t *d_idx,
+                            const int8_t *d_score, uint8_t *d_flags, uint8_t *d_umi,
+                            cudaStream_t stream)
+{
+    if (!d_list && n_cand == 0) return NR_OK;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
+    const uint64_t want = d_list ? (uint64_t)sms * 8 : (n_cand + 255) / 256;
+    const unsigned grid = (unsigned)(want < (uint64_t)sms * 8 ? (want ? want : 1) : (uint64_t)sms * 8);
+    nr_deep_finalize_kernel<<<grid, 256, 0, stream>>>(
+        (const uint4 *)d_bases, d_meta, d_nmask, d_list, d_list_count, n_cand, wl->d_lo, wl->d_hi,
+        wl->d_nm, (int)wl->L, (int)wl->pad_l, (int)wl->pad_r, d_idx, d_score, d_flags, d_umi);
+    NR_CHECK_CUDA(cudaGetLastError());
+    return NR_OK;
 }

@@ -107,6 +107,16 @@ void run(const nr_deep_index_host &ix, int padL, int padR, const uint8_t *cand,
 
 extern "C" {
 
+// UMI column of one pair by the plane automaton (cost c of the pair known, c <= 8)
+int nr_emul_deep_umi(const uint8_t *q, int m, uint32_t lo, uint32_t hi, uint32_t nm, int L, int padL,
+                     int padR, int c)
+{
+    nr_deep_rows rows;
+    nr_deep_rows_from_codes(q, m, rows);
+    rows.edge = 1ull;
+    return nr_deep_umi_row<8>(rows, lo, hi, nm, L, m, padL, padR, c);
+}
+
 // wl_lo / wl_hi / wl_nm: packed cores (hi, nm nullable).  cand: N x 64 codes (4 = N), clen: N.
 // took[i] = 0 when no (entry, strand) pair reaches cost <= K (or the read has no / too many
 // rows): the kernel hands those to the next tier.

@@ -142,3 +142,43 @@ def test_deep_real_737k_sample(oracle, emul):
     assert check(ref, out, cl, 16, 5, cands, wl) > 350
     assert info[1] < len(wl) and info[2] < len(wl)
     assert 0 < info[3] < info[0] and 0 < info[5] < info[1], info      # prefix side shares columns
+
+
+def test_umi_row_by_planes_equals_oracle_pair(oracle, emul):
+    """the deep tier's finaliser derives the UMI column from the plane automaton; the oracle's
+    pair DP (tier 1) is the definition."""
+    O = oracle
+    rng = np.random.default_rng(21)
+    n_checked = n_none = 0
+    for _ in range(6000):
+        L = int(rng.choice([16, 16, 32, 12]))
+        pad_l = int(rng.choice([30, 4, 16, 0, 2, 15]))
+        pad_r = int(rng.choice([40, 17, 28, 0, 3, 24]))
+        core = list(rs(rng, L))
+        if rng.random() < 0.2:
+            core[int(rng.integers(0, L))] = "N"
+        core = "".join(core)
+        mid = mutate(rng, core.replace("N", "A"), int(rng.integers(0, 5)))
+        pre, suf = rs(rng, int(rng.integers(0, 36))), rs(rng, int(rng.integers(0, 30)))
+        mode = rng.integers(0, 6)
+        q = (mid[int(rng.integers(1, 4)):] + suf) if mode == 0 else \
+            (pre + mid[:-int(rng.integers(1, 4))]) if mode == 1 else (pre + mid + suf)
+        q = list(q[:63])
+        if not q:
+            continue
+        if rng.random() < 0.15:
+            q[int(rng.integers(0, len(q)))] = "N"
+        q = "".join(q)
+        a1, u1 = O.pair(q, core, pad_l, pad_r)
+        c = L - a1
+        if c > 8:
+            continue
+        wlc, _ = O.encode_many([core], L)
+        lo, hi, nm = pack_cores(wlc)
+        qc = np.ascontiguousarray(O.encode(q))
+        u = emul.nr_emul_deep_umi(P(qc, C.c_uint8), len(qc), int(lo[0]), int(hi[0]), int(nm[0]), L,
+                                  pad_l, pad_r, int(c))
+        assert u == u1, (q, core, pad_l, pad_r, a1, u1, u)
+        n_checked += 1
+        n_none += u1 < 0
+    assert n_checked > 2500 and n_none > 50
