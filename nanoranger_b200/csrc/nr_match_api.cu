@@ -2,6 +2,7 @@
 // (chunked, double-buffered H2D -> pack -> match -> D2H) and the workspace/counter helpers.
 // Replaces scripts/barcode_align.sh:14-41 of the reference (see include/nanoranger_b200.h).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -298,9 +299,18 @@ struct HostCtx {
 void staged_copy(void *dst, const void *src, size_t n)
 {
     constexpr size_t MIN_PER_THREAD = 4u << 20;
-    unsigned hw = std::thread::hardware_concurrency();
+    // host threads this process may use for staging: its share of the cores when several ranks
+    // run on one box (torchrun exports LOCAL_WORLD_SIZE), never more than 6
+    static const size_t budget = [] {
+        unsigned hw = std::thread::hardware_concurrency();
+        size_t share = hw ? hw : 1;
+        const char *lws = getenv("LOCAL_WORLD_SIZE");
+        const long ranks = lws ? atol(lws) : 1;
+        if (ranks > 1) share = std::max<size_t>(1, share / (size_t)ranks);
+        return std::min<size_t>(share, 6);
+    }();
     size_t want = n / MIN_PER_THREAD;
-    size_t nt = std::min<size_t>(std::min<size_t>(want, hw ? hw : 1), 6);
+    size_t nt = std::min<size_t>(want, budget);
     if (nt <= 1) { memcpy(dst, src, n); return; }
     std::vector<std::thread> th;
     size_t per = (n + nt - 1) / nt;

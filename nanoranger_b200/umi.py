@@ -95,17 +95,24 @@ def partition_records(bc, gene, umi, world: int):
 def exchange_records(rec_t, send_counts, group=None):
     """One variable-count all-to-all of (bc, gene, umi[, src]) records (torch int32 [n,3|4] on the
     process group's device: NCCL over NVLink on GPUs, gloo in the CPU tests).
-    -> received records [m,3]."""
+    send_counts: per-destination row counts, a list / array on the host or -- as
+    partition_device returns them -- an int64 tensor on the device.  The split sizes both
+    directions need come from ONE all-gather of the counts (world x world matrix) and one read of
+    it on the host; the record exchange itself is a single all_to_all_single.
+    -> received records [m,3|4]."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    sc = torch.as_tensor(send_counts, dtype=torch.int64, device=rec_t.device)
-    rc = torch.empty(world, dtype=torch.int64, device=rec_t.device)
-    dist.all_to_all_single(rc, sc, group=group)
-    rcl = [int(x) for x in rc.tolist()]
-    out = torch.empty((sum(rcl), rec_t.shape[1]), dtype=rec_t.dtype, device=rec_t.device)
-    dist.all_to_all_single(out, rec_t.contiguous(), output_split_sizes=rcl,
-                           input_split_sizes=[int(x) for x in send_counts], group=group)
+    rank = dist.get_rank(group)
+    sc = torch.as_tensor(send_counts, dtype=torch.int64).to(rec_t.device).contiguous()
+    allc = torch.empty(world * world, dtype=torch.int64, device=rec_t.device)
+    dist.all_gather_into_tensor(allc, sc, group=group)
+    m = allc.view(world, world).tolist()               # the only host synchronisation
+    send = [int(x) for x in m[rank]]
+    recv = [int(m[r][rank]) for r in range(world)]
+    out = torch.empty((sum(recv), rec_t.shape[1]), dtype=rec_t.dtype, device=rec_t.device)
+    dist.all_to_all_single(out, rec_t[:sum(send)].contiguous(), output_split_sizes=recv,
+                           input_split_sizes=send, group=group)
     return out
 
 
@@ -147,7 +154,8 @@ def records_device(bases, meta, nmask, res, min_score: int, umi_len: int, gene=N
 
 def partition_device(d_bc, d_gene, d_umi, world: int, d_src=None):
     """Device records -> ([n,4] int32 rows (bc, gene, umi, src) ordered by owner rank,
-    send_counts list[world]).  Same owner hash as owner_rank()."""
+    send_counts int64 tensor [world] ON THE DEVICE: no host synchronisation here).  Same owner
+    hash as owner_rank()."""
     import torch
     n = d_bc.numel()
     dev = d_bc.device
@@ -161,7 +169,7 @@ def partition_device(d_bc, d_gene, d_umi, world: int, d_src=None):
             d_bc.data_ptr(), d_gene.data_ptr() if d_gene is not None else None, d_umi.data_ptr(),
             d_src.data_ptr() if d_src is not None else None, n, world, rows.data_ptr(),
             counts.data_ptr(), cursor.data_ptr(), st), "nr_umi_partition_device")
-    return rows[:n], [int(x) for x in counts.tolist()]
+    return rows[:n], counts
 
 
 def unzip_device(rows):

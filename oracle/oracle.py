@@ -215,3 +215,69 @@ def hw_search_numpy(query: str, target: str, k: int, wildcard: bool = True) -> d
     es = sorted(ends)
     return {"editDistance": best, "n_locations": len(es), "first": (ends[es[0]], es[0]),
             "last": (ends[es[-1]], es[-1])}
+
+
+# ---------------------------------------------------------------------------------------
+# CPU build of the GPU path's own algorithm (nr_filter_cpu.cpp): bench baseline "port-filtered".
+
+_fc = None
+
+
+def filter_cpu_lib():
+    global _fc
+    if _fc is None:
+        so = os.path.join(_HERE, "libnr_filter_cpu.so")
+        src = os.path.join(_HERE, "nr_filter_cpu.cpp")
+        hdr = os.path.join(_HERE, "..", "nanoranger_b200", "csrc", "nr_filter_core.h")
+        if not os.path.exists(so) or (os.path.exists(src) and os.path.exists(hdr) and
+                                      os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr))):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libnr_filter_cpu.so"])
+        L = C.CDLL(so)
+        L.nr_cpu_filter_create.restype = C.c_void_p
+        L.nr_cpu_filter_create.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int]
+        L.nr_cpu_filter_destroy.argtypes = [C.c_void_p]
+        L.nr_cpu_filter_match.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int] + \
+            [C.c_void_p] * 6
+        L.nr_cpu_filter_match.restype = C.c_int
+        _fc = L
+    return _fc
+
+
+class FilterCPU:
+    """the seed filter on the host cores, 16-column N-free whitelists."""
+
+    def __init__(self, wl_codes: np.ndarray, pad_l: int, pad_r: int):
+        wl_codes = np.ascontiguousarray(wl_codes, dtype=np.uint8)
+        assert wl_codes.shape[1] == 16 and (wl_codes < 4).all()
+        lo = np.zeros(len(wl_codes), np.uint32)
+        for j in range(16):
+            lo |= wl_codes[:, j].astype(np.uint32) << np.uint32(2 * j)
+        self._lo = lo
+        self._h = filter_cpu_lib().nr_cpu_filter_create(lo.ctypes.data, len(lo), pad_l, pad_r)
+
+    def match(self, cand_codes, cand_len, threads=None, min_len=24):
+        cand = np.full((len(cand_codes), 64), 4, dtype=np.uint8)
+        cand[:, : cand_codes.shape[1]] = cand_codes
+        clen = np.ascontiguousarray(cand_len, dtype=np.uint8)
+        N = len(clen)
+        out = dict(best_idx=np.full(N, -1, np.int32), best_score=np.zeros(N, np.int8),
+                   n_best=np.zeros(N, np.int32), strand=np.zeros(N, np.uint8),
+                   umi_q=np.full(N, -1, np.int16), took=np.zeros(N, np.uint8))
+        rc = filter_cpu_lib().nr_cpu_filter_match(
+            self._h, cand.ctypes.data, clen.ctypes.data, N, min_len, threads or os.cpu_count() or 1,
+            out["best_idx"].ctypes.data, out["best_score"].ctypes.data, out["n_best"].ctypes.data,
+            out["strand"].ctypes.data, out["umi_q"].ctypes.data, out["took"].ctypes.data)
+        if rc != 0:
+            raise ValueError("nr_cpu_filter_match: bad arguments")
+        return out
+
+    def close(self):
+        if self._h:
+            filter_cpu_lib().nr_cpu_filter_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -24,6 +24,12 @@ def test_reference_arm_json_line():
     assert d["e2e"] == {"value": d["value"], "unit": "candidates/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("synthetic-ont6pct-5p-flanks-vs-737K")
+    # the STAR harness ran (no STAR in the image: it must say so, literally)
+    assert d["star_concordance"]["status"] == "STAR absent — concordance not measured"
+    assert d["config"]["star_binary"] == "absent"
+    # the like-for-like CPU figure: the GPU path's own algorithm on the host cores
+    f = d["cpu_baseline_filtered"]
+    assert f["kind"] == "port-filtered" and f["value"] > 10 * d["value"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():

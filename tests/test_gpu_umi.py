@@ -123,7 +123,7 @@ def test_partition_by_owner(cuda_device, world):
     rows, counts = U.partition_device(t[0], t[1], t[2], world)
     rows = rows.cpu().numpy().view(np.uint32)
     own = U.owner_rank(bc, world)
-    assert counts == np.bincount(own, minlength=world).tolist()
+    assert counts.tolist() == np.bincount(own, minlength=world).tolist()
     got_own = U.owner_rank(rows[:, 0], world)
     assert (np.diff(got_own) >= 0).all()                         # ordered by owner
     src = rows[:, 3].astype(np.int64)

@@ -143,3 +143,28 @@ def test_umi_cluster_oracle_basics(oracle):
     assert k1 == 3 and rep1[3] == u                             # 1-read neighbour joins the 3-read UMI
     assert rep1[5] == u and rep1[6] == u                        # 1 vs 1: 1 >= 2*1-1, joins the smaller UMI
     assert rep1[4] == 0xFFFF
+
+
+def test_cpu_filter_port_equals_exhaustive_oracle(oracle):
+    """oracle/nr_filter_cpu.cpp (the GPU path's algorithm on the host, bench baseline
+    "port-filtered") against the exhaustive scorer on the real 737K list."""
+    import time
+    from nanoranger_b200 import synth, whitelists
+    O = oracle
+    wl_a = whitelists.load_737k()
+    d = synth.make_candidates(wl_a, 1500, seed=9, p_n=0.004)
+    seqs = synth.to_strings(d["seqs"], d["offsets"])
+    cc, cl = O.encode_many(seqs, 64)
+    wlc = O._CODE[wl_a]
+    ref = O.match(wlc, 30, 40, cc, cl)
+    f = O.FilterCPU(wlc, 30, 40)
+    t = time.perf_counter()
+    out = f.match(cc, cl)
+    dt = time.perf_counter() - t
+    hi = (ref["best_score"] >= 14) & (out["took"] == 1)
+    assert hi.sum() > 1000
+    for k in ("best_idx", "best_score", "n_best", "strand", "umi_q"):
+        assert np.array_equal(out[k][hi], ref[k][hi]), k
+    lo = (ref["best_score"] < 14) & (out["took"] == 1)
+    assert (out["best_score"][lo] == -128).all()
+    assert dt < 30
