@@ -499,11 +499,12 @@ NR_HD uint64_t nr_rev_bits64(uint64_t x)
 }
 
 // Verification of one nominated (entry, strand) for a read with N (nm: N mask of the strand,
-// rdp: any substituted variant).  The diagonal walk of nr_verify16 runs with the N rows counted
-// as matches -- a lower bound on the true cost, so "nothing within cost 2" is exact -- and
-// whatever survives is scored by the N-aware automaton over the rows around the slot.
-NR_HD int nr_verify16n(const uint32_t *rdp, uint64_t nm, int m, uint32_t core, int padL, int padR,
-                       int p, const nr_probe_t &t, int *umi)
+// rdp: any substituted variant), in two halves so that the kernel can run the dear half on full
+// warps.  nr_prefilter16n: the diagonal walk of nr_verify16 with the N rows counted as matches --
+// a lower bound on the true cost, so "nothing within cost 2" is exact.  nr_score16n: the N-aware
+// automaton over the rows around the slot, for whatever survives.
+NR_HD bool nr_prefilter16n(const uint32_t *rdp, uint64_t nm, int m, uint32_t core, int p,
+                           const nr_probe_t &t)
 {
     const int fwd = t.drop != 0;
     const int pinned = fwd ? p : p + nr_probe_end(t);
@@ -518,8 +519,20 @@ NR_HD int nr_verify16n(const uint32_t *rdp, uint64_t nm, int m, uint32_t core, i
     else nt = (pinned >= 0 && pinned <= 63) ? (uint32_t)(nr_rev_bits64(nm) >> (63 - pinned))
                                             : (uint32_t)(nr_rev_bits64(nm) << (pinned - 63));
     vm &= ~nr_spread_even(nt);
-    if (!nr_lv16(V, vm, fwd ? core : nr_rev_bases32(core))) { *umi = -1; return 3; }
+    return nr_lv16(V, vm, fwd ? core : nr_rev_bases32(core)) != 0;
+}
+
+NR_HD int nr_score16n(const uint32_t *rdp, uint64_t nm, int m, uint32_t core, int padL, int padR,
+                      int p, int *umi)
+{
     const int r0 = nr_rows_first(p);
     return nr_nfa16n_w(nr_window64(rdp, r0), (uint32_t)(nm >> r0), m, core, padL, padR, r0,
                        nr_rows_last(p, m), umi);
+}
+
+NR_HD int nr_verify16n(const uint32_t *rdp, uint64_t nm, int m, uint32_t core, int padL, int padR,
+                       int p, const nr_probe_t &t, int *umi)
+{
+    if (!nr_prefilter16n(rdp, nm, m, core, p, t)) { *umi = -1; return 3; }
+    return nr_score16n(rdp, nm, m, core, padL, padR, p, umi);
 }

@@ -30,7 +30,7 @@ int nr_launch_deep(const nr_whitelist *wl, int K, const void *d_bases, const uin
                    uint8_t *d_nbest, uint8_t *d_flags, uint8_t *d_umi, uint32_t *d_next_list,
                    uint32_t *d_next_count, unsigned long long *d_work_next,
                    unsigned long long *d_resolved, uint8_t *d_scratch, size_t scratch_bytes,
-                   cudaStream_t stream);
+                   int small, cudaStream_t stream);
 int nr_launch_deep_finalize(const nr_whitelist *wl, const void *d_bases, const uint8_t *d_meta,
                             const uint64_t *d_nmask, const uint32_t *d_list,
                             const uint32_t *d_list_count, uint64_t n_cand, const int32_t *d_idx,
@@ -80,7 +80,7 @@ size_t deep_scratch(const nr_whitelist *wl)
 // list A (or every candidate when from_all) -> deep tier K = 3 -> K = 5 -> exhaustive DP kernel,
 // all on the stream, counts on the device
 int resolve_chain(const nr_whitelist *wl, const void *d_bases, const uint8_t *d_meta,
-                  const uint64_t *d_nmask, uint64_t n, int min_score, bool from_all,
+                  const uint64_t *d_nmask, uint64_t n, int min_score, bool from_all, bool few,
                   int32_t *d_idx, int8_t *d_score, uint8_t *d_nbest, uint8_t *d_flags,
                   uint8_t *d_umi_q, uint8_t *ws, size_t ws_bytes, int sms, cudaStream_t st)
 {
@@ -93,11 +93,11 @@ int resolve_chain(const nr_whitelist *wl, const void *d_bases, const uint8_t *d_
         const size_t sb = ws_bytes - NR_WS_HEADER - lists_bytes(n);
         int rc = nr_launch_deep(wl, 3, d_bases, d_meta, d_nmask, from_all ? nullptr : listA, cntA, n,
                                 min_score, d_idx, d_score, d_nbest, d_flags, d_umi_q, listB, cntB,
-                                (unsigned long long *)(ws + 88), ctr + 5, scratch, sb, st);
+                                (unsigned long long *)(ws + 88), ctr + 5, scratch, sb, few, st);
         if (rc != NR_OK) return rc;
         rc = nr_launch_deep(wl, 5, d_bases, d_meta, d_nmask, listB, cntB, n, min_score, d_idx,
                             d_score, d_nbest, d_flags, d_umi_q, listC, cntC,
-                            (unsigned long long *)(ws + 96), ctr + 6, scratch, sb, st);
+                            (unsigned long long *)(ws + 96), ctr + 6, scratch, sb, few, st);
         if (rc != NR_OK) return rc;
         rc = nr_launch_deep_finalize(wl, d_bases, d_meta, d_nmask, from_all ? nullptr : listA, cntA,
                                      n, d_idx, d_score, d_flags, d_umi_q, st);
@@ -174,7 +174,7 @@ extern "C" int nr_match_device(const nr_whitelist_t *wl, const void *d_bases,
     if (eff == NR_MODE_EXHAUSTIVE)
         // AUTO on a whitelist without a seed index (slide-seq cores, N columns): every candidate
         // through the deep tier, the brute-force kernel only for what it leaves
-        return resolve_chain(wl, d_bases, d_meta, d_nmask, n, min_score, true, d_idx, d_score,
+        return resolve_chain(wl, d_bases, d_meta, d_nmask, n, min_score, true, false, d_idx, d_score,
                              d_nbest, d_flags, d_umi_q, ws, workspace_bytes, sms, st);
     uint32_t *d_count = (uint32_t *)(ws + 64);
     uint32_t *d_list = (uint32_t *)(ws + NR_WS_HEADER);
@@ -185,9 +185,9 @@ extern "C" int nr_match_device(const nr_whitelist_t *wl, const void *d_bases,
                                 (unsigned long long *)(ws + 72), (unsigned long long *)(ws + 104),
                                 nullptr, &grid, st);
     if (rc != NR_OK) return rc;
-    // candidates the filter left (N, short, > 32 co-optimal pairs; in AUTO also everything below
-    // cost 2) are resolved exactly, counts read on the device
-    return resolve_chain(wl, d_bases, d_meta, d_nmask, n, min_score, false, d_idx, d_score,
+    // candidates the filter left (more than two N, short, > 32 co-optimal pairs; in AUTO also
+    // everything below cost 2) are resolved exactly, counts read on the device
+    return resolve_chain(wl, d_bases, d_meta, d_nmask, n, min_score, false, eff != NR_MODE_AUTO, d_idx, d_score,
                          d_nbest, d_flags, d_umi_q, ws, workspace_bytes, sms, st);
 }
 
@@ -217,7 +217,7 @@ extern "C" int nr_match_device_counted(const nr_whitelist_t *wl, const void *d_b
     if (rc != NR_OK) return rc;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
-    return resolve_chain(wl, d_bases, d_meta, d_nmask, n, min_score, false, d_idx, d_score,
+    return resolve_chain(wl, d_bases, d_meta, d_nmask, n, min_score, false, true, d_idx, d_score,
                          d_nbest, d_flags, d_umi_q, ws, workspace_bytes, sms, st);
 }
 

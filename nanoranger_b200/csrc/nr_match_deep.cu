@@ -447,23 +447,29 @@ unsigned deep_threads(size_t G)
     return (unsigned)t;
 }
 
+// small: the caller expects few candidates (the leftovers of NR_MODE_FILTERED).  The tier then runs
+// with its plane tables in global scratch and 256 threads per block, i.e. with the shared-memory
+// footprint of the filtered kernel: a launch that asks for > 100 KB of shared memory makes every
+// SM it lands on switch its L1/shared split, which serialises it against the filtered kernels of
+// the other chunks in flight (nr_match_host pipelines chunks over several streams).
 template <int K, bool WLN>
 int launch_kw(const nr_whitelist *wl, nr_deep_params &P, uint8_t *d_scratch, size_t scratch_bytes,
-              cudaStream_t stream)
+              bool small, cudaStream_t stream)
 {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
     const size_t G = (size_t)wl->deep_gpre + wl->deep_gsuf;
     const size_t pb = deep_planes_bytes(wl, K);
-    const unsigned threads = deep_threads(G);
-    if (pb + G <= DEEP_SMEM_MAX) {
+    const size_t per = (pb + 255) & ~(size_t)255;
+    const bool fits = pb + G <= DEEP_SMEM_MAX;
+    const bool have_scratch = d_scratch && scratch_bytes >= per;
+    if (fits && !(small && have_scratch)) {
         const size_t smem = pb + G;
         NR_CHECK_CUDA(cudaFuncSetAttribute(nr_match_deep_kernel<K, true, WLN>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nr_match_deep_kernel<K, true, WLN><<<sms, threads, smem, stream>>>(P);
+        nr_match_deep_kernel<K, true, WLN><<<sms, deep_threads(G), smem, stream>>>(P);
     } else {
-        const size_t per = (pb + 255) & ~(size_t)255;
-        size_t blocks = d_scratch ? scratch_bytes / per : 0;
+        size_t blocks = have_scratch ? scratch_bytes / per : 0;
         if (blocks > (size_t)sms) blocks = (size_t)sms;
         if (blocks == 0 || G > DEEP_SMEM_MAX) {
             nr_set_error("deep tier: no scratch for %zu groups", G);
@@ -473,7 +479,7 @@ int launch_kw(const nr_whitelist *wl, nr_deep_params &P, uint8_t *d_scratch, siz
         P.scratch_per_block = per;
         NR_CHECK_CUDA(cudaFuncSetAttribute(nr_match_deep_kernel<K, false, WLN>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G));
-        nr_match_deep_kernel<K, false, WLN><<<(unsigned)blocks, threads, G, stream>>>(P);
+        nr_match_deep_kernel<K, false, WLN><<<(unsigned)blocks, fits ? 256u : deep_threads(G), G, stream>>>(P);
     }
     NR_CHECK_CUDA(cudaGetLastError());
     return NR_OK;
@@ -481,21 +487,21 @@ int launch_kw(const nr_whitelist *wl, nr_deep_params &P, uint8_t *d_scratch, siz
 
 template <int K>
 int launch_k(const nr_whitelist *wl, nr_deep_params &P, uint8_t *d_scratch, size_t scratch_bytes,
-             cudaStream_t stream)
+             bool small, cudaStream_t stream)
 {
-    return wl->has_n ? launch_kw<K, true>(wl, P, d_scratch, scratch_bytes, stream)
-                     : launch_kw<K, false>(wl, P, d_scratch, scratch_bytes, stream);
+    return wl->has_n ? launch_kw<K, true>(wl, P, d_scratch, scratch_bytes, small, stream)
+                     : launch_kw<K, false>(wl, P, d_scratch, scratch_bytes, small, stream);
 }
 
 }  // namespace
 
-// global scratch one launch of the deep tier needs (0 when the plane tables fit shared memory)
+// global scratch one launch of the deep tier may use: the plane tables of one block per SM (the
+// only home of the tables when they do not fit shared memory; the small-footprint variant
+// otherwise)
 size_t nr_deep_scratch_bytes(const nr_whitelist *wl, int K)
 {
     if (!wl->has_deep) return 0;
-    const size_t G = (size_t)wl->deep_gpre + wl->deep_gsuf;
     const size_t pb = deep_planes_bytes(wl, K);
-    if (pb + G <= DEEP_SMEM_MAX) return 0;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
     return (size_t)sms * ((pb + 255) & ~(size_t)255);
@@ -516,7 +522,7 @@ int nr_launch_deep(const nr_whitelist *wl, int K, const void *d_bases, const uin
                    uint8_t *d_nbest, uint8_t *d_flags, uint8_t *d_umi, uint32_t *d_next_list,
                    uint32_t *d_next_count, unsigned long long *d_work_next,
                    unsigned long long *d_resolved, uint8_t *d_scratch, size_t scratch_bytes,
-                   cudaStream_t stream)
+                   int small, cudaStream_t stream)
 {
     if (!nr_deep_usable(wl)) { nr_set_error("deep tier not available for this whitelist"); return NR_EUNSUPPORTED; }
     if (!d_list && n_cand == 0) return NR_OK;
@@ -534,8 +540,8 @@ int nr_launch_deep(const nr_whitelist *wl, int K, const void *d_bases, const uin
     P.o_idx = d_idx; P.o_score = d_score; P.o_nbest = d_nbest; P.o_flags = d_flags; P.o_umi = d_umi;
     P.next_list = d_next_list; P.next_count = d_next_count; P.work_next = d_work_next;
     P.resolved = d_resolved; P.scratch = nullptr; P.scratch_per_block = 0;
-    if (K == 3) return launch_k<3>(wl, P, d_scratch, scratch_bytes, stream);
-    if (K == 5) return launch_k<5>(wl, P, d_scratch, scratch_bytes, stream);
+    if (K == 3) return launch_k<3>(wl, P, d_scratch, scratch_bytes, small != 0, stream);
+    if (K == 5) return launch_k<5>(wl, P, d_scratch, scratch_bytes, small != 0, stream);
     nr_set_error("deep tier: K must be 3 or 5");
     return NR_EINVAL;
 }

@@ -29,6 +29,7 @@
 // Candidates the filter cannot take (contain N, shorter than NR_FILTER_MIN_LEN, more than 32
 // co-optimal pairs) are appended to a device list that the exhaustive kernel resolves.
 #include <atomic>
+#include <type_traits>
 #include <utility>
 
 #include "nr_common.cuh"
@@ -40,6 +41,7 @@
 #define NR_FBLOCKS 4                       // resident blocks per SM the register budget is set for
 #endif
 #define NR_QCAP 480                        // queue slots per warp
+#define NR_VQCAP 64                        // N pass: rows waiting for the N-aware automaton, per warp
 
 struct nr_filter_params {
     const uint32_t *bits[4];      // key bitmap, 2^19 words per dropped quarter, contiguous:
@@ -100,8 +102,12 @@ struct WarpSmem {
     uint4 tile[32];                  // packed records of the warp's 32 candidates
     uint32_t rdp[2][NR_RDP_WORDS];   // candidate in flight: forward / reverse complement, padded
     uint32_t queue[NR_QCAP];         // bitmap hits waiting for verification: probe | strand | slot
-    uint64_t nm[2];                  // N pass: N mask of the candidate in flight, per strand
 };
+struct WarpSmemN : WarpSmem {        // the N pass carries more (kept out of the main pass: L1 space)
+    uint64_t nm[2];                  // N mask of the candidate in flight, per strand
+    uint4 vq[NR_VQCAP];              // rows that passed the wildcard walk: entry, core, strand | slot
+};
+template <bool NMODE> using WarpSmemT = std::conditional_t<NMODE, WarpSmemN, WarpSmem>;
 
 struct Acc {                 // running answer of the candidate in flight (warp-uniform unless noted)
     int best;                // best cost so far (3 = none)
@@ -110,6 +116,7 @@ struct Acc {                 // running answer of the candidate in flight (warp-
     int umi;                 // per lane: smallest leaving row of that pair, -1 none
     int overflow;            // more than 32 pairs at `best`
     int qn;                  // queued hits
+    int vn;                  // N pass: rows waiting in vq
     unsigned long long c_hits, c_ver, c_pass;   // per lane partial counters
 };
 
@@ -118,10 +125,63 @@ __device__ __constant__ nr_probe_t c_probes[NR_PROBES_ALL];
 
 __device__ __forceinline__ int merge_umi(int a, int b) { return a < 0 ? b : (b < 0 ? a : min(a, b)); }
 
+// fold one batch of verified rows (per lane: cost, pair, UMI row) into the running answer
+__device__ __forceinline__ void merge_batch(Acc &acc, int cost, uint32_t k, int u)
+{
+    const uint32_t lane = nr_lane();
+    const int rb = __reduce_min_sync(0xffffffffu, cost);
+    if (rb < 3 && rb <= acc.best) {
+        if (rb < acc.best) { acc.best = rb; acc.nb = 0; }
+        uint32_t contrib = __ballot_sync(0xffffffffu, cost == rb);
+        while (contrib) {
+            const int src = __ffs(contrib) - 1;
+            contrib &= contrib - 1;
+            const uint32_t kk = __shfl_sync(0xffffffffu, k, src);
+            const int uu = __shfl_sync(0xffffffffu, u, src);
+            const uint32_t found = __ballot_sync(0xffffffffu, (int)lane < acc.nb && acc.key == kk);
+            if (found) {
+                if ((int)lane == __ffs(found) - 1) acc.umi = merge_umi(acc.umi, uu);
+            } else if (acc.nb < 32) {
+                if ((int)lane == acc.nb) { acc.key = kk; acc.umi = uu; }
+                acc.nb++;
+            } else {
+                acc.overflow = 1;
+            }
+        }
+    }
+}
+
+// N pass: score up to 32 waiting rows with the N-aware automaton, one row per lane.  The automaton
+// costs ~800 instructions per row and only a lane or two of a verification batch survive the
+// wildcard walk: scoring them where they arise would run it at 2 active lanes (ncu), so survivors
+// are parked in vq and scored a full warp at a time.
+template <bool COUNT>
+__device__ __forceinline__ void flush_vq(const nr_filter_params &P, WarpSmemN &sm, Acc &acc, int m)
+{
+    const uint32_t lane = nr_lane();
+    while (acc.vn > 0) {
+        const int cnt = min(32, acc.vn);
+        const int base = acc.vn - cnt;
+        acc.vn = base;
+        int cost = 3, u = -1;
+        uint32_t k = 0;
+        if ((int)lane < cnt) {
+            const uint4 it = sm.vq[base + lane];
+            const int strand = (int)(it.z & 1u);
+            const int p = (int)(it.z >> 1) - 16;
+            cost = nr_score16n(sm.rdp[strand], sm.nm[strand], m, it.y, P.padL, P.padR, p, &u);
+            k = (it.x << 1) | (uint32_t)strand;
+            if (COUNT) acc.c_pass += cost < 3;
+        }
+        __syncwarp();
+        merge_batch(acc, cost, k, u);
+    }
+}
+
 // Take up to 32 queued bitmap hits, expand each into the index rows that share its key
 // (kstart gives first row and count), and verify the rows 32 at a time, one row per lane.
 template <bool COUNT, bool NMODE>
-__device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, Acc &acc, int m,
+__device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmemT<NMODE> &sm, Acc &acc, int m,
                                       const uint32_t *s_probes, const Tables &T4)
 {
     const uint32_t lane = nr_lane();
@@ -174,42 +234,37 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmem &sm, A
         const uint32_t o_excl = __shfl_sync(0xffffffffu, excl, lo);
         const uint32_t o_item = __shfl_sync(0xffffffffu, item, lo);
         int cost = 3, u = -1;
-        uint32_t k = 0;
+        uint32_t k = 0, vcore = 0, vwhere = 0;
         if (active) {
             const nr_probe_t ot = probe_unpack(s_probes[(o_item >> 16) & 63u]);
             const uint32_t od = (uint32_t)ot.drop;
             const int strand = (int)((o_item >> 24) & 1u);
             const int p = (int)(o_item >> 25) - 16;
             const uint2 e = __ldcg(T4.ents[od] + o_start + (g - o_excl));
-            if (NMODE) {
-                // reads with N: diagonal walk with the N rows as wildcards, then the N-aware
-                // automaton (sm.rdp holds a substituted variant; the N rows ignore their base)
-                cost = nr_verify16n(sm.rdp[strand], sm.nm[strand], m, e.y, P.padL, P.padR, p, ot, &u);
+            if constexpr (NMODE) {
+                // reads with N: diagonal walk with the N rows as wildcards here (sm.rdp holds a
+                // substituted variant; the N rows ignore their base), the N-aware automaton later
+                cost = nr_prefilter16n(sm.rdp[strand], sm.nm[strand], m, e.y, p, ot) ? 0 : 3;
+                vcore = e.y;
+                vwhere = (uint32_t)strand | ((uint32_t)(p + 16) << 1);
             } else {
                 cost = nr_verify16(sm.rdp[strand], m, e.y, P.padL, P.padR, p, ot, &u);
             }
             k = (e.x << 1) | (uint32_t)strand;
-            if (COUNT) { acc.c_ver++; acc.c_pass += cost < 3; }
+            if (COUNT) { acc.c_ver++; if (!NMODE) acc.c_pass += cost < 3; }
         }
-        const int rb = __reduce_min_sync(0xffffffffu, cost);
-        if (rb < 3 && rb <= acc.best) {
-            if (rb < acc.best) { acc.best = rb; acc.nb = 0; }
-            uint32_t contrib = __ballot_sync(0xffffffffu, cost == rb);
-            while (contrib) {
-                const int src = __ffs(contrib) - 1;
-                contrib &= contrib - 1;
-                const uint32_t kk = __shfl_sync(0xffffffffu, k, src);
-                const int uu = __shfl_sync(0xffffffffu, u, src);
-                const uint32_t found = __ballot_sync(0xffffffffu, (int)lane < acc.nb && acc.key == kk);
-                if (found) {
-                    if ((int)lane == __ffs(found) - 1) acc.umi = merge_umi(acc.umi, uu);
-                } else if (acc.nb < 32) {
-                    if ((int)lane == acc.nb) { acc.key = kk; acc.umi = uu; }
-                    acc.nb++;
-                } else {
-                    acc.overflow = 1;
-                }
+        if constexpr (NMODE) {
+            // park the survivors of the wildcard walk; score them a full warp at a time
+            const uint32_t bal = __ballot_sync(0xffffffffu, cost < 3);
+            if (bal) {
+                if (cost < 3)
+                    sm.vq[acc.vn + __popc(bal & ((1u << lane) - 1u))] = make_uint4(k >> 1, vcore, vwhere, 0u);
+                acc.vn += __popc(bal);
+                __syncwarp();
+                if (acc.vn > NR_VQCAP - 32) flush_vq<COUNT>(P, sm, acc, m);
             }
+        } else {
+            merge_batch(acc, cost, k, u);
         }
     }
 }
@@ -291,7 +346,7 @@ __device__ __forceinline__ uint64_t probe_range(const uint32_t *__restrict__ bit
 // Place the hits of one work item (per-lane probe mask at (strand, p)) in the warp's queue,
 // draining it as often as needed.
 template <bool COUNT, bool NMODE>
-__device__ __forceinline__ void enqueue(const nr_filter_params &P, WarpSmem &sm, Acc &acc, int m,
+__device__ __forceinline__ void enqueue(const nr_filter_params &P, WarpSmemT<NMODE> &sm, Acc &acc, int m,
                                         const uint32_t *s_probes, const Tables &T4, uint64_t mask,
                                         int strand, int p)
 {
@@ -346,7 +401,7 @@ __device__ __forceinline__ void enqueue(const nr_filter_params &P, WarpSmem &sm,
 // NMODE: the staged read is substituted variant `v`; slots that cannot reach a substituted N
 // position are skipped (nr_filter_core.h).
 template <bool COUNT, bool NMODE>
-__device__ __forceinline__ void run_stage(const nr_filter_params &P, WarpSmem &sm, Acc &acc, int m,
+__device__ __forceinline__ void run_stage(const nr_filter_params &P, WarpSmemT<NMODE> &sm, Acc &acc, int m,
                                           const uint32_t *s_probes, const Tables &s_tab,
                                           const uint32_t *__restrict__ bits_all, int stage, int p0,
                                           int nP, bool edge, int v, int n0, int n1,
@@ -420,7 +475,7 @@ template <bool COUNT, bool NMODE>
 __global__ void __launch_bounds__(NR_FWARPS * 32, NR_FBLOCKS)
 nr_match_filtered_kernel(const nr_filter_params P)
 {
-    __shared__ WarpSmem smem[NR_FWARPS];
+    __shared__ WarpSmemT<NMODE> smem[NR_FWARPS];
     __shared__ uint32_t s_probes[64];
     __shared__ Tables s_tab;
     if (threadIdx.x < 64)
@@ -432,11 +487,11 @@ nr_match_filtered_kernel(const nr_filter_params P)
     __syncthreads();
     const uint32_t lane = nr_lane();
     const int warp = threadIdx.x >> 5;
-    WarpSmem &sm = smem[warp];
+    WarpSmemT<NMODE> &sm = smem[warp];
     const uint32_t *__restrict__ bits_all = P.bits[0];
     // candidates per tile: the N pass gets few reads (a few per cent of the batch), each several
     // times dearer than a plain read: small tiles keep its tail short
-    constexpr uint32_t TS = NMODE ? 4u : 32u;
+    constexpr uint32_t TS = NMODE ? 2u : 32u;
     const uint64_t n_items = NMODE ? (uint64_t)*P.list_n_count : P.n_cand;
     const uint64_t n_tiles = (n_items + TS - 1) / TS;
     unsigned long long c_probes_n = 0, c_listed = 0;
@@ -500,13 +555,13 @@ nr_match_filtered_kernel(const nr_filter_params P)
                 if (P.list_n && !to_list) to_nlist = true; else to_list = true;
             }
             if (!to_list && !to_nlist) {
-                acc.best = 3; acc.nb = 0; acc.key = 0; acc.umi = -1; acc.overflow = 0; acc.qn = 0;
+                acc.best = 3; acc.nb = 0; acc.key = 0; acc.umi = -1; acc.overflow = 0; acc.qn = 0; acc.vn = 0;
                 const int p0 = nr_slot_first(m, P.padR), p1 = nr_slot_last(m, P.padL);
                 const int nP = p1 - p0 + 1;
                 const bool edge = p0 <= -1 && p1 >= -1;
                 const uint4 t4 = sm.tile[c];
                 const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
-                if (!NMODE) {
+                if constexpr (!NMODE) {
                     stage_read(sm, w4, m);
                     // Three stages over all slots, each drained before the next starts.  Prefixes of
                     // the probe table are complete for small costs (nr_filter_core.h): after stage 0
@@ -540,6 +595,9 @@ nr_match_filtered_kernel(const nr_filter_params P)
                             run_stage<COUNT, true>(P, sm, acc, m, s_probes, s_tab, bits_all, stage, p0,
                                                    nP, edge, v, n0, n1, c_probes_n);
                         }
+                        // the rows parked by all variants of the round (any variant's bases serve:
+                        // variants differ at the N rows only, and those ignore their base)
+                        flush_vq<COUNT>(P, sm, acc, m);
                     }
                 }
 
@@ -652,7 +710,8 @@ int nr_launch_filtered(const nr_whitelist *wl, const void *d_bases, const uint8_
         // the N pass: how many reads it gets is only known on the device; a grid sized for one
         // read in eight (far more than any real rate of N) exits at once where there is no tile
         P.tile_next = d_tile_next_n;
-        uint64_t want_n = (want + 7) / 8;
+        // (each of its reads is a latency chain of several probe stages: the more warps the better)
+        uint64_t want_n = (want + 1) / 2;
         unsigned grid_n = (unsigned)(want_n < cap ? (want_n ? want_n : 1) : cap);
         if (d_counters)
             nr_match_filtered_kernel<true, true><<<grid_n, NR_FWARPS * 32, 0, stream>>>(P);
