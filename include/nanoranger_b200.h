@@ -182,8 +182,10 @@ int nr_hw_search_host(const char *text, const uint64_t *offsets, uint64_t n, con
  * Replaces the output stage of scripts/barcode_align.sh:14-41: writes `path` with one record per
  * candidate whose best score is reached by exactly one (entry, strand) pair (STAR:
  * --outFilterMultimapNmax 1, --outSAMunmapped None, --outSAMmode NoQS), carrying the fields
- * utils.process_matching_* read: QNAME FLAG RNAME POS 255 CIGAR * 0 0 SEQ * NH HI AS.  POS/CIGAR
- * are anchored so that reference column pad_l + core_len pairs with read base umi_q.
+ * utils.process_matching_* read: QNAME FLAG RNAME POS 255 CIGAR * 0 0 SEQ * NH:i:1 HI:i:1 AS:i.
+ * This is the FAST form (opt-in): POS/CIGAR are anchored -- an ungapped M run placed so that
+ * reference column pad_l + core_len pairs with read base umi_q -- which is all the reference's
+ * own parser needs; nr_sam_write_aligned below writes real alignments and nM / MD.
  * names / seqs / ref_names: concatenated bytes with n + 1 (n_ref + 1) offsets.
  * header_full != 0: one @SQ per whitelist entry (STAR's layout), else only the entries used. */
 int nr_sam_write(const char *path, int header_full, const char *names, const uint64_t *name_off,
@@ -192,6 +194,21 @@ int nr_sam_write(const char *path, int header_full, const char *names, const uin
                  const uint8_t *umi_q, const char *ref_names, const uint64_t *ref_off,
                  uint64_t n_ref, uint32_t pad_l, uint32_t core_len, uint32_t pad_r,
                  uint64_t *n_written);
+
+/* The same file with REAL alignments: every kept record is traced back on the host (threads
+ * workers, 0 = all cores) against N^padL + core + N^padR of its entry; POS / CIGAR are that
+ * alignment (M, I, D; EndToEnd: no clipping), and the attributes are the ones
+ * scripts/barcode_align.sh:21 asks STAR for, in its order: AS:i nM:i MD:Z (nM = mismatches where
+ * both bases are ACGT; N on either side counts as a match in MD).  Among co-optimal alignments
+ * the one leaving the core at the smallest read row is reported, i.e. the pysam aligned_pairs
+ * lookup of utils.py:705-708 at reference column padL+L returns umi_q.  The traceback is checked
+ * against the matcher's score and umi_q; a disagreement fails the call. */
+int nr_sam_write_aligned(const nr_whitelist_t *wl, const char *path, int header_full,
+                         const char *names, const uint64_t *name_off, const char *seqs,
+                         const uint64_t *seq_off, uint64_t n, const int32_t *idx,
+                         const int8_t *score, const uint8_t *nbest, const uint8_t *flags,
+                         const uint8_t *umi_q, const char *ref_names, const uint64_t *ref_off,
+                         uint64_t n_ref, int threads, uint64_t *n_written);
 
 /* ---- measurement support -------------------------------------------------------------------
  * INT-pipe roofline denominator: runs a dependent LOP3/IADD3 chain on

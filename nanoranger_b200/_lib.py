@@ -36,7 +36,7 @@ SYMBOLS = (
     "nr_int_peak_dual", "nr_match_device_counted", "nr_match_counters",
     "nr_umi_records_device", "nr_umi_records_workspace_bytes", "nr_umi_partition_device",
     "nr_umi_unzip_device", "nr_hw_search_device", "nr_hw_search_host",
-    "nr_sam_write", "nr_match_tier_counts",
+    "nr_sam_write", "nr_match_tier_counts", "nr_sam_write_aligned",
 )
 
 _lib = None
@@ -99,6 +99,9 @@ def lib() -> C.CDLL:
     L.nr_sam_write.argtypes = [C.c_char_p, i32, vp, vp, vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, u64,
                                u32, u32, u32, C.POINTER(u64)]
     L.nr_sam_write.restype = i32
+    L.nr_sam_write_aligned.argtypes = [vp, C.c_char_p, i32, vp, vp, vp, vp, u64, vp, vp, vp, vp, vp, vp, vp,
+                                       u64, i32, C.POINTER(u64)]
+    L.nr_sam_write_aligned.restype = i32
     L.nr_int_peak.argtypes = [i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.nr_int_peak.restype = i32
     L.nr_int_peak_dual.argtypes = [i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]

@@ -34,6 +34,7 @@ struct nr_whitelist {
     uint32_t *d_lo;  // n
     uint32_t *d_hi;  // n (L > 16) or nullptr
     uint32_t *d_nm;  // n (has_n) or nullptr
+    uint32_t *h_lo, *h_hi, *h_nm;   // host copies (hi / nm nullable): the SAM writer's tracebacks
     // seed index: for j in 0..3 the 24-bit key made of the three 4-base quarters other than
     // quarter j.  bits[j][w] = bitmap word of keys 32w..32w+31, rank[j][w] = number of distinct
     // keys below 32w (2^19 + 1 words each); kstart[j][r] = first row of the r-th distinct key

@@ -203,6 +203,19 @@ extern "C" int nr_whitelist_create(const char *cores, uint64_t n, uint32_t core_
         }
         w->has_index = 1;
     }
+    {
+        // host copies for nr_sam_write_aligned (tracebacks of the kept records run on the host)
+        w->h_lo = (uint32_t *)malloc(nb);
+        if (core_len > 16) w->h_hi = (uint32_t *)malloc(nb);
+        if (has_n) w->h_nm = (uint32_t *)malloc(nb);
+        if (!w->h_lo || (core_len > 16 && !w->h_hi) || (has_n && !w->h_nm)) {
+            nr_set_error("out of host memory");
+            return fail(NR_ENOMEM);
+        }
+        memcpy(w->h_lo, lo.data(), nb);
+        if (w->h_hi) memcpy(w->h_hi, hi.data(), nb);
+        if (w->h_nm) memcpy(w->h_nm, nmv.data(), nb);
+    }
     if (core_len >= 2) {
         // deep tier: prefix / suffix grouping (host: two sorts of n keys)
         nr_deep_index_host ix;
@@ -259,6 +272,7 @@ extern "C" void nr_whitelist_destroy(nr_whitelist_t *w)
     cudaSetDevice(w->device);
     nr_host_ctx_destroy(w->host_ctx);
     cudaFree(w->d_lo); cudaFree(w->d_hi); cudaFree(w->d_nm);
+    free(w->h_lo); free(w->h_hi); free(w->h_nm);
     cudaFree(w->d_bits[0]);
     cudaFree(w->d_deep_pre_start); cudaFree(w->d_deep_pre_rep); cudaFree(w->d_deep_suf_rep);
     cudaFree(w->d_deep_ent_suf); cudaFree(w->d_deep_ent_idx);

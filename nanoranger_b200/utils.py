@@ -180,7 +180,7 @@ def match_records(wl: Whitelist, names, seqs, offsets, ref_names, mode=NR_MODE_A
 
 
 def barcode_align(input_fastq, genome_dir, out_name, threads=1, *ignored, device: int = 0,
-                  header: str = "used", mode=NR_MODE_AUTO):
+                  header: str = "used", mode=NR_MODE_AUTO, alignments: str = "traceback"):
     """scripts/barcode_align.sh <input.fa.gz> <genome_dir> <out_prefix> <threads> [ignored]:
     writes `<out_prefix>.sam`.  `threads` is accepted for call compatibility (the work runs on
     the GPU).
@@ -190,7 +190,12 @@ def barcode_align(input_fastq, genome_dir, out_name, threads=1, *ignored, device
     decide go through the deep tier (exact optimum over the whole whitelist), so the low-score
     tail of `_barcode_scores.csv` (utils.py:698, 728-730) is the oracle's.  NR_MODE_FILTERED is
     opt-in: it resolves exactly everything the reference keeps (AS >= core length - 2) and leaves
-    the rest out of the SAM."""
+    the rest out of the SAM.
+
+    alignments: "traceback" (default) writes real POS / CIGAR and the `AS nM MD` attributes
+    scripts/barcode_align.sh:21 asks STAR for (host tracebacks of the kept records, `threads`
+    workers, all cores when threads <= 1); "anchored" writes the fast form -- an ungapped M run
+    placed so that the reference's aligned_pairs lookup (utils.py:705-708) finds the same UMI."""
     import ctypes as C
     from . import _lib
     from ._lib import NR_MODE_FILTERED
@@ -205,12 +210,26 @@ def barcode_align(input_fastq, genome_dir, out_name, threads=1, *ignored, device
         if n == 0:
             nbuf = seqs = np.zeros(1, np.uint8)
         written = C.c_uint64(0)
-        _lib.check(_lib.lib().nr_sam_write(
-            f"{out_name}.sam".encode(), 1 if header == "full" else 0, nbuf.ctypes.data,
-            noff.ctypes.data, seqs.ctypes.data, offsets.ctypes.data, n, res.idx.ctypes.data,
-            res.score.ctypes.data, res.nbest.ctypes.data, res.flags.ctypes.data,
-            res.umi_q.ctypes.data, rbuf.ctypes.data, roff.ctypes.data, len(ref_names), wl.pad_l,
-            wl.core_len, wl.pad_r, C.byref(written)), "nr_sam_write")
+        if alignments == "traceback":
+            try:
+                nthr = int(threads)
+            except (TypeError, ValueError):
+                nthr = 0
+            _lib.check(_lib.lib().nr_sam_write_aligned(
+                wl.handle, f"{out_name}.sam".encode(), 1 if header == "full" else 0, nbuf.ctypes.data,
+                noff.ctypes.data, seqs.ctypes.data, offsets.ctypes.data, n, res.idx.ctypes.data,
+                res.score.ctypes.data, res.nbest.ctypes.data, res.flags.ctypes.data,
+                res.umi_q.ctypes.data, rbuf.ctypes.data, roff.ctypes.data, len(ref_names),
+                nthr if nthr > 1 else 0, C.byref(written)), "nr_sam_write_aligned")
+        elif alignments == "anchored":
+            _lib.check(_lib.lib().nr_sam_write(
+                f"{out_name}.sam".encode(), 1 if header == "full" else 0, nbuf.ctypes.data,
+                noff.ctypes.data, seqs.ctypes.data, offsets.ctypes.data, n, res.idx.ctypes.data,
+                res.score.ctypes.data, res.nbest.ctypes.data, res.flags.ctypes.data,
+                res.umi_q.ctypes.data, rbuf.ctypes.data, roff.ctypes.data, len(ref_names), wl.pad_l,
+                wl.core_len, wl.pad_r, C.byref(written)), "nr_sam_write")
+        else:
+            raise ValueError(f"alignments must be 'traceback' or 'anchored', not {alignments!r}")
         n = int(written.value)
     finally:
         wl.close()

@@ -126,3 +126,109 @@ def test_pipeline_5p10X_tags(cuda_device, tmp_path):
         assert (bamio.get_tag(r, "CB"), bamio.get_tag(r, "UB"), bamio.get_tag(r, "XT")) == (b, u, t)
     ct = pd.read_csv(f"{out}/s_trns_ct.csv")
     assert ct.iloc[0, 0] == "lite" and int(ct.iloc[0, 1]) == len(want)
+
+
+# ---- real alignments in the SAM (nr_sam_write_aligned) ---------------------------------------------
+
+def _walk(pos, cigar, seq, ref):
+    """pysam-style aligned pairs + score / mismatches / MD recomputed from POS, CIGAR, SEQ and the
+    padded reference (the scoring of scripts/barcode_align.sh:18-33)."""
+    import re
+    r, q = pos - 1, 0
+    pairs, score, nm, md, run, in_del = {}, 0, 0, "", 0, False
+    for n, op in re.findall(r"(\d+)([MID])", cigar):
+        n = int(n)
+        if op == "M":
+            for _ in range(n):
+                a, b = seq[q], ref[r]
+                pairs[r] = q
+                if a == "N" or b == "N":
+                    run += 1
+                elif a == b:
+                    score += 1
+                    run += 1
+                else:
+                    score -= 1
+                    nm += 1
+                    md += f"{run}{b}"
+                    run = 0
+                r += 1
+                q += 1
+            in_del = False
+        elif op == "I":
+            score -= n
+            q += n
+        else:
+            score -= n
+            md += f"{run}^" + ref[r:r + n]
+            run = 0
+            r += n
+    md += str(run)
+    return pairs, score, nm, md, q, r
+
+
+def _check_sam(path, names, ref, ref_strs, pad_l, L, pad_r):
+    from nanoranger_b200 import samio
+    by_name = {n: i for i, n in enumerate(names)}
+    n_fwd = n_rev = n_gapped = 0
+    with open(path) as f:
+        for ln in f:
+            if ln.startswith("@"):
+                continue
+            t = ln.rstrip("\n").split("\t")
+            i = by_name[t[0]]
+            assert ref["n_best"][i] == 1
+            tags = t[11:]
+            assert [x[:5] for x in tags] == ["AS:i:", "nM:i:", "MD:Z:"], tags      # barcode_align.sh:21
+            a_s, n_m, md = int(tags[0][5:]), int(tags[1][5:]), tags[2][5:]
+            flag, rname, pos, cigar, seq = int(t[1]), t[2], int(t[3]), t[5], t[9]
+            core = ref_strs[ref["best_idx"][i]]
+            padded = "N" * pad_l + core + "N" * pad_r
+            pairs, score, nm, md2, qlen, rend = _walk(pos, cigar, seq, padded)
+            assert qlen == len(seq) and rend <= len(padded)                 # EndToEnd, inside the chromosome
+            assert score == a_s == int(ref["best_score"][i]), (t[0], cigar, score, a_s)
+            assert nm == n_m and md2 == md, (t[0], cigar, md, md2)
+            assert (flag == 16) == (ref["strand"][i] == 1)
+            n_gapped += ("I" in cigar) or ("D" in cigar)
+            if flag == 0:
+                # utils.py:705-708: query index paired with reference column padL+L
+                u = pairs.get(pad_l + L, -1)
+                assert u == int(ref["umi_q"][i]), (t[0], cigar, u, ref["umi_q"][i])
+                assert samio.query_index_at(pos, cigar, pad_l + L) == (None if u < 0 else u)
+                n_fwd += 1
+            else:
+                n_rev += 1
+    return n_fwd, n_rev, n_gapped
+
+
+def test_sam_records_are_real_alignments_tcr3(cuda_device, tmp_path):
+    from nanoranger_b200 import utils, whitelists
+    names, seqs, off, ref = _load("tcr3")
+    out = str(tmp_path)
+    wl_a = whitelists.load_737k()
+    wl_names = whitelists.ascii_to_strings(wl_a)
+    np.savez_compressed(f"{out}/nr_whitelist.npz", cores=wl_a, names=np.array(wl_names), pad_l=30, pad_r=40)
+    n = utils.barcode_align(os.path.join(G, "tcr3.fa.gz"), out, f"{out}/t_matching", 4)
+    assert n == int((ref["n_best"] == 1).sum())
+    n_fwd, n_rev, n_gapped = _check_sam(f"{out}/t_matching.sam", names, ref, wl_names, 30, 16, 40)
+    assert n_fwd > 1500 and n_rev > 10 and n_gapped > 100
+    # the anchored (fast) form stays available and yields the same UMI lookups
+    n2 = utils.barcode_align(os.path.join(G, "tcr3.fa.gz"), out, f"{out}/a_matching", 4, alignments="anchored")
+    assert n2 == n
+
+
+def test_sam_records_are_real_alignments_slideseq(cuda_device, tmp_path):
+    """32-column cores with N columns, pads 15/24 (utils.py:584-601)."""
+    from nanoranger_b200 import utils
+    from nanoranger_b200.whitelists import LINKER_SLIDESEQ
+    names, seqs, off, ref = _load("slideseq")
+    out = str(tmp_path)
+    bcs = gzip.open(os.path.join(G, "slideseq_whitelist.txt.gz"), "rt").read().split()
+    cores = [b[:8] + LINKER_SLIDESEQ + b[8:] for b in bcs]
+    np.savez_compressed(f"{out}/nr_whitelist.npz",
+                        cores=np.frombuffer("".join(cores).encode(), np.uint8).reshape(len(cores), 32),
+                        names=np.array(bcs), pad_l=15, pad_r=24)
+    n = utils.barcode_align(os.path.join(G, "slideseq.fa.gz"), out, f"{out}/s_matching", 4)
+    assert n == int((ref["n_best"] == 1).sum())
+    n_fwd, n_rev, n_gapped = _check_sam(f"{out}/s_matching.sam", names, ref, cores, 15, 32, 24)
+    assert n_fwd > 500 and n_gapped > 50
