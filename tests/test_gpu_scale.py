@@ -152,3 +152,47 @@ def test_umi_collapse_properties_at_scale(batch):
     # idempotence: collapsing the representatives changes nothing
     r2 = U.collapse_device(rec["bc"], rec["gene"], r1["rep_umi"], 12, 0)
     assert r2["n_groups"] == r1["n_groups"] and torch.equal(r2["g_reads"], r1["g_reads"])
+
+
+def test_barcode_align_2M_candidates_every_score_exact(cuda_device, oracle, tmp_path):
+    """The reference-shaped call on an input far above the old 200 000-candidate switch: the
+    default mode resolves EVERY read, so each sampled read's SAM record (presence, flag, barcode,
+    AS) equals the oracle's at all AS values, and `_barcode_scores.csv` (utils.py:698, 728-730) is
+    the histogram of all uniquely mapped forward reads of the file."""
+    import gzip
+    import pandas as pd
+    from nanoranger_b200 import samio, synth, utils, whitelists
+    n, n_s = 2_000_000, 20_000
+    out = str(tmp_path)
+    wl_a = whitelists.load_737k()
+    wl_names = whitelists.ascii_to_strings(wl_a)
+    d = synth.make_candidates(wl_a, n, seed=77, p_n=1e-3, umi_len=10)
+    o = d["offsets"].astype(np.int64)
+    raw = d["seqs"].tobytes()
+    with gzip.open(f"{out}/s_BCUMI.fasta.gz", "wb", compresslevel=1) as f:
+        f.write(b"".join(b">r%d_0_0_0_t\n%s\n" % (i, raw[o[i]:o[i + 1]]) for i in range(n)))
+    np.savez_compressed(f"{out}/nr_whitelist.npz", cores=wl_a, names=np.array(wl_names), pad_l=30, pad_r=40)
+    written = utils.barcode_align(f"{out}/s_BCUMI.fasta.gz", out, f"{out}/s_matching", 16)
+    t = samio.read_sam_table(f"{out}/s_matching.sam")
+    assert written == len(t["qname"]) and written > 0.5 * n
+    # per read, on the sample
+    seqs = [raw[o[i]:o[i + 1]].decode() for i in range(n_s)]
+    cc, cl = oracle.encode_many(seqs, 64)
+    ref = oracle.match(oracle._CODE[wl_a], 30, 40, cc, cl)
+    rid = np.array([int(q[1:].split("_")[0]) for q in t["qname"]])
+    sel = rid < n_s
+    got = {int(r): (int(f), str(b), int(a)) for r, f, b, a in
+           zip(rid[sel], t["flag"][sel], t["rname"][sel], t["AS"][sel])}
+    exp = {i: (16 if ref["strand"][i] else 0, wl_names[ref["best_idx"][i]], int(ref["best_score"][i]))
+           for i in range(n_s) if ref["n_best"][i] == 1}
+    assert got == exp
+    assert min(a for _, _, a in exp.values()) < 14             # the low-score tail is really there
+    # the file the reference writes from those records
+    utils.process_matching_5p10X("s", out)
+    sc = pd.read_csv(f"{out}/s_barcode_scores.csv")
+    fwd = t["AS"][t["flag"] == 0]
+    v, c = np.unique(fwd, return_counts=True)
+    assert dict(zip(sc.score.tolist(), sc["count"].tolist())) == dict(zip(v.tolist(), c.tolist()))
+    # (most sub-threshold reads tie between several barcodes and are absent, as in STAR's output;
+    #  the unique ones are the tail of the histogram)
+    assert (v < 14).any() and c[v < 14].sum() > 1000
