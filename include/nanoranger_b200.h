@@ -122,6 +122,9 @@ void nr_host_free(void *p);
  * (barcode idx, gene id, 2-bit packed UMI) are sorted by (barcode, gene, umi); identical
  * records collapse (max_dist = 0: the reference's np.unique), and with max_dist = 1 distinct
  * UMIs of a (barcode, gene) group are merged by the directional one-hop rule.
+ * UMI words are compared on all 32 bits (a caller may use codes above bit 2 * umi_len as escape
+ * values for UMIs it cannot pack; with max_dist = 1 only bits below 2 * umi_len take part in the
+ * neighbour search).
  * Outputs (device, caller-allocated, n entries each unless noted):
  *   rep_umi[i]     representative UMI of the cluster record i belongs to
  *   n_groups[0]    number of (barcode, gene, cluster) groups

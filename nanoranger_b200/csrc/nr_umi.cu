@@ -430,8 +430,9 @@ extern "C" int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_ge
 
     k_init<<<nb, T, 0, st>>>(d_umi, n, w.umi_a, w.idx_a);
     size_t need = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, need, w.umi_a, w.umi_b, w.idx_a, w.idx_b, N, 0,
-                                    2 * umi_len, st);
+    // all 32 bits of the UMI word: a caller may carry escape codes above bit 2 * umi_len (the host
+    // path's N-containing UMIs), and equal words must end up adjacent whatever their width
+    cub::DeviceRadixSort::SortPairs(nullptr, need, w.umi_a, w.umi_b, w.idx_a, w.idx_b, N, 0, 32, st);
     size_t need2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, need2, w.key_a, w.key_b, w.idx_b, w.idx_a, N, 0, 64, st);
     size_t need3 = 0;
@@ -443,7 +444,7 @@ extern "C" int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_ge
     }
     size_t tb = w.cub_bytes;
     NR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.umi_a, w.umi_b, w.idx_a, w.idx_b,
-                                                  N, 0, 2 * umi_len, st));
+                                                  N, 0, 32, st));
     k_gather_key<<<nb, T, 0, st>>>(d_bc, d_gene, w.idx_b, n, w.key_a);
     tb = w.cub_bytes;
     NR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.key_a, w.key_b, w.idx_b, w.idx_a,

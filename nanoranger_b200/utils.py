@@ -95,7 +95,11 @@ def write_bc_3p10XTCR_nuc(sample, outdir, bc_file):
 
 def write_bc_3p10XGEX(sample, outdir, barcodes):
     """utils.py:1412-1458: sum `split/*bc_count.json`, keep raw 16-mers seen in > 20 reads that are
-    on the whitelist, N*4 + bc + N*17; also writes `{sample}_bc_read_count.csv`."""
+    on the whitelist, N*4 + bc + N*17.  File contract kept as the reference writes it:
+    `{sample}_bc_read_count.csv` is the pandas Series named `read_count` (barcode index, header
+    `,read_count`) in the insertion order of the aggregated counts (:1434-1436); the FASTA lists
+    the shared barcodes in that same order (:1446-1447); whitelist lines are taken verbatim -- no
+    suffix stripping here (:1442)."""
     out = f"{outdir}/{sample}_bcreads.fasta"
     if os.path.isfile(out):
         print(out, " exists, skip")
@@ -105,14 +109,14 @@ def write_bc_3p10XGEX(sample, outdir, barcodes):
     for fn in sorted(f for f in os.listdir(split) if f.endswith("bc_count.json")):
         with open(os.path.join(split, fn)) as fh:
             for k, v in json.load(fh).items():
-                agg[k] = agg.get(k, 0) + int(v)
-    df = pd.DataFrame({"bc": list(agg.keys()), "read_cnt": list(agg.values())})
-    df = df.sort_values(by="read_cnt", ascending=False, kind="stable")
-    df.to_csv(f"{outdir}/{sample}_bc_read_count.csv", index=None)
-    observed = set(df[df.read_cnt > 20].bc)
-    wl = _read_bc_table(barcodes).bc.apply(lambda x: x.split("-")[0])
-    bcs = [b for b in wl if b in observed]
-    _write_padded(out, bcs, bcs, 4, 17)
+                agg[k] = agg.get(k, 0) + v
+    read_cnt = pd.Series(agg, dtype="int64" if agg else "float64")
+    read_cnt.name = "read_count"
+    read_cnt.to_csv(f"{outdir}/{sample}_bc_read_count.csv")
+    raw_bcs = read_cnt[read_cnt > 20]
+    shared = set(_read_bc_table(barcodes)["bc"]) & set(raw_bcs.index)
+    bcs = list(raw_bcs[raw_bcs.index.isin(shared)].index)
+    _write_padded(out, bcs, bcs, 3 + 1, 12 + 4 + 1)
 
 
 # ---- barcode_ref.sh -------------------------------------------------------------------------------
@@ -285,8 +289,11 @@ def umi_dedup_table(bcs, umis, umi_len, device: int = 0):
         extra = {s: k for k, s in enumerate(sorted({umis[i] for i in np.flatnonzero(~ok)}))}
         for i in np.flatnonzero(~ok):
             codes[i] = np.uint32((1 << (2 * umi_len)) + extra[umis[i]])
-    r = U.collapse_host(inv.astype(np.uint32), np.zeros(len(inv), np.uint32), codes,
-                        min(16, umi_len + (0 if ok.all() else 1)), 0, device)
+    # (nr_umi_collapse_device sorts all 32 bits of the UMI word, so the escape codes need no
+    # widened umi_len; the device-resident records path, nr_umi_records_device, cannot carry such
+    # UMIs in 2 bit/base and counts them in its stats[2] instead -- the count matrix path therefore
+    # leaves N-containing UMIs out, this per-barcode table keeps them like the reference does)
+    r = U.collapse_host(inv.astype(np.uint32), np.zeros(len(inv), np.uint32), codes, umi_len, 0, device)
     umi_cnt = np.bincount(r["g_bc"].astype(np.int64), minlength=len(names))
     read_cnt = np.bincount(r["g_bc"].astype(np.int64), weights=r["g_reads"],
                            minlength=len(names)).astype(np.int64)

@@ -92,7 +92,29 @@ def test_write_bc_3p10XGEX(tmp_path):
     txt = open(tmp_path / "s_bcreads.fasta").read().split("\n")
     assert txt[0] == ">" + "A" * 16 and txt[1] == "NNNN" + "A" * 16 + "N" * 17     # 25 reads, listed
     assert txt[2] == ">" + "C" * 16 and len(txt) == 5                              # G*16 not whitelisted
-    assert os.path.exists(tmp_path / "s_bc_read_count.csv")
+    # byte-level: the pandas Series the reference writes (utils.py:1434-1436): barcode index, the
+    # column named read_count, insertion order of the aggregated dict
+    assert open(tmp_path / "s_bc_read_count.csv").read() == \
+        ",read_count\n" + "A" * 16 + ",25\n" + "C" * 16 + ",30\n" + "G" * 16 + ",50\n"
+
+
+def test_write_bc_3p10XGEX_order_and_verbatim_whitelist(tmp_path):
+    """FASTA order = order of the counts (not of the whitelist); whitelist lines are compared
+    verbatim (a `-1` suffix in the file makes nothing match, as in the reference: utils.py:1442-1447)."""
+    import json
+    from nanoranger_b200 import utils
+    os.makedirs(tmp_path / "split")
+    json.dump({"T" * 16: 40, "C" * 16: 30, "A" * 16: 21, "G" * 16: 20},
+              open(tmp_path / "split" / "part_1_bc_count.json", "w"))
+    wl = tmp_path / "3M.txt"
+    wl.write_text("A" * 16 + "\n" + "C" * 16 + "\n" + "T" * 16 + "\n" + "G" * 16 + "\n")
+    utils.write_bc_3p10XGEX("s", str(tmp_path), str(wl))
+    names = [ln[1:] for ln in open(tmp_path / "s_bcreads.fasta").read().split("\n") if ln.startswith(">")]
+    assert names == ["T" * 16, "C" * 16, "A" * 16]                 # > 20 reads, count order
+    os.remove(tmp_path / "s_bcreads.fasta")
+    wl.write_text("A" * 16 + "-1\n" + "C" * 16 + "-1\n")
+    utils.write_bc_3p10XGEX("s", str(tmp_path), str(wl))
+    assert open(tmp_path / "s_bcreads.fasta").read() == ""
 
 
 def test_sort_cnt_and_pack_umis():
