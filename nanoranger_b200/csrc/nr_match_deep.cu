@@ -437,13 +437,14 @@ size_t deep_planes_bytes(const nr_whitelist *wl, int K)
 
 constexpr size_t DEEP_SMEM_MAX = 227 * 1024 - 18 * 1024;    // dynamic budget next to ~17 KB static
 
-// threads per block: every thread gets the same number of phase-A groups (to within one warp)
-unsigned deep_threads(size_t G)
+// threads per block: every thread gets the same number of phase-A groups (to within one warp).
+// `cap` = 512 when two blocks fit an SM (they then hide each other's barriers and serial parts).
+unsigned deep_threads(size_t G, size_t cap)
 {
-    const size_t rounds = (G + NR_DEEP_MAXTHREADS - 1) / NR_DEEP_MAXTHREADS;
+    const size_t rounds = (G + cap - 1) / cap;
     size_t t = ((G + rounds - 1) / rounds + 31) & ~(size_t)31;
     if (t < 256) t = 256;
-    if (t > NR_DEEP_MAXTHREADS) t = NR_DEEP_MAXTHREADS;
+    if (t > cap) t = cap;
     return (unsigned)t;
 }
 
@@ -465,9 +466,12 @@ int launch_kw(const nr_whitelist *wl, nr_deep_params &P, uint8_t *d_scratch, siz
     const bool have_scratch = d_scratch && scratch_bytes >= per;
     if (fits && !(small && have_scratch)) {
         const size_t smem = pb + G;
+        // two resident blocks per SM when their tables fit side by side (static ~17 KB each)
+        const bool two = 2 * (smem + 18 * 1024) <= 227 * 1024;
         NR_CHECK_CUDA(cudaFuncSetAttribute(nr_match_deep_kernel<K, true, WLN>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nr_match_deep_kernel<K, true, WLN><<<sms, deep_threads(G), smem, stream>>>(P);
+        nr_match_deep_kernel<K, true, WLN><<<two ? 2 * sms : sms, deep_threads(G, two ? 512 : NR_DEEP_MAXTHREADS),
+                                             smem, stream>>>(P);
     } else {
         size_t blocks = have_scratch ? scratch_bytes / per : 0;
         if (blocks > (size_t)sms) blocks = (size_t)sms;
@@ -479,7 +483,8 @@ int launch_kw(const nr_whitelist *wl, nr_deep_params &P, uint8_t *d_scratch, siz
         P.scratch_per_block = per;
         NR_CHECK_CUDA(cudaFuncSetAttribute(nr_match_deep_kernel<K, false, WLN>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G));
-        nr_match_deep_kernel<K, false, WLN><<<(unsigned)blocks, fits ? 256u : deep_threads(G), G, stream>>>(P);
+        nr_match_deep_kernel<K, false, WLN><<<(unsigned)blocks, fits ? 256u : deep_threads(G, NR_DEEP_MAXTHREADS),
+                                              G, stream>>>(P);
     }
     NR_CHECK_CUDA(cudaGetLastError());
     return NR_OK;
