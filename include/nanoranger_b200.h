@@ -52,8 +52,8 @@ extern "C" {
                                  brute-force DP for the rest                                     */
 #define NR_MODE_EXHAUSTIVE 1  /* brute-force DP over every (entry, strand) pair                  */
 #define NR_MODE_FILTERED 2    /* lossless seed filter + exact verification; exact for
-                                 score >= min_score, requires L == 16, N-free whitelist and
-                                 min_score >= L - 2                                              */
+                                 score >= min_score; requires a seed index
+                                 (nr_whitelist_has_index) and min_score >= L - 2                 */
 
 typedef struct nr_whitelist nr_whitelist_t;
 
@@ -64,8 +64,10 @@ const char *nr_version(void);
  * Replaces scripts/barcode_ref.sh:11-18 (STAR --runMode genomeGenerate over the padded FASTA
  * written by utils.write_bc_*, utils.py:584-622, 1116-1132, 1412-1458).
  * cores: n * core_len ASCII bytes (ACGTN, row-major, no separators) -- the FASTA sequences
- * without their N pads; pad_l / pad_r are the pad lengths.  Builds the packed whitelist and,
- * when core_len == 16 and no entry contains N, the quarter-key seed index on `device`. */
+ * without their N pads; pad_l / pad_r are the pad lengths.  Builds the packed whitelist, the
+ * grouping the deep tier works on, and a seed index on `device`: the quarter-key index when
+ * core_len == 16 and no entry contains N (10x lists), the anchored index when the cores are
+ * 8 columns + a constant run of 12..28 columns + a tail (slide-seq: utils.py:584-601). */
 int nr_whitelist_create(const char *cores, uint64_t n, uint32_t core_len, uint32_t pad_l,
                         uint32_t pad_r, int device, nr_whitelist_t **out);
 void nr_whitelist_destroy(nr_whitelist_t *wl);

@@ -43,6 +43,12 @@ struct nr_whitelist {
     uint32_t *d_rank[4];
     uint2 *d_ents[4];
     uint32_t *d_kstart[4];
+    // anchored seed filter (nr_anchor_core.h): cores = 8 columns + constant linker + tail (slide-seq)
+    int has_anchor;
+    int anchor_lk;                // linker columns
+    uint64_t anchor_link;         // the linker, column k at bits 2k
+    uint32_t *d_anchor_start;     // 4^8 + 1: rows of every 8-mer in front of the linker
+    uint32_t *d_anchor_rows;      // entry indices grouped by that 8-mer (N columns expanded)
     // deep tier (nr_deep_core.h, nr_deep_index.h): entries grouped by their first deep_s columns
     // (prefix groups, runs of the sorted order) and by their last L - deep_s (suffix groups)
     int has_deep;

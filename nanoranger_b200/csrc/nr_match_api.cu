@@ -24,6 +24,11 @@ int nr_launch_filtered(const nr_whitelist *wl, const void *d_bases, const uint8_
                        unsigned long long *d_tile_next, unsigned long long *d_tile_next_n,
                        unsigned long long *d_counters, int *grid_out, cudaStream_t stream);
 
+int nr_launch_anchored(const nr_whitelist *wl, const void *d_bases, const uint8_t *d_meta,
+                       uint64_t n_cand, int min_score, int resolve_below, int32_t *d_idx,
+                       int8_t *d_score, uint8_t *d_nbest, uint8_t *d_flags, uint8_t *d_umi,
+                       uint32_t *d_list, uint32_t *d_list_count, unsigned long long *d_tile_next,
+                       unsigned long long *d_counters, cudaStream_t stream);
 int nr_launch_deep(const nr_whitelist *wl, int K, const void *d_bases, const uint8_t *d_meta,
                    const uint64_t *d_nmask, const uint32_t *d_list, const uint32_t *d_list_count,
                    uint64_t n_cand, int min_score, int32_t *d_idx, int8_t *d_score,
@@ -119,7 +124,7 @@ extern "C" size_t nr_match_workspace_bytes(const nr_whitelist_t *wl, uint64_t n,
 
 static int resolve_mode(const nr_whitelist *wl, int min_score, int mode)
 {
-    bool can_filter = wl->has_index && min_score >= (int)wl->L - 2;
+    bool can_filter = (wl->has_index || wl->has_anchor) && min_score >= (int)wl->L - 2;
     if (mode == NR_MODE_AUTO) return can_filter ? NR_MODE_AUTO : NR_MODE_EXHAUSTIVE;
     if (mode == NR_MODE_FILTERED && !can_filter) return -1;
     return mode;
@@ -144,7 +149,8 @@ extern "C" int nr_match_device(const nr_whitelist_t *wl, const void *d_bases,
     }
     int eff = resolve_mode(wl, min_score, mode);
     if (eff < 0) {
-        nr_set_error("NR_MODE_FILTERED needs a 16-column N-free whitelist and min_score >= %d",
+        nr_set_error("NR_MODE_FILTERED needs a whitelist with a seed index (16-column N-free cores, or "
+                     "8 + linker + tail cores) and min_score >= %d",
                      (int)wl->L - 2);
         return NR_EUNSUPPORTED;
     }
@@ -179,6 +185,14 @@ extern "C" int nr_match_device(const nr_whitelist_t *wl, const void *d_bases,
     uint32_t *d_count = (uint32_t *)(ws + 64);
     uint32_t *d_list = (uint32_t *)(ws + NR_WS_HEADER);
     int grid = 0;
+    if (wl->has_anchor) {
+        int rc = nr_launch_anchored(wl, d_bases, d_meta, n, min_score, eff == NR_MODE_AUTO ? 1 : 0, d_idx,
+                                    d_score, d_nbest, d_flags, d_umi_q, d_list, d_count,
+                                    (unsigned long long *)(ws + 72), nullptr, st);
+        if (rc != NR_OK) return rc;
+        return resolve_chain(wl, d_bases, d_meta, d_nmask, n, min_score, false, eff != NR_MODE_AUTO, d_idx,
+                             d_score, d_nbest, d_flags, d_umi_q, ws, workspace_bytes, sms, st);
+    }
     int rc = nr_launch_filtered(wl, d_bases, d_meta, d_nmask, n, min_score,
                                 eff == NR_MODE_AUTO ? 1 : 0, d_idx, d_score, d_nbest, d_flags,
                                 d_umi_q, d_list, d_count, d_list + 3 * n, (uint32_t *)(ws + 84),
@@ -209,14 +223,22 @@ extern "C" int nr_match_device_counted(const nr_whitelist_t *wl, const void *d_b
     uint8_t *ws = (uint8_t *)d_workspace;
     NR_CHECK_CUDA(cudaMemsetAsync(ws, 0, NR_WS_ZERO, st));
     uint32_t *listA = (uint32_t *)(ws + NR_WS_HEADER);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
+    if (wl->has_anchor) {
+        int rc = nr_launch_anchored(wl, d_bases, d_meta, n, min_score, 0, d_idx, d_score, d_nbest, d_flags,
+                                    d_umi_q, listA, (uint32_t *)(ws + 64), (unsigned long long *)(ws + 72),
+                                    (unsigned long long *)ws, st);
+        if (rc != NR_OK) return rc;
+        return resolve_chain(wl, d_bases, d_meta, d_nmask, n, min_score, false, true, d_idx, d_score,
+                             d_nbest, d_flags, d_umi_q, ws, workspace_bytes, sms, st);
+    }
     int rc = nr_launch_filtered(wl, d_bases, d_meta, d_nmask, n, min_score, 0, d_idx, d_score,
                                 d_nbest, d_flags, d_umi_q, listA, (uint32_t *)(ws + 64),
                                 listA + 3 * n, (uint32_t *)(ws + 84),
                                 (unsigned long long *)(ws + 72), (unsigned long long *)(ws + 104),
                                 (unsigned long long *)ws, nullptr, st);
     if (rc != NR_OK) return rc;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
     return resolve_chain(wl, d_bases, d_meta, d_nmask, n, min_score, false, true, d_idx, d_score,
                          d_nbest, d_flags, d_umi_q, ws, workspace_bytes, sms, st);
 }

@@ -15,6 +15,7 @@
 #include "nr_common.cuh"
 #include "nr_filter_core.h"
 #include "nr_deep_index.h"
+#include "nr_anchor_index.h"
 
 static thread_local char g_err[512] = "";
 
@@ -216,6 +217,25 @@ extern "C" int nr_whitelist_create(const char *cores, uint64_t n, uint32_t core_
         if (w->h_hi) memcpy(w->h_hi, hi.data(), nb);
         if (w->h_nm) memcpy(w->h_nm, nmv.data(), nb);
     }
+    if (!w->has_index) {
+        // anchored seed filter: cores with a constant middle (slide-seq: 8 + linker 18 + 6)
+        nr_anchor_index_host ax;
+        nr_anchor_index_build(lo.data(), core_len > 16 ? hi.data() : nullptr, has_n ? nmv.data() : nullptr,
+                              n, (int)core_len, ax);
+        if (ax.ok) {
+            const size_t b_st = ax.start.size() * 4, b_rw = ax.rows.size() * 4;
+            if (cudaMalloc(&w->d_anchor_start, b_st) != cudaSuccess ||
+                cudaMalloc(&w->d_anchor_rows, b_rw ? b_rw : 4) != cudaSuccess) {
+                nr_set_error("cudaMalloc anchored index");
+                return fail(NR_ENOMEM);
+            }
+            w->bytes += b_st + b_rw;
+            cudaMemcpy(w->d_anchor_start, ax.start.data(), b_st, cudaMemcpyHostToDevice);
+            if (b_rw) cudaMemcpy(w->d_anchor_rows, ax.rows.data(), b_rw, cudaMemcpyHostToDevice);
+            w->anchor_lk = ax.Lk; w->anchor_link = ax.link;
+            w->has_anchor = 1;
+        }
+    }
     if (core_len >= 2) {
         // deep tier: prefix / suffix grouping (host: two sorts of n keys)
         nr_deep_index_host ix;
@@ -274,6 +294,7 @@ extern "C" void nr_whitelist_destroy(nr_whitelist_t *w)
     cudaFree(w->d_lo); cudaFree(w->d_hi); cudaFree(w->d_nm);
     free(w->h_lo); free(w->h_hi); free(w->h_nm);
     cudaFree(w->d_bits[0]);
+    cudaFree(w->d_anchor_start); cudaFree(w->d_anchor_rows);
     cudaFree(w->d_deep_pre_start); cudaFree(w->d_deep_pre_rep); cudaFree(w->d_deep_suf_rep);
     cudaFree(w->d_deep_ent_suf); cudaFree(w->d_deep_ent_idx);
     cudaFree(w->d_deep_suf_start); cudaFree(w->d_deep_sent_pre); cudaFree(w->d_deep_sent_idx);
@@ -284,5 +305,5 @@ extern "C" void nr_whitelist_destroy(nr_whitelist_t *w)
 }
 
 extern "C" uint64_t nr_whitelist_size(const nr_whitelist_t *w) { return w ? w->n : 0; }
-extern "C" int nr_whitelist_has_index(const nr_whitelist_t *w) { return w ? w->has_index : 0; }
+extern "C" int nr_whitelist_has_index(const nr_whitelist_t *w) { return w ? (w->has_index || w->has_anchor) : 0; }
 extern "C" uint64_t nr_whitelist_device_bytes(const nr_whitelist_t *w) { return w ? w->bytes : 0; }

@@ -53,18 +53,17 @@ def test_auto_small_whitelists_all_tiers(cuda_device, oracle, pad_l, pad_r, qlen
 
 
 def test_auto_without_seed_index_goes_through_deep_tier(cuda_device, oracle):
-    """32-column slide-seq cores with N columns (utils.py:584-601): no seed index, AUTO = deep
-    tier over every candidate."""
+    """cores no seed filter covers (20 columns, N columns in some entries): no seed index, AUTO =
+    deep tier over every candidate."""
     from nanoranger_b200 import NR_MODE_AUTO, Whitelist
     rng = np.random.default_rng(9)
-    linker = "TCTTCAGCGTTCCCGAGA"
     bcs = set()
     while len(bcs) < 4000:
-        b = list(rs(rng, 14))
+        b = list(rs(rng, 20))
         if rng.random() < 0.15:
-            b[int(rng.integers(0, 14))] = "N"
+            b[int(rng.integers(0, 20))] = "N"
         bcs.add("".join(b))
-    wl_strs = [b[:8] + linker + b[8:] for b in sorted(bcs)]
+    wl_strs = sorted(bcs)
     seqs = []
     for _ in range(2000):
         core = wl_strs[int(rng.integers(0, len(wl_strs)))].replace("N", "ACGT"[int(rng.integers(0, 4))])
@@ -76,8 +75,8 @@ def test_auto_without_seed_index_goes_through_deep_tier(cuda_device, oracle):
     wl = Whitelist(wl_strs, 15, 24)
     assert not wl.has_index
     ref = _oracle(oracle, wl_strs, 15, 24, seqs)
-    res, ws = _run_device(wl, seqs, 30, NR_MODE_AUTO)
-    compare(ref, res, 30, exact_below=True, label="auto slide-seq")
+    res, ws = _run_device(wl, seqs, 18, NR_MODE_AUTO)
+    compare(ref, res, 18, exact_below=True, label="auto 20-column cores")
     t = wl.tier_counts(ws)
     assert t["deep_k3"] > 1000, t
 
