@@ -34,8 +34,8 @@ if ROOT not in sys.path:
 CELLS_PER_CANDIDATE_737K = 737280 * 16 * 50      # SURVEY.md section 8d "equivalent cell updates"
 # kernels one step launches (nr_pack_device + nr_match_device in NR_MODE_FILTERED), in stream order
 STEP_KERNELS = ("nr_pack_kernel", "nr_match_filtered_kernel<main pass>", "nr_match_filtered_kernel<N pass>",
-                "nr_match_deep_kernel<K=3>", "nr_match_deep_kernel<K=5>", "nr_deep_finalize_kernel",
-                "nr_match_exhaustive16_kernel")
+                "nr_match_deep_kernel<K=3>", "nr_match_deep_kernel<K=5>", "nr_match_exhaustive16_kernel",
+                "nr_deep_finalize_kernel")
 P_N = 1e-3                                       # per-base probability of an N in the synthetic flanks
 
 

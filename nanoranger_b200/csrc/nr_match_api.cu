@@ -104,15 +104,19 @@ int resolve_chain(const nr_whitelist *wl, const void *d_bases, const uint8_t *d_
                             d_score, d_nbest, d_flags, d_umi_q, listC, cntC,
                             (unsigned long long *)(ws + 96), ctr + 6, scratch, sb, few, st);
         if (rc != NR_OK) return rc;
-        rc = nr_launch_deep_finalize(wl, d_bases, d_meta, d_nmask, from_all ? nullptr : listA, cntA,
-                                     n, d_idx, d_score, d_flags, d_umi_q, st);
-        if (rc != NR_OK) return rc;
         ex_list = listC; ex_cnt = cntC;
     } else if (from_all) {
         ex_list = nullptr; ex_cnt = nullptr;
     }
-    return nr_launch_exhaustive(wl, d_bases, d_meta, d_nmask, ex_list, ex_cnt, n, min_score, d_idx,
-                                d_score, d_nbest, d_flags, d_umi_q, sms * 2, ws + 128, st);
+    int rc = nr_launch_exhaustive(wl, d_bases, d_meta, d_nmask, ex_list, ex_cnt, n, min_score, d_idx,
+                                  d_score, d_nbest, d_flags, d_umi_q, sms * 2, ws + 128, st);
+    if (rc != NR_OK || !nr_deep_usable(wl)) return rc;
+    // UMI columns of what the deep tier resolved.  LAST: the finaliser walks the tier's input list
+    // and picks the candidates whose umi_q is the pending mark, so every candidate of that list
+    // must have been written by now (the brute-force kernel never writes the mark; before it ran,
+    // its candidates would still hold whatever the caller's buffer contained)
+    return nr_launch_deep_finalize(wl, d_bases, d_meta, d_nmask, from_all ? nullptr : listA, cntA, n,
+                                   d_idx, d_score, d_flags, d_umi_q, st);
 }
 }  // namespace
 

@@ -16,8 +16,14 @@ def _run_device(wl, seqs, min_score, mode, counted=False):
     d_off = torch.from_numpy(off.view(np.int64).copy()).to(dev)
     bases, meta, nmask = wl.pack_device(d_seqs, d_off)
     ws = wl.workspace(len(seqs), dev)
+    # poisoned outputs and workspace: a kernel that reads a result slot nobody has written yet (or
+    # relies on a zeroed workspace beyond the header the API clears) fails here, not once in a while
+    out = wl.alloc_result(len(seqs), dev)
+    out.idx.fill_(0x7FFFFFF0); out.score.fill_(-77); out.nbest.fill_(254); out.flags.fill_(0xFF)
+    out.umi_q.fill_(254)
+    ws.fill_(0xA5)
     res = wl.match_device(bases, meta, nmask, min_score=min_score, mode=mode, workspace=ws,
-                          counted=counted)
+                          counted=counted, out=out)
     torch.cuda.synchronize()
     from nanoranger_b200 import MatchResult
     out = MatchResult(*(t.cpu().numpy() for t in (res.idx, res.score, res.nbest, res.flags, res.umi_q)))

@@ -1,7 +1,7 @@
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch
-from nanoranger_b200 import Whitelist, NR_MODE_AUTO, pack_ascii
+from nanoranger_b200 import Whitelist, NR_MODE_AUTO, NR_MODE_FILTERED, pack_ascii
 from nanoranger_b200.whitelists import LINKER_SLIDESEQ
 from helpers import rs, mutate
 rng = np.random.default_rng(5)
@@ -21,10 +21,11 @@ dev = torch.device("cuda:0")
 d_seqs = torch.from_numpy(buf.copy()).to(dev); d_off = torch.from_numpy(off.view(np.int64).copy()).to(dev)
 bases, meta, nmask = wl.pack_device(d_seqs, d_off)
 ws = wl.workspace(n, dev)
-out = wl.match_device(bases, meta, nmask, min_score=30, mode=NR_MODE_AUTO, workspace=ws)
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); out = wl.match_device(bases, meta, nmask, min_score=30, mode=NR_MODE_AUTO, workspace=ws); e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1)
-cells = float(sum(len(s) for s in seqs)) * len(cores) * 32 * 2
-print(f"slide-seq generic kernel: {n} candidates x {len(cores)} entries: {ms:.1f} ms, {n/ms*1e3:.0f} cand/s, {cells/ms/1e6:.0f} GCUPS, assigned {float(out.assigned(30).float().mean()):.3f}")
+for mode, name in ((NR_MODE_FILTERED, "filtered"), (NR_MODE_AUTO, "auto")):
+    out = wl.match_device(bases, meta, nmask, min_score=30, mode=mode, workspace=ws)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); out = wl.match_device(bases, meta, nmask, min_score=30, mode=mode, workspace=ws); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(f"slide-seq {name}: {n} candidates x {len(cores)} entries: {ms:.1f} ms, {n/ms*1e3:.3e} cand/s, "
+          f"assigned {float(out.assigned(30).float().mean()):.3f}, tiers {wl.tier_counts(ws)}")
