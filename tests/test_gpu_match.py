@@ -93,8 +93,9 @@ def test_737k_synthetic_vs_oracle(cuda_device, oracle):
 
 
 def test_slideseq_geometry_generic_kernel(cuda_device, oracle):
-    """32-column cores with N inside (write_bc_slideseq, utils.py:584-601): generic kernel."""
-    from nanoranger_b200 import Whitelist, NR_MODE_AUTO
+    """32-column cores with N inside (write_bc_slideseq, utils.py:584-601): the brute-force generic
+    kernel (NR_MODE_EXHAUSTIVE) and AUTO (anchored filter + deep tier) against the oracle."""
+    from nanoranger_b200 import Whitelist, NR_MODE_AUTO, NR_MODE_EXHAUSTIVE
     from nanoranger_b200.whitelists import LINKER_SLIDESEQ
     rng = np.random.default_rng(5)
     bcs = sorted({rs(rng, 14) for _ in range(1500)})
@@ -108,10 +109,12 @@ def test_slideseq_geometry_generic_kernel(cuda_device, oracle):
         a = int(rng.integers(0, 18))
         seqs.append((rs(rng, a) + mid + rs(rng, 30))[:int(rng.integers(40, 60))])
     wl = Whitelist(cores, 15, 24)
-    assert not wl.has_index
+    assert wl.has_index                      # the anchored index (8 + linker + 6)
     ref = _oracle(oracle, cores, 15, 24, seqs)
+    res, _ = _run_device(wl, seqs, 30, NR_MODE_EXHAUSTIVE)
+    compare(ref, res, 30, exact_below=True, label="slideseq brute force")
     res, _ = _run_device(wl, seqs, 30, NR_MODE_AUTO)
-    compare(ref, res, 30, exact_below=True, label="slideseq")
+    compare(ref, res, 30, exact_below=True, label="slideseq auto")
 
 
 def test_host_entry_point_matches_device(cuda_device, oracle):
