@@ -429,6 +429,53 @@ def measure_wl3m(args, ctx, batch, steps, warmup):
     }
 
 
+def measure_slideseq(args, ctx, batch, steps, warmup):
+    """BASELINE config 2's whitelist: the reference's slide-seq list (17 753 barcodes of 14 nt,
+    2 584 with N, as 8 + linker 18 + 6 = 32 scored columns, pads 15/24, threshold AS >= 30:
+    utils.py:584-601, 638), synthetic ONT-profile candidates; FILTERED (anchored seed filter) and
+    AUTO (every score exact), device-resident."""
+    import gzip
+    import torch
+    from nanoranger_b200 import NR_MODE_AUTO, NR_MODE_FILTERED, Whitelist, synth
+    from nanoranger_b200.whitelists import LINKER_SLIDESEQ
+    rank, world, dev = ctx["rank"], ctx["world"], ctx["dev"]
+    path = os.path.join(ROOT, "tests", "golden", "slideseq_whitelist.txt.gz")
+    bcs = gzip.open(path, "rt").read().split()
+    cores = [b[:8] + LINKER_SLIDESEQ + b[8:] for b in bcs]
+    wl_ascii = np.frombuffer("".join(cores).encode(), np.uint8).reshape(len(cores), 32)
+    wl = Whitelist(wl_ascii, 15, 24, device=ctx["local_rank"])
+    d = synth.make_candidates(wl_ascii, batch, seed=args.seed + 53 + 1000 * rank, geometry="slideseq",
+                              p_n=args.p_n)
+    d_seqs = torch.from_numpy(d["seqs"]).to(dev)
+    d_off = torch.from_numpy(d["offsets"].view(np.int64).copy()).to(dev)
+    ws = wl.workspace(batch, dev, NR_MODE_AUTO)
+    out = wl.alloc_result(batch, dev)
+
+    def mk(mode):
+        def step():
+            bases, meta, nmask = wl.pack_device(d_seqs, d_off)
+            wl.match_device(bases, meta, nmask, min_score=30, mode=mode, out=out, workspace=ws)
+        return step
+
+    ms_f = timed_steps(ctx, mk(NR_MODE_FILTERED), steps, warmup)
+    assigned = all_sum(ctx, [float(out.assigned(30).sum().item())])[0]
+    ms_a = timed_steps(ctx, mk(NR_MODE_AUTO), max(1, steps // 2), 1)
+    tiers = wl.tier_counts(ws)
+    wl.close()
+    if rank != 0:
+        return None
+    return {
+        "value": world * batch / (ms_f * 1e-3), "unit": "candidates/s", "ms_per_step": ms_f, "steps": steps,
+        "auto_mode_value": world * batch / (ms_a * 1e-3),
+        "assigned_fraction": assigned / (world * batch),
+        "config": {"workload": "synthetic-ont6pct-slideseq-candidates-vs-slideseq.matched.barcodes",
+                   "whitelist": f"{len(cores)} x 32 columns (8 + linker 18 + 6), the reference's "
+                                "data/slideseq.matched.barcodes.tsv.gz", "pads": [15, 24], "min_score": 30,
+                   "candidates_per_gpu_per_step": batch, "p_n": args.p_n},
+        "auto_tiers_rank0": tiers,
+    }
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -623,11 +670,13 @@ def run_flanks(args, ctx):
     del d_seqs, d_off, ws, out
     torch.cuda.empty_cache()
 
-    kin = w3m = None
+    kin = w3m = sls = None
     if not args.no_extras:
         kin = measure_kinnex(args, ctx, args.kinnex_batch, max(3, args.steps // 2), 2)
         torch.cuda.empty_cache()
         w3m = measure_wl3m(args, ctx, args.wl3m_batch, max(2, args.steps // 3), 1)
+        torch.cuda.empty_cache()
+        sls = measure_slideseq(args, ctx, 1 << 20, max(2, args.steps // 3), 1)
     if rank != 0:
         return
 
@@ -715,7 +764,7 @@ def run_flanks(args, ctx):
                 "pageable_buffers_value": world * B / e2e_pageable_s},
         "gpu_launches": len(STEP_KERNELS) * args.steps, "kernels_per_step": list(STEP_KERNELS),
         "clocks": clocks, "roofline": roofline,
-        "kinnex": kin, "wl3m": w3m,
+        "kinnex": kin, "wl3m": w3m, "slideseq": sls,
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

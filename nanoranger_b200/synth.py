@@ -3,6 +3,7 @@
 Templates follow what the reference's extractors emit:
   5'  : CGCTCTTCCGATCT + barcode(16) + UMI(umi_len) + TTTCTTATAT      (utils.py:105, 137-139, 202)
   3'  : 3 adapter bases + barcode(16) + UMI(12) + TTTT                 (utils.py:1374-1376)
+  slide-seq : 8 nt + bc[:8] + linker(18) + bc[8:] + 16 nt               (utils.py:443-448, 584-601)
 Per-base iid errors: substitution, insertion, deletion (default 2 % each, 6 % total); a fraction
 of candidates carries a random non-whitelist 16-mer (negatives).  Fully vectorised numpy.
 """
@@ -43,6 +44,13 @@ def make_candidates(whitelist_ascii: np.ndarray, n: int, seed: int = 2, geometry
     elif geometry == "3p":
         left = rng.integers(0, 4, size=(n, 3), dtype=np.uint8)
         right = np.full((n, 4), 3, dtype=np.uint8)
+    elif geometry == "slideseq":
+        # decon_3pXCR_slideseq keeps 22 nt before / 16 nt after the linker hit of the reverse strand
+        # (utils.py:443-448), i.e. 16 + 8 before and 6 + 16 after the linker in barcode orientation;
+        # whitelist_ascii holds the 32-column cores (N columns read as A); no separate UMI segment
+        left = rng.integers(0, 4, size=(n, 8), dtype=np.uint8)
+        right = rng.integers(0, 4, size=(n, 16), dtype=np.uint8)
+        umi_codes = umi_codes[:, :0]
     else:
         raise ValueError(geometry)
     tmpl = np.concatenate([left, bc, umi_codes, right], axis=1)   # [n, T]
