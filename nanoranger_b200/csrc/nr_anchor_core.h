@@ -19,6 +19,13 @@
 //      automaton of nr_deep_core.h (K = 2), which also yields the UMI column of the winner.
 // Scripts are ordered by cost, so a read whose best pair costs t only runs the scripts with
 // linker cost + script cost <= t (the stages of the 16-column filter, nr_filter_core.h).
+//
+// Reads with one or two N.  An N row scores 0 against any column (cost 1, no shift).  The linker
+// walk counts N rows as matches (a lower bound on the linker cost: the budget for P only grows);
+// the scripts run on the window with each N inside it substituted by the four bases (4 or 16
+// windows): a placement of true cost c that aligns the N to a column of P costs c - 1 in the
+// window that carries that column's base, so it is nominated at the same stage or earlier; the
+// scorer knows the N rows (nr_deep_rows.nrow).
 #pragma once
 #include <stdint.h>
 
@@ -184,4 +191,10 @@ NR_HD int nr_anchor_score(const nr_deep_rows &rows, uint32_t lo, uint32_t hi, ui
         }
     }
     return best;
+}
+
+// substitute base `x` at window position k (0..9)
+NR_HD uint32_t nr_anchor_subst(uint32_t W, int k, uint32_t x)
+{
+    return (W & ~(3u << (2 * k))) | (x << (2 * k));
 }

@@ -19,9 +19,10 @@
 //              the plane automaton (K = 2, nr_deep_core.h), exact
 //   merge      best cost, the distinct (entry, strand) pairs attaining it, smallest entry
 // The winner's UMI column comes from the same automaton without the end-overhang rule
-// (nr_deep_umi_row).  Candidates the filter cannot take (contain N, more than 63 bases, more
-// junctions or co-optimal pairs than the warp's lists hold) go to the device list the deep tier
-// resolves.
+// (nr_deep_umi_row).  Reads with one or two N: wildcard linker walk, script windows with the N
+// substituted by every base, N-aware scorer (nr_anchor_core.h).  Candidates the filter cannot take
+// (more than two N, more than 63 bases, more junctions or co-optimal pairs than the warp's lists
+// hold) go to the device list the deep tier resolves.
 #include "nr_common.cuh"
 #include "nr_anchor_core.h"
 #include "nr_filter_core.h"
@@ -38,6 +39,7 @@ struct nr_anchor_params {
     int L, Lk, padL, padR;
     const uint4 *bases;
     const uint8_t *meta;
+    const uint64_t *nmask;
     uint64_t n_cand;
     int min_score;
     int resolve_below;
@@ -56,6 +58,7 @@ struct WarpSmemA {
     uint4 tile[32];
     uint32_t rdp[2][NR_RDP_WORDS];
     nr_deep_rows rows[2];
+    uint64_t nm[2];                 // N rows of the candidate in flight, per strand (bit i = base i)
     uint32_t junc[NR_AJCAP];        // strand | a << 1 | linker cost << 8
     uint32_t queue[NR_AQCAP];       // row of the P table | strand << 31
 };
@@ -79,10 +82,10 @@ __device__ __forceinline__ nr_anchor_script script_unpack(uint32_t w)
     return s;
 }
 
-// row masks of one strand from its packed words (bit i <-> read row i)
-__device__ __forceinline__ void rows_from_words(const uint32_t *w, int m, nr_deep_rows &r)
+// row masks of one strand from its packed words (bit i <-> read row i); nm: bases that are N
+__device__ __forceinline__ void rows_from_words(const uint32_t *w, int m, uint64_t nm, nr_deep_rows &r)
 {
-    const uint64_t len_mask = (1ull << m) - 1ull;               // m <= 63
+    const uint64_t len_mask = ((1ull << m) - 1ull) & ~nm;       // m <= 63
 #pragma unroll
     for (uint32_t c = 0; c < 4; c++) {
         uint64_t eq = 0;
@@ -98,7 +101,7 @@ __device__ __forceinline__ void rows_from_words(const uint32_t *w, int m, nr_dee
         }
         r.eq[c] = (eq & len_mask) << 1;
     }
-    r.nrow = 0;
+    r.nrow = nm << 1;
     r.valid = (m >= 63) ? ~0ull : ((1ull << (m + 1)) - 1ull);
     r.edge = 1ull | (1ull << m);
 }
@@ -172,11 +175,17 @@ nr_match_anchored_kernel(const nr_anchor_params P)
         const uint64_t tile = ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(t64 >> 32), 0) << 32) |
                               (uint64_t)__shfl_sync(0xffffffffu, (uint32_t)t64, 0);
         if (tile >= n_tiles) break;
-        uint32_t mt = 0x100u;
+        uint32_t mt = 0x100u, nm_lo = 0, nm_hi = 0;
         {
             const uint64_t mine = tile * 32 + lane;
             uint4 b = make_uint4(0u, 0u, 0u, 0u);
-            if (mine < P.n_cand) { b = __ldcs(P.bases + mine); mt = P.meta[mine]; }
+            if (mine < P.n_cand) {
+                b = __ldcs(P.bases + mine); mt = P.meta[mine];
+                if (mt != 0xFFu && (mt & 0x80u)) {
+                    const uint64_t nm = P.nmask[mine];
+                    nm_lo = (uint32_t)nm; nm_hi = (uint32_t)(nm >> 32);
+                }
+            }
             __syncwarp();
             sm.tile[lane] = b;
             __syncwarp();
@@ -195,7 +204,10 @@ nr_match_anchored_kernel(const nr_anchor_params P)
                 continue;
             }
             const int m = (int)(cmt & 0x7Fu);
-            bool to_list = (cmt & 0x80u) || m > NR_DEEP_MAXM || m < 1;
+            uint64_t nm = ((uint64_t)__shfl_sync(0xffffffffu, nm_hi, c) << 32) |
+                          (uint64_t)__shfl_sync(0xffffffffu, nm_lo, c);
+            if (m >= 1 && m <= NR_DEEP_MAXM) nm &= (1ull << m) - 1ull;
+            bool to_list = __popcll(nm) > 2 || m > NR_DEEP_MAXM || m < 1;
             AccA acc;
             acc.best = 3; acc.nb = 0; acc.key = 0; acc.overflow = 0; acc.qn = 0;
             if (!to_list) {
@@ -211,8 +223,9 @@ nr_match_anchored_kernel(const nr_anchor_params P)
                         if ((int)lane == k + 1) { vf = w4[k]; vr = rc[k]; }
                     __syncwarp();
                     if (lane < NR_RDP_WORDS) { sm.rdp[0][lane] = vf; sm.rdp[1][lane] = vr; }
-                    if (lane == 8) rows_from_words(w4, m, sm.rows[0]);
-                    if (lane == 9) rows_from_words(rc, m, sm.rows[1]);
+                    const uint64_t nmr = nm ? (__brevll(nm) >> (64 - m)) : 0ull;
+                    if (lane == 8) { rows_from_words(w4, m, nm, sm.rows[0]); sm.nm[0] = nm; }
+                    if (lane == 9) { rows_from_words(rc, m, nmr, sm.rows[1]); sm.nm[1] = nmr; }
                     __syncwarp();
                 }
                 // junctions: rows a where the linker fits at cost <= 2 (a >= 6: P may hang over the
@@ -228,7 +241,9 @@ nr_match_anchored_kernel(const nr_anchor_params P)
                     int ck = 3;
                     if (ok) {
                         const uint64_t V = nr_window64(sm.rdp[strand], a - 1);
-                        const uint64_t vm = nr_valid_mask(1 - a, m - a + 1);
+                        // N rows count as matches in the walk (a lower bound on the linker cost)
+                        const uint64_t vm = nr_valid_mask(1 - a, m - a + 1) &
+                                            ~nr_spread_even((uint32_t)(sm.nm[strand] >> (a - 1)));
                         const int fl = nr_anchor_linker(V, vm, P.link, Lk);
                         if (fl) ck = (fl & 1) ? 0 : ((fl & 2) ? 1 : 2);
                     }
@@ -254,9 +269,20 @@ nr_match_anchored_kernel(const nr_anchor_params P)
 #pragma unroll 1
                             for (int d = 0; ck + d <= t; d++) {
                                 const int cs = t - ck - d, e = a - d;
-                                const uint32_t W = (uint32_t)nr_window64(sm.rdp[strand], e - 10) & 0xFFFFFu;
+                                const uint32_t W0 = (uint32_t)nr_window64(sm.rdp[strand], e - 10) & 0xFFFFFu;
+                                // N rows inside the window: every base they can stand for
+                                const uint64_t nms = sm.nm[strand];
+                                const uint32_t nw = (uint32_t)(e >= 10 ? nms >> (e - 10) : nms << (10 - e)) & 0x3FFu;
+                                const int nn = __popc(nw);
+                                const int k0 = nn ? __ffs((int)nw) - 1 : 0, k1 = nn > 1 ? 31 - __clz((int)nw) : 0;
+                                const int nvar = nn == 0 ? 1 : (nn == 1 ? 4 : 16);
                                 const int s0 = s_first[cs], s1 = s_first[cs + 1];
+#pragma unroll 1
+                                for (int v = 0; v < nvar; v++)
                                 for (int sb = s0; sb < s1; sb += 32) {
+                                    uint32_t W = W0;
+                                    if (nn >= 1) W = nr_anchor_subst(W, k0, (uint32_t)(v & 3));
+                                    if (nn >= 2) W = nr_anchor_subst(W, k1, (uint32_t)(v >> 2));
                                     const int si = sb + (int)lane;
                                     uint32_t start = 0, cnt = 0;
                                     if (si < s1) {
@@ -342,7 +368,7 @@ nr_match_anchored_kernel(const nr_anchor_params P)
 // Enqueue the anchored matcher on `stream`.  The workspace header (list count, tile counter) must
 // have been zeroed on the stream.
 int nr_launch_anchored(const nr_whitelist *wl, const void *d_bases, const uint8_t *d_meta,
-                       uint64_t n_cand, int min_score, int resolve_below, int32_t *d_idx,
+                       const uint64_t *d_nmask, uint64_t n_cand, int min_score, int resolve_below, int32_t *d_idx,
                        int8_t *d_score, uint8_t *d_nbest, uint8_t *d_flags, uint8_t *d_umi,
                        uint32_t *d_list, uint32_t *d_list_count, unsigned long long *d_tile_next,
                        unsigned long long *d_counters, cudaStream_t stream)
@@ -357,7 +383,7 @@ int nr_launch_anchored(const nr_whitelist *wl, const void *d_bases, const uint8_
     P.lo = wl->d_lo; P.hi = wl->d_hi; P.nm = wl->d_nm;
     P.link = wl->anchor_link; P.L = (int)wl->L; P.Lk = wl->anchor_lk;
     P.padL = (int)wl->pad_l; P.padR = (int)wl->pad_r;
-    P.bases = (const uint4 *)d_bases; P.meta = d_meta; P.n_cand = n_cand;
+    P.bases = (const uint4 *)d_bases; P.meta = d_meta; P.nmask = d_nmask; P.n_cand = n_cand;
     P.min_score = min_score; P.resolve_below = resolve_below;
     P.o_idx = d_idx; P.o_score = d_score; P.o_nbest = d_nbest; P.o_flags = d_flags; P.o_umi = d_umi;
     P.list = d_list; P.list_count = d_list_count; P.tile_next = d_tile_next; P.counters = d_counters;

@@ -25,7 +25,7 @@ int nr_launch_filtered(const nr_whitelist *wl, const void *d_bases, const uint8_
                        unsigned long long *d_counters, int *grid_out, cudaStream_t stream);
 
 int nr_launch_anchored(const nr_whitelist *wl, const void *d_bases, const uint8_t *d_meta,
-                       uint64_t n_cand, int min_score, int resolve_below, int32_t *d_idx,
+                       const uint64_t *d_nmask, uint64_t n_cand, int min_score, int resolve_below, int32_t *d_idx,
                        int8_t *d_score, uint8_t *d_nbest, uint8_t *d_flags, uint8_t *d_umi,
                        uint32_t *d_list, uint32_t *d_list_count, unsigned long long *d_tile_next,
                        unsigned long long *d_counters, cudaStream_t stream);
@@ -190,7 +190,7 @@ extern "C" int nr_match_device(const nr_whitelist_t *wl, const void *d_bases,
     uint32_t *d_list = (uint32_t *)(ws + NR_WS_HEADER);
     int grid = 0;
     if (wl->has_anchor) {
-        int rc = nr_launch_anchored(wl, d_bases, d_meta, n, min_score, eff == NR_MODE_AUTO ? 1 : 0, d_idx,
+        int rc = nr_launch_anchored(wl, d_bases, d_meta, d_nmask, n, min_score, eff == NR_MODE_AUTO ? 1 : 0, d_idx,
                                     d_score, d_nbest, d_flags, d_umi_q, d_list, d_count,
                                     (unsigned long long *)(ws + 72), nullptr, st);
         if (rc != NR_OK) return rc;
@@ -230,7 +230,7 @@ extern "C" int nr_match_device_counted(const nr_whitelist_t *wl, const void *d_b
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
     if (wl->has_anchor) {
-        int rc = nr_launch_anchored(wl, d_bases, d_meta, n, min_score, 0, d_idx, d_score, d_nbest, d_flags,
+        int rc = nr_launch_anchored(wl, d_bases, d_meta, d_nmask, n, min_score, 0, d_idx, d_score, d_nbest, d_flags,
                                     d_umi_q, listA, (uint32_t *)(ws + 64), (unsigned long long *)(ws + 72),
                                     (unsigned long long *)ws, st);
         if (rc != NR_OK) return rc;

@@ -28,7 +28,7 @@ void window(const uint8_t *q, int m, int p, uint64_t *V, uint64_t *vm)
 
 extern "C" {
 
-// cand: N x 64 codes (0..3; reads with N are not taken), clen: N.  took[i] = 0: not taken.
+// cand: N x 64 codes (0..3, 4 = N; reads with more than two N are not taken), clen: N.  took[i] = 0: not taken.
 // score -128 / idx -1 when no pair reaches cost <= 2.  info: Lp, Lk, Ls, rows of the P table.
 int nr_emul_anchored(const uint32_t *wl_lo, const uint32_t *wl_hi, const uint32_t *wl_nm, int64_t n, int L,
                      int padL, int padR, const uint8_t *cand, const uint8_t *clen, int64_t N, int32_t *idx,
@@ -47,16 +47,18 @@ int nr_emul_anchored(const uint32_t *wl_lo, const uint32_t *wl_hi, const uint32_
         const int m = clen[c];
         idx[c] = -1; score[c] = -128; nbest[c] = 0; strand[c] = 0; umi[c] = -1; took[c] = 0;
         if (m < 1 || m > NR_DEEP_MAXM) continue;
-        bool has_n = false;
-        for (int i = 0; i < m; i++) has_n |= cand[c * 64 + i] > 3;
-        if (has_n) continue;
+        int n_n = 0;
+        for (int i = 0; i < m; i++) n_n += cand[c * 64 + i] > 3;
+        if (n_n > 2) continue;
         took[c] = 1;
         uint8_t q[2][64];
+        uint64_t nmk[2] = {0, 0};
         nr_deep_rows rows[2];
         for (int st = 0; st < 2; st++) {
             for (int i = 0; i < m; i++) {
                 const uint8_t x = cand[c * 64 + (st ? m - 1 - i : i)];
-                q[st][i] = st ? (uint8_t)(3 - x) : x;
+                q[st][i] = x > 3 ? 4 : (st ? (uint8_t)(3 - x) : x);
+                if (x > 3) nmk[st] |= 1ull << i;
             }
             nr_deep_rows_from_codes(q[st], m, rows[st]);
         }
@@ -68,6 +70,11 @@ int nr_emul_anchored(const uint32_t *wl_lo, const uint32_t *wl_hi, const uint32_
                 if (a < 0) continue;
                 uint64_t V, vm;
                 window(q[st], m, a - 1, &V, &vm);
+                // N rows count as matches in the walk
+                for (int t = 0; t < 32; t++) {
+                    const int i = a - 1 + t;
+                    if (i >= 0 && i < m && ((nmk[st] >> i) & 1ull)) vm &= ~(1ull << (2 * t));
+                }
                 const int fl = nr_anchor_linker(V, vm, ix.link, Lk);
                 if (!fl) continue;
                 js.push_back({st, a, (fl & 1) ? 0 : ((fl & 2) ? 1 : 2)});
@@ -78,12 +85,21 @@ int nr_emul_anchored(const uint32_t *wl_lo, const uint32_t *wl_hi, const uint32_
             for (const J &j : js)
                 for (int d = 0; j.ck + d <= t; d++) {
                     const int cs = t - j.ck - d, e = j.a - d;
-                    uint32_t W = 0;
+                    uint32_t W0 = 0;
+                    int npos[2] = {-1, -1}, nw = 0;               // N positions inside the window
                     for (int k = 0; k < 10; k++) {
                         const int i = e - 10 + k;
-                        if (i >= 0 && i < m) W |= (uint32_t)(q[j.st][i] & 3) << (2 * k);
+                        if (i >= 0 && i < m) {
+                            if (q[j.st][i] > 3) npos[nw++] = k;
+                            else W0 |= (uint32_t)(q[j.st][i] & 3) << (2 * k);
+                        }
                     }
+                    const int nvar = nw == 0 ? 1 : (nw == 1 ? 4 : 16);
+                    for (int v = 0; v < nvar; v++)
                     for (int s = tab.first[cs]; s < tab.first[cs + 1]; s++) {
+                        uint32_t W = W0;
+                        if (nw >= 1) W = nr_anchor_subst(W, npos[0], (uint32_t)(v & 3));
+                        if (nw >= 2) W = nr_anchor_subst(W, npos[1], (uint32_t)(v >> 2));
                         uint32_t key;
                         if (!nr_anchor_apply(tab.s[s], W, e, &key)) continue;
                         counters[0]++;

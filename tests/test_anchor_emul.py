@@ -81,7 +81,7 @@ def slide_whitelist(rng, n, p_n=0.15, near=0.3):
     return [b[:8] + LINKER + b[8:] for b in bcs]
 
 
-def slide_candidates(rng, O, wl, n):
+def slide_candidates(rng, O, wl, n, with_n=0.0):
     out = []
     for _ in range(n):
         core = wl[int(rng.integers(0, len(wl)))]
@@ -99,6 +99,11 @@ def slide_candidates(rng, O, wl, n):
         q = q[:63]
         if rng.random() < 0.12:
             q = O.revcomp(q)
+        if with_n and rng.random() < with_n and len(q) > 2:
+            q = list(q)
+            for _k in range(int(rng.choice([1, 1, 2, 3]))):
+                q[int(rng.integers(0, len(q)))] = "N"
+            q = "".join(q)
         out.append(q)
     return out
 
@@ -112,6 +117,18 @@ def test_anchored_filter_lossless_random(oracle, emul, pad_l, pad_r):
     assert tuple(info[:3]) == (8, 18, 6)
     # (with tiny pads the flanks of the read cost 1 per base: few candidates reach AS >= 30)
     assert check(ref, out, 32, cands, wl) > (600 if pad_l >= 15 else 0)
+
+
+def test_anchored_filter_reads_with_n(oracle, emul):
+    """one or two N anywhere in the read (inside the 8 columns in front of the linker, inside the
+    linker, in the tail): substituted windows + wildcard linker walk stay lossless."""
+    rng = np.random.default_rng(77)
+    wl = slide_whitelist(rng, 1500)
+    cands = slide_candidates(rng, oracle, wl, 3000, with_n=1.0)
+    ref, out, info, cnt = run_emul(emul, oracle, wl, cands, 15, 24)
+    n_n = np.array([c.count("N") for c in cands])
+    assert (out["took"][n_n <= 2] == 1).all() and (out["took"][n_n > 2] == 0).all()
+    assert check(ref, out, 32, cands, wl) > 400
 
 
 def _variants(rng, core):

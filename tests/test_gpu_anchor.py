@@ -21,7 +21,8 @@ def test_anchored_filtered_and_auto_vs_oracle(cuda_device, oracle, pad_l, pad_r)
     rng = np.random.default_rng(90 + pad_l)
     wl_strs = slide_whitelist(rng, 3000)
     seqs = slide_candidates(rng, oracle, wl_strs, 4000)
-    seqs += [s[:k] + "N" + s[k + 1:] for s, k in zip(seqs[:200], rng.integers(0, 30, 200))]   # reads with N
+    seqs += slide_candidates(rng, oracle, wl_strs, 1500, with_n=1.0)              # one to three N anywhere
+    seqs += [s[:k] + "N" + s[k + 1:] for s, k in zip(seqs[:200], rng.integers(0, 30, 200))]
     seqs += ["A", "N" * 40, LINKER, LINKER * 3, "ACGT" * 16]
     wl = Whitelist(wl_strs, pad_l, pad_r)
     assert wl.has_index
