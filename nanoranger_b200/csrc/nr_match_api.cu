@@ -292,8 +292,18 @@ extern "C" void nr_host_free(void *p) { if (p) cudaFreeHost(p); }
 // directly; pageable buffers go through the slot's pinned staging area.
 namespace {
 
-constexpr uint64_t CHUNK_CAND = 1ull << 18;               // candidates per chunk
-constexpr uint64_t CHUNK_BYTES = CHUNK_CAND * 64;         // sequence bytes per chunk
+// candidates per chunk: 2^20 by default (NR_HOST_CHUNK_LOG2 = 16..22 overrides it, for experiments:
+// 2^18 1.67e8, 2^19 1.87e8, 2^20 1.95e8, 2^21 1.95e8 candidates/s end to end on the bench workload --
+// every chunk pays the N pass and four near-empty tail launches)
+uint64_t chunk_cand()
+{
+    const char *e = getenv("NR_HOST_CHUNK_LOG2");
+    long v = e ? atol(e) : 20;
+    if (v < 16 || v > 22) v = 20;
+    return 1ull << v;
+}
+const uint64_t CHUNK_CAND = chunk_cand();
+const uint64_t CHUNK_BYTES = CHUNK_CAND * 64;             // sequence bytes per chunk
 constexpr int NSLOT = 4;
 
 struct Slot {

@@ -1,21 +1,23 @@
-import os, sys, time, gzip, tempfile
+"""End-to-end rate of nr_match_host (pinned host buffers) on the bench workload.
+usage: time_host.py [n] [p_n]   (NR_HOST_CHUNK_LOG2 selects the chunk size)"""
+import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
-from nanoranger_b200 import synth, whitelists, utils, fastx
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
-wl = whitelists.load_737k()
-d = synth.make_candidates(wl, n, seed=5)
-seqs = synth.to_strings(d["seqs"], d["offsets"])
-out = tempfile.mkdtemp()
-t = time.time()
-with gzip.open(f"{out}/s_BCUMI.fasta.gz", "wt", compresslevel=1) as f:
-    for i, s in enumerate(seqs):
-        f.write(f">read{i:08d}-uuid_{i}_{i+500}_0_GENE{i%50}-201|ENST{i%50}.1_900\n{s}\n")
-print("write fasta", time.time() - t)
-with open(f"{out}/wl.txt", "w") as f:
-    f.write("\n".join(x + "-1" for x in whitelists.ascii_to_strings(wl)) + "\n")
-t = time.time(); utils.write_bc_5p10X("s", out, f"{out}/wl.txt"); print("write_bc", time.time() - t)
-t = time.time(); utils.barcode_ref(f"{out}/s_bcreads.fasta", f"{out}/ref/"); print("barcode_ref", time.time() - t)
-t = time.time(); names, sq, off = fastx.read_fasta(f"{out}/s_BCUMI.fasta.gz"); print("read_fasta", time.time() - t)
-t = time.time(); k = utils.barcode_align(f"{out}/s_BCUMI.fasta.gz", f"{out}/ref/", f"{out}/s_matching", 8); print("barcode_align", time.time() - t, k)
-t = time.time(); utils.process_matching_5p10X("s", out); print("process_matching", time.time() - t)
+import numpy as np, torch
+from nanoranger_b200 import MatchResult, NR_MODE_AUTO, NR_MODE_FILTERED, Whitelist, synth, whitelists
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 22
+p_n = float(sys.argv[2]) if len(sys.argv) > 2 else 1e-3
+wl_a = whitelists.load_737k()
+d = synth.make_candidates(wl_a, n, seed=2, p_n=p_n)
+wl = Whitelist(wl_a, 30, 40)
+def pinned(a):
+    t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True); t.numpy()[...] = a; return t
+ps, po = pinned(d["seqs"]), pinned(d["offsets"].view(np.int64))
+outs = [torch.empty(n, dtype=dt, pin_memory=True) for dt in (torch.int32, torch.int8, torch.uint8, torch.uint8, torch.uint8)]
+res = MatchResult(*(t.numpy() for t in outs))
+for mode, name in ((NR_MODE_FILTERED, "filtered"), (NR_MODE_AUTO, "auto")):
+    wl.match_host(ps.numpy(), po.numpy().view(np.uint64), min_score=14, mode=mode, out=res)
+    t0 = time.perf_counter()
+    for _ in range(4):
+        wl.match_host(ps.numpy(), po.numpy().view(np.uint64), min_score=14, mode=mode, out=res)
+    dt = (time.perf_counter() - t0) / 4
+    print(f"chunk 2^{os.environ.get('NR_HOST_CHUNK_LOG2', '20')} {name}: {n / dt:.3e} cand/s ({dt * 1e3:.1f} ms)")
