@@ -33,7 +33,8 @@
 
 #define NR_DEEP_MAXTHREADS 1024
 #define NR_DEEP_HCAP 2048          // groups per phase-B window (= capacity of the hot list)
-#define NR_DEEP_ITEM 128           // entries per phase-B work item (4 per lane, loads issued together)
+#define NR_DEEP_ITEM 512           // entries per phase-B work item: four batches of NR_DEEP_BATCH
+#define NR_DEEP_BATCH 128          // entries per batch (4 per lane, loads issued together)
 #define NR_UMI_PENDING 254         // umi_q placeholder between the resolver and the finaliser
 
 struct nr_deep_params {
@@ -288,49 +289,59 @@ nr_match_deep_kernel(const nr_deep_params P)
                     for (int e = 0; e <= K; e++) own[e] = plane_ld<SMEM>(planes + (size_t)e * G + gg);
                     if (gg < P.g_pre) {
                         if (gmn + gsmin > *(volatile int *)&s_bound) continue;
-                        const uint32_t p0 = __ldg(P.pre_start + gg) + off, p1 = __ldg(P.pre_start + gg + 1);
-                        uint32_t h[NR_DEEP_ITEM / 32];
+                        const uint32_t p1 = __ldg(P.pre_start + gg + 1);
+                        const uint32_t first = __ldg(P.pre_start + gg) + off;          // this lane's first entry
+                        const uint32_t last = min(p1, first - lane + NR_DEEP_ITEM);     // end of the item
+#pragma unroll 1
+                        for (uint32_t p0 = first; p0 < last; p0 += NR_DEEP_BATCH) {
+                            uint32_t h[NR_DEEP_BATCH / 32];
 #pragma unroll
-                        for (int u = 0; u < NR_DEEP_ITEM / 32; u++)
-                            h[u] = p0 + 32 * u < p1 ? __ldg(P.ent_suf + p0 + 32 * u) : 0xFFFFFFFFu;
+                            for (int u = 0; u < NR_DEEP_BATCH / 32; u++)
+                                h[u] = p0 + 32 * u < p1 ? __ldg(P.ent_suf + p0 + 32 * u) : 0xFFFFFFFFu;
 #pragma unroll
-                        for (int u = 0; u < NR_DEEP_ITEM / 32; u++) {
-                            if (h[u] == 0xFFFFFFFFu) continue;
-                            const int bound = *(volatile int *)&s_bound;
-                            if (gmn + (int)mins[P.g_pre + h[u]] > bound) continue;
-                            uint64_t b[K + 1];
+                            for (int u = 0; u < NR_DEEP_BATCH / 32; u++) {
+                                if (h[u] == 0xFFFFFFFFu) continue;
+                                const int bound = *(volatile int *)&s_bound;
+                                if (gmn + (int)mins[P.g_pre + h[u]] > bound) continue;
+                                uint64_t b[K + 1];
 #pragma unroll
-                            for (int e = 0; e <= K; e++)
-                                b[e] = plane_ld<SMEM>(planes + (size_t)e * G + P.g_pre + h[u]);
-                            const int t = nr_deep_join<K>(own, b);
-                            if (t <= bound) {
-                                const uint32_t key = (__ldg(P.ent_idx + p0 + 32 * u) << 1) | (uint32_t)st;
-                                if (t < bc) { bc = t; bn = 1; bk = key; atomicMin(&s_bound, t); }
-                                else if (t == bc) { bn++; bk = min(bk, key); }
+                                for (int e = 0; e <= K; e++)
+                                    b[e] = plane_ld<SMEM>(planes + (size_t)e * G + P.g_pre + h[u]);
+                                const int t = nr_deep_join<K>(own, b);
+                                if (t <= bound) {
+                                    const uint32_t key = (__ldg(P.ent_idx + p0 + 32 * u) << 1) | (uint32_t)st;
+                                    if (t < bc) { bc = t; bn = 1; bk = key; atomicMin(&s_bound, t); }
+                                    else if (t == bc) { bn++; bk = min(bk, key); }
+                                }
                             }
                         }
                     } else {
                         const uint32_t hh = gg - P.g_pre;
                         if (gmn + gfmin > *(volatile int *)&s_bound) continue;
-                        const uint32_t p0 = __ldg(P.suf_start + hh) + off, p1 = __ldg(P.suf_start + hh + 1);
-                        uint32_t gq[NR_DEEP_ITEM / 32];
+                        const uint32_t p1 = __ldg(P.suf_start + hh + 1);
+                        const uint32_t first = __ldg(P.suf_start + hh) + off;
+                        const uint32_t last = min(p1, first - lane + NR_DEEP_ITEM);
+#pragma unroll 1
+                        for (uint32_t p0 = first; p0 < last; p0 += NR_DEEP_BATCH) {
+                            uint32_t gq[NR_DEEP_BATCH / 32];
 #pragma unroll
-                        for (int u = 0; u < NR_DEEP_ITEM / 32; u++)
-                            gq[u] = p0 + 32 * u < p1 ? __ldg(P.sent_pre + p0 + 32 * u) : 0xFFFFFFFFu;
+                            for (int u = 0; u < NR_DEEP_BATCH / 32; u++)
+                                gq[u] = p0 + 32 * u < p1 ? __ldg(P.sent_pre + p0 + 32 * u) : 0xFFFFFFFFu;
 #pragma unroll
-                        for (int u = 0; u < NR_DEEP_ITEM / 32; u++) {
-                            if (gq[u] == 0xFFFFFFFFu) continue;
-                            const int fm = mins[gq[u]];
-                            const int bound = *(volatile int *)&s_bound;
-                            if (fm <= A || fm + gmn > bound) continue;   // fm <= A: the prefix side has it
-                            uint64_t f[K + 1];
+                            for (int u = 0; u < NR_DEEP_BATCH / 32; u++) {
+                                if (gq[u] == 0xFFFFFFFFu) continue;
+                                const int fm = mins[gq[u]];
+                                const int bound = *(volatile int *)&s_bound;
+                                if (fm <= A || fm + gmn > bound) continue;   // fm <= A: the prefix side has it
+                                uint64_t f[K + 1];
 #pragma unroll
-                            for (int e = 0; e <= K; e++) f[e] = plane_ld<SMEM>(planes + (size_t)e * G + gq[u]);
-                            const int t = nr_deep_join<K>(f, own);
-                            if (t <= bound) {
-                                const uint32_t key = (__ldg(P.sent_idx + p0 + 32 * u) << 1) | (uint32_t)st;
-                                if (t < bc) { bc = t; bn = 1; bk = key; atomicMin(&s_bound, t); }
-                                else if (t == bc) { bn++; bk = min(bk, key); }
+                                for (int e = 0; e <= K; e++) f[e] = plane_ld<SMEM>(planes + (size_t)e * G + gq[u]);
+                                const int t = nr_deep_join<K>(f, own);
+                                if (t <= bound) {
+                                    const uint32_t key = (__ldg(P.sent_idx + p0 + 32 * u) << 1) | (uint32_t)st;
+                                    if (t < bc) { bc = t; bn = 1; bk = key; atomicMin(&s_bound, t); }
+                                    else if (t == bc) { bn++; bk = min(bk, key); }
+                                }
                             }
                         }
                     }

@@ -143,7 +143,6 @@ __global__ void k_order_keys(const uint32_t *du_first, const uint32_t *grp_id, c
 }
 
 #define NR_UMI_LARGE 96      // groups with more distinct UMIs go to the block-wide kernel
-#define NR_UMI_HUGE 2048     // ... and beyond this the representatives are found through a hash set
 
 __device__ __forceinline__ bool umi_joins(uint32_t rep_umi, uint32_t rep_cnt, uint32_t u,
                                           uint32_t cnt, int max_dist)
@@ -199,18 +198,20 @@ k_cluster_small(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__
     }
 }
 
-// one block per large group.  Same walk, NR_UMI_ROUND UMIs per round:
-//  (1) all threads look for the earliest representative (among those of earlier rounds) each
-//      member can join -- by comparing the round with every such representative, or, in huge
-//      groups, by looking the 3 * umi_len Hamming neighbours of each member up in a hash set of
-//      the representatives (the work per round then no longer grows with the group);
-//  (2) the round is settled in walk order, 32 members at a time: a member without an earlier
-//      representative may still join one created earlier in the same round (compared by all
-//      threads) or earlier among its own 32 (settled by one warp with adjacency masks);
-//  (3) the new representatives are appended (and inserted in the hash set).
-// The global-memory latency of (1) and (3) is paid once per round instead of once per 32 UMIs.
-#define NR_UMI_ROUND 128
-
+// one block per large group, no sequential walk.  The directional rule -- a UMI joins the EARLIEST
+// representative (in walk order) within Hamming distance 1 whose reads >= 2 * reads - 1, else it
+// becomes a representative -- only depends on the fate of the UMI's eligible neighbours at earlier
+// walk positions, and a UMI of len bases has 3 * len neighbours.  So:
+//   (1) every distinct UMI of the group goes into a hash set (UMI -> walk position);
+//   (2) rounds over the undecided UMIs, all threads in parallel: look the 3 * len neighbours up;
+//       among the eligible ones at earlier positions let r = earliest representative, q = earliest
+//       undecided.  r < q: join r (everything before r is known not to be a representative).
+//       No undecided and no representative: become a representative.  Otherwise wait a round.
+// The earliest undecided position is decided in every round, and dependency chains are short (the
+// neighbour graph is sparse), so a group of 20 000 distinct UMIs settles in a handful of rounds
+// instead of 160 sequential rounds of 128 (which made the rank owning the deepest (cell, gene)
+// group the straggler of the multi-GPU collapse).  State lives in du_rep: NONE undecided, own
+// index = representative, other index = joined.
 __device__ __forceinline__ uint32_t umi_hash(uint32_t u, uint32_t bits)
 {
     return (u * 0x9E3779B1u) >> (32u - bits);
@@ -219,138 +220,68 @@ __device__ __forceinline__ uint32_t umi_hash(uint32_t u, uint32_t bits)
 __global__ void __launch_bounds__(256)
 k_cluster_large(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ du_first,
                 const uint32_t *__restrict__ grp_first, const uint32_t *__restrict__ totals,
-                int max_dist, int umi_len, uint32_t *__restrict__ order,
-                uint32_t *__restrict__ du_rep, uint32_t *__restrict__ rep_u,
-                uint32_t *__restrict__ rep_c, uint32_t *__restrict__ htab)
+                int max_dist, int umi_len, const uint32_t *__restrict__ order,
+                uint32_t *__restrict__ du_rep, uint32_t *__restrict__ pos_u,
+                uint32_t *__restrict__ pos_c, uint32_t *__restrict__ htab)
 {
     constexpr uint32_t NONE = 0xFFFFFFFFu;
-    __shared__ uint32_t c_d[NR_UMI_ROUND], c_u[NR_UMI_ROUND], c_c[NR_UMI_ROUND], c_best[NR_UMI_ROUND];
-    __shared__ uint32_t n_d[NR_UMI_ROUND], n_u[NR_UMI_ROUND], n_c[NR_UMI_ROUND];   // this round's new reps
-    __shared__ uint32_t c_join[32], c_adj[32];
-    __shared__ uint32_t s_nrep, s_nnew;
-    const uint32_t lane = threadIdx.x & 31u;
+    __shared__ uint32_t s_left;
     const uint32_t n_groups = totals[1];
     if (max_dist <= 0) return;
+    const uint32_t per = 3u * (uint32_t)umi_len;
     for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const uint32_t d0 = grp_first[g], d1 = grp_first[g + 1];
         const uint32_t nd = d1 - d0;
         if (nd <= NR_UMI_LARGE) continue;
-        const bool hashed = nd > NR_UMI_HUGE;
         // hash set of this group: the smallest power of two >= 2 nd slots out of its 4 nd
         const uint32_t hbits = 32u - (uint32_t)__clz((int)(2u * nd - 1u));
         const uint32_t hmask = (1u << hbits) - 1u;
         uint32_t *tab = htab + 4ull * d0;
         __syncthreads();
-        if (threadIdx.x == 0) s_nrep = 0;
-        for (uint32_t r0 = 0; r0 < nd; r0 += NR_UMI_ROUND) {
+        for (uint32_t r = threadIdx.x; r < nd; r += blockDim.x) {
+            const uint32_t d = order[d0 + r];
+            const uint32_t u = s_umi[du_first[d]];
+            pos_u[d0 + r] = u;
+            pos_c[d0 + r] = du_first[d + 1] - du_first[d];
+            du_rep[d] = NONE;
+            uint32_t slot = umi_hash(u, hbits);
+            while (atomicCAS(&tab[slot], NONE, r) != NONE) slot = (slot + 1u) & hmask;
+        }
+        for (;;) {
             __syncthreads();
-            const uint32_t in_round = min((uint32_t)NR_UMI_ROUND, nd - r0);
-            if (threadIdx.x < NR_UMI_ROUND) {
-                uint32_t d = 0, u = 0, c = 0;
-                if (threadIdx.x < in_round) {
-                    d = order[d0 + r0 + threadIdx.x];
-                    u = s_umi[du_first[d]];
-                    c = du_first[d + 1] - du_first[d];
-                }
-                c_d[threadIdx.x] = d; c_u[threadIdx.x] = u; c_c[threadIdx.x] = c;
-                c_best[threadIdx.x] = NONE;
-            }
-            if (threadIdx.x == 0) s_nnew = 0;
+            if (threadIdx.x == 0) s_left = 0;
             __syncthreads();
-            const uint32_t nrep0 = s_nrep;
-            // (1) representatives of earlier rounds
-            if (hashed) {
-                const uint32_t per = 3u * (uint32_t)umi_len;
-                for (uint32_t i = threadIdx.x; i < in_round * per; i += blockDim.x) {
-                    const uint32_t k = i / per, r = i - k * per;
-                    const uint32_t key = c_u[k] ^ ((r % 3u + 1u) << (2u * (r / 3u)));
+            uint32_t left = 0;
+            for (uint32_t r = threadIdx.x; r < nd; r += blockDim.x) {
+                const uint32_t d = order[d0 + r];
+                if (__ldcg(du_rep + d) != NONE) continue;
+                const uint32_t u = pos_u[d0 + r], c = pos_c[d0 + r];
+                uint32_t rmin = NONE, qmin = NONE;
+                for (uint32_t k = 0; k < per; k++) {
+                    const uint32_t key = u ^ ((k % 3u + 1u) << (2u * (k / 3u)));
                     uint32_t slot = umi_hash(key, hbits);
                     for (;;) {
-                        const uint32_t q = tab[slot];
-                        if (q == NONE) break;
-                        if (rep_u[d0 + q] == key) {
-                            if (rep_c[d0 + q] + 1 >= 2 * c_c[k]) atomicMin(&c_best[k], q);
+                        const uint32_t j = tab[slot];
+                        if (j == NONE) break;
+                        if (pos_u[d0 + j] == key) {
+                            if (j < r && pos_c[d0 + j] + 1 >= 2 * c) {
+                                const uint32_t dj = order[d0 + j];
+                                const uint32_t st = __ldcg(du_rep + dj);
+                                if (st == dj) rmin = min(rmin, j);
+                                else if (st == NONE) qmin = min(qmin, j);
+                            }
                             break;
                         }
                         slot = (slot + 1u) & hmask;
                     }
                 }
-            } else {
-                for (uint32_t q = threadIdx.x; q < nrep0; q += blockDim.x) {
-                    const uint32_t ru = rep_u[d0 + q], rc = rep_c[d0 + q];
-#pragma unroll 8
-                    for (uint32_t k = 0; k < NR_UMI_ROUND; k++)
-                        if (k < in_round && umi_joins(ru, rc, c_u[k], c_c[k], max_dist))
-                            atomicMin(&c_best[k], q);
-                }
+                if (rmin != NONE && rmin < qmin) __stcg(du_rep + d, order[d0 + rmin]);
+                else if (qmin == NONE) __stcg(du_rep + d, d);
+                else left++;
             }
-            // (2) settle the round, 32 members at a time
-            for (uint32_t base = 0; base < in_round; base += 32) {
-                const uint32_t cnt = min(32u, in_round - base);
-                __syncthreads();
-                if (threadIdx.x < 32) { c_join[threadIdx.x] = NONE; c_adj[threadIdx.x] = 0u; }
-                __syncthreads();
-                const uint32_t nnew = s_nnew;
-                // representatives created earlier in this round: earliest one wins
-                for (uint32_t i = threadIdx.x; i < cnt * nnew; i += blockDim.x) {
-                    const uint32_t k = i / nnew, j = i - k * nnew;
-                    if (c_best[base + k] == NONE &&
-                        umi_joins(n_u[j], n_c[j], c_u[base + k], c_c[base + k], max_dist))
-                        atomicMin(&c_join[k], j);
-                }
-                // predecessors among these 32 a member could join if they become representatives
-                for (uint32_t i = threadIdx.x; i < cnt * cnt; i += blockDim.x) {
-                    const uint32_t k = i / cnt, j = i - k * cnt;
-                    if (j < k && umi_joins(c_u[base + j], c_c[base + j], c_u[base + k], c_c[base + k], max_dist))
-                        atomicOr(&c_adj[k], 1u << j);
-                }
-                __syncthreads();
-                if (threadIdx.x < 32) {
-                    const bool have = lane < cnt;
-                    const uint32_t u = c_u[base + lane], c = c_c[base + lane], d = c_d[base + lane];
-                    const uint32_t adj = c_adj[lane];
-                    const uint32_t best = c_best[base + lane], jn = c_join[lane];
-                    uint32_t R = 0;                  // members that became representatives
-                    uint32_t join = NONE;            // representative joined among these 32
-                    for (uint32_t k = 0; k < cnt; k++) {
-                        bool is_rep = false;
-                        if (lane == k && have && best == NONE && jn == NONE) {
-                            uint32_t m = adj & R;
-                            if (m) join = (uint32_t)__ffs((int)m) - 1u;
-                            else is_rep = true;
-                        }
-                        R |= __ballot_sync(0xffffffffu, is_rep);
-                    }
-                    if (have) {
-                        if (best != NONE) {
-                            du_rep[d] = order[d0 + best];
-                        } else if (jn != NONE) {
-                            du_rep[d] = n_d[jn];
-                        } else if (join != NONE) {
-                            du_rep[d] = c_d[base + join];
-                        } else {
-                            const uint32_t j = nnew + (uint32_t)__popc(R & ((1u << lane) - 1u));
-                            du_rep[d] = d;
-                            n_d[j] = d; n_u[j] = u; n_c[j] = c;
-                        }
-                    }
-                    if (lane == 0) s_nnew = nnew + (uint32_t)__popc(R);
-                }
-            }
+            if (left) atomicAdd(&s_left, left);
             __syncthreads();
-            // (3) append the new representatives (walk order = creation order)
-            const uint32_t nnew = s_nnew;
-            if (threadIdx.x < nnew) {
-                const uint32_t pos = nrep0 + threadIdx.x;
-                order[d0 + pos] = n_d[threadIdx.x];
-                rep_u[d0 + pos] = n_u[threadIdx.x];
-                rep_c[d0 + pos] = n_c[threadIdx.x];
-                if (hashed) {
-                    uint32_t slot = umi_hash(n_u[threadIdx.x], hbits);
-                    while (atomicCAS(&tab[slot], NONE, pos) != NONE) slot = (slot + 1u) & hmask;
-                }
-            }
-            if (threadIdx.x == 0) s_nrep = nrep0 + nnew;
+            if (s_left == 0) break;
         }
     }
 }
