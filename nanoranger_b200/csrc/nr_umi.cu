@@ -12,12 +12,16 @@
 // Pipeline (all on `stream`, no host synchronisation):
 //   1  LSD radix sort: by umi (2 * umi_len bits), then stable by (barcode << 32 | gene)
 //   2  head flags + scans -> distinct-UMI ids, group ids; run lengths -> reads per distinct UMI
-//   3  one warp per group: rank the distinct UMIs, walk them, pick representatives
+//   3  small groups: one warp (or block) walks the distinct UMIs in rank order and picks the
+//      representatives; large groups: hash sets + parallel rounds over the whole grid (below)
 //   4  reads per representative, compaction of the representatives into the group table,
 //      scatter of the representative UMI back to input order
+#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 
 #include "nr_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -34,7 +38,7 @@ struct UmiWs {
     uint32_t *du_rep;                      // per distinct: distinct id of its representative
     uint32_t *rep_reads;                   // per distinct: reads of the cluster it represents
     uint32_t *rep_flag, *rep_pos;          // per distinct
-    uint32_t *rep_u, *rep_c;               // per group slot: UMI / reads of the representatives found so far
+    uint32_t *rep_u, *rep_c;               // per distinct UMI of a large group: walk position / UMI word
     uint32_t *htab;                        // 4 slots per distinct UMI: hash sets of representatives (huge groups)
     uint32_t *totals;                      // [0] n distinct, [1] n groups, [2] n reps
     void *cub_tmp;
@@ -198,91 +202,133 @@ k_cluster_small(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__
     }
 }
 
-// one block per large group, no sequential walk.  The directional rule -- a UMI joins the EARLIEST
-// representative (in walk order) within Hamming distance 1 whose reads >= 2 * reads - 1, else it
-// becomes a representative -- only depends on the fate of the UMI's eligible neighbours at earlier
-// walk positions, and a UMI of len bases has 3 * len neighbours.  So:
-//   (1) every distinct UMI of the group goes into a hash set (UMI -> walk position);
-//   (2) rounds over the undecided UMIs, all threads in parallel: look the 3 * len neighbours up;
-//       among the eligible ones at earlier positions let r = earliest representative, q = earliest
-//       undecided.  r < q: join r (everything before r is known not to be a representative).
-//       No undecided and no representative: become a representative.  Otherwise wait a round.
-// The earliest undecided position is decided in every round, and dependency chains are short (the
-// neighbour graph is sparse), so a group of 20 000 distinct UMIs settles in a handful of rounds
-// instead of 160 sequential rounds of 128 (which made the rank owning the deepest (cell, gene)
-// group the straggler of the multi-GPU collapse).  State lives in du_rep: NONE undecided, own
-// index = representative, other index = joined.
+// Large groups (more than NR_UMI_LARGE distinct UMIs), no sequential walk.  The directional rule -- a
+// UMI joins the EARLIEST representative (in walk order) within Hamming distance 1 whose reads >=
+// 2 * reads - 1, else it becomes a representative -- only depends on the fate of the UMI's eligible
+// neighbours at earlier walk positions, and a UMI of len bases has 3 * len neighbours.  So:
+//   init    every distinct UMI of a large group goes into the group's hash set (UMI -> distinct id)
+//           and is marked undecided;
+//   rounds  one cooperative launch filling the GPU; thread = one undecided UMI of the work list:
+//           look the 3 * len neighbours up; among the eligible ones at earlier positions let r =
+//           earliest representative, q = earliest undecided.  r < q: join r (everything before r
+//           is known not to be a representative).  No undecided and no representative: become a
+//           representative.  Otherwise go onto the next round's work list.  A grid-wide barrier
+//           separates the rounds; the earliest undecided position of every group is decided in
+//           every round, so the loop ends, after as many rounds as the longest chain of
+//           neighbours waiting on each other (a handful to a few dozen).
+// Decisions are final once written, so reading a neighbour's state while its own thread decides it
+// in the same round is harmless: "undecided" only makes the reader wait one more round.
+// A (cell, gene) group of 20 000 distinct UMIs is thereby settled by the whole GPU in a few rounds
+// instead of by one block in 160 sequential rounds of 128 -- the straggler of the multi-GPU
+// collapse, where the deepest group grows with the number of ranks.  State lives in du_rep: NONE
+// undecided, own id = representative, other id = joined.
+
 __device__ __forceinline__ uint32_t umi_hash(uint32_t u, uint32_t bits)
 {
     return (u * 0x9E3779B1u) >> (32u - bits);
 }
 
+struct LargeGroup {
+    uint32_t d0, nd, hbits;
+};
+
+__device__ __forceinline__ LargeGroup large_group_of(uint32_t d, const uint32_t *__restrict__ du_first,
+                                                     const uint32_t *__restrict__ grp_id,
+                                                     const uint32_t *__restrict__ grp_first)
+{
+    const uint32_t g = grp_id[du_first[d]];
+    LargeGroup G;
+    G.d0 = grp_first[g];
+    G.nd = grp_first[g + 1] - G.d0;
+    G.hbits = 32u - (uint32_t)__clz((int)(2u * G.nd - 1u));   // smallest power of two >= 2 nd, of its 4 nd slots
+    return G;
+}
+
 __global__ void __launch_bounds__(256)
-k_cluster_large(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ du_first,
-                const uint32_t *__restrict__ grp_first, const uint32_t *__restrict__ totals,
-                int max_dist, int umi_len, const uint32_t *__restrict__ order,
-                uint32_t *__restrict__ du_rep, uint32_t *__restrict__ pos_u,
-                uint32_t *__restrict__ pos_c, uint32_t *__restrict__ htab)
+k_large_init(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ du_first,
+             const uint32_t *__restrict__ grp_id, const uint32_t *__restrict__ grp_first,
+             const uint32_t *__restrict__ totals, const uint32_t *__restrict__ order,
+             uint32_t *__restrict__ du_rep, uint32_t *__restrict__ pos, uint32_t *__restrict__ val,
+             uint32_t *__restrict__ htab, uint32_t *__restrict__ work, uint32_t *__restrict__ work_count)
 {
     constexpr uint32_t NONE = 0xFFFFFFFFu;
-    __shared__ uint32_t s_left;
-    const uint32_t n_groups = totals[1];
-    if (max_dist <= 0) return;
-    const uint32_t per = 3u * (uint32_t)umi_len;
-    for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        const uint32_t d0 = grp_first[g], d1 = grp_first[g + 1];
-        const uint32_t nd = d1 - d0;
-        if (nd <= NR_UMI_LARGE) continue;
-        // hash set of this group: the smallest power of two >= 2 nd slots out of its 4 nd
-        const uint32_t hbits = 32u - (uint32_t)__clz((int)(2u * nd - 1u));
-        const uint32_t hmask = (1u << hbits) - 1u;
-        uint32_t *tab = htab + 4ull * d0;
-        __syncthreads();
-        for (uint32_t r = threadIdx.x; r < nd; r += blockDim.x) {
-            const uint32_t d = order[d0 + r];
-            const uint32_t u = s_umi[du_first[d]];
-            pos_u[d0 + r] = u;
-            pos_c[d0 + r] = du_first[d + 1] - du_first[d];
-            du_rep[d] = NONE;
-            uint32_t slot = umi_hash(u, hbits);
-            while (atomicCAS(&tab[slot], NONE, r) != NONE) slot = (slot + 1u) & hmask;
-        }
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;      // global walk index
+    if (i >= totals[0]) return;
+    const uint32_t d = order[i];
+    const LargeGroup G = large_group_of(d, du_first, grp_id, grp_first);
+    if (G.nd <= NR_UMI_LARGE) return;
+    const uint32_t u = s_umi[du_first[d]];
+    pos[d] = i - G.d0;
+    val[d] = u;
+    du_rep[d] = NONE;
+    uint32_t *tab = htab + 4ull * G.d0;
+    const uint32_t hmask = (1u << G.hbits) - 1u;
+    uint32_t slot = umi_hash(u, G.hbits);
+    while (atomicCAS(&tab[slot], NONE, d) != NONE) slot = (slot + 1u) & hmask;
+    work[atomicAdd(work_count, 1u)] = d;
+}
+
+// one round for distinct UMI d of a large group; returns true when d is (now) decided
+__device__ __forceinline__ bool large_round(uint32_t d, const LargeGroup &G, uint32_t per,
+                                            const uint32_t *__restrict__ du_first,
+                                            uint32_t *__restrict__ du_rep,
+                                            const uint32_t *__restrict__ pos,
+                                            const uint32_t *__restrict__ val,
+                                            const uint32_t *__restrict__ htab)
+{
+    constexpr uint32_t NONE = 0xFFFFFFFFu;
+    if (__ldcg(du_rep + d) != NONE) return true;
+    const uint32_t *tab = htab + 4ull * G.d0;
+    const uint32_t hmask = (1u << G.hbits) - 1u;
+    const uint32_t u = val[d], c = du_first[d + 1] - du_first[d], r = pos[d];
+    uint32_t rmin = NONE, rmin_d = NONE, qmin = NONE;
+    for (uint32_t k = 0; k < per; k++) {
+        const uint32_t key = u ^ ((k % 3u + 1u) << (2u * (k / 3u)));
+        uint32_t slot = umi_hash(key, G.hbits);
         for (;;) {
-            __syncthreads();
-            if (threadIdx.x == 0) s_left = 0;
-            __syncthreads();
-            uint32_t left = 0;
-            for (uint32_t r = threadIdx.x; r < nd; r += blockDim.x) {
-                const uint32_t d = order[d0 + r];
-                if (__ldcg(du_rep + d) != NONE) continue;
-                const uint32_t u = pos_u[d0 + r], c = pos_c[d0 + r];
-                uint32_t rmin = NONE, qmin = NONE;
-                for (uint32_t k = 0; k < per; k++) {
-                    const uint32_t key = u ^ ((k % 3u + 1u) << (2u * (k / 3u)));
-                    uint32_t slot = umi_hash(key, hbits);
-                    for (;;) {
-                        const uint32_t j = tab[slot];
-                        if (j == NONE) break;
-                        if (pos_u[d0 + j] == key) {
-                            if (j < r && pos_c[d0 + j] + 1 >= 2 * c) {
-                                const uint32_t dj = order[d0 + j];
-                                const uint32_t st = __ldcg(du_rep + dj);
-                                if (st == dj) rmin = min(rmin, j);
-                                else if (st == NONE) qmin = min(qmin, j);
-                            }
-                            break;
-                        }
-                        slot = (slot + 1u) & hmask;
-                    }
+            const uint32_t dj = tab[slot];
+            if (dj == NONE) break;
+            if (val[dj] == key) {
+                const uint32_t pj = pos[dj];
+                if (pj < r && (du_first[dj + 1] - du_first[dj]) + 1 >= 2 * c) {
+                    const uint32_t st = __ldcg(du_rep + dj);
+                    if (st == dj) { if (pj < rmin) { rmin = pj; rmin_d = dj; } }
+                    else if (st == NONE) qmin = min(qmin, pj);
                 }
-                if (rmin != NONE && rmin < qmin) __stcg(du_rep + d, order[d0 + rmin]);
-                else if (qmin == NONE) __stcg(du_rep + d, d);
-                else left++;
+                break;
             }
-            if (left) atomicAdd(&s_left, left);
-            __syncthreads();
-            if (s_left == 0) break;
+            slot = (slot + 1u) & hmask;
         }
+    }
+    if (rmin != NONE && rmin < qmin) { __stcg(du_rep + d, rmin_d); return true; }
+    if (qmin == NONE) { __stcg(du_rep + d, d); return true; }
+    return false;
+}
+
+// work_a / work_b: the undecided UMIs of this and the next round; count[3]: their lengths in
+// rotation (round r reads count[r % 3], appends to count[(r + 1) % 3], clears count[(r + 2) % 3])
+__global__ void __launch_bounds__(256)
+k_large_rounds(const uint32_t *__restrict__ du_first, const uint32_t *__restrict__ grp_id,
+               const uint32_t *__restrict__ grp_first, int umi_len, uint32_t *__restrict__ du_rep,
+               const uint32_t *__restrict__ pos, const uint32_t *__restrict__ val,
+               const uint32_t *__restrict__ htab, uint32_t *work_a, uint32_t *work_b, uint32_t *count)
+{
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    const uint32_t per = 3u * (uint32_t)umi_len;
+    for (uint32_t r = 0;; r++) {
+        const uint32_t n_in = __ldcg(count + r % 3u);
+        if (n_in == 0) break;
+        if (tid == 0) __stcg(count + (r + 2u) % 3u, 0u);
+        const uint32_t *in = (r & 1u) ? work_b : work_a;
+        uint32_t *out = (r & 1u) ? work_a : work_b;
+        for (uint32_t i = tid; i < n_in; i += nthr) {
+            const uint32_t d = __ldcg(in + i);
+            const LargeGroup G = large_group_of(d, du_first, grp_id, grp_first);
+            if (!large_round(d, G, per, du_first, du_rep, pos, val, htab))
+                __stcg(out + atomicAdd(count + (r + 1u) % 3u, 1u), d);
+        }
+        grid.sync();
     }
 }
 
@@ -404,9 +450,23 @@ extern "C" int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_ge
                                              w.du_rank_order, w.du_rep);
     if (max_dist > 0) {
         NR_CHECK_CUDA(cudaMemsetAsync(w.htab, 0xFF, (size_t)(n + 1) * 16, st));
-        k_cluster_large<<<sms * 4, 256, 0, st>>>(w.s_umi, w.du_first, w.grp_first, w.totals,
-                                                 max_dist, umi_len, w.du_rank_order, w.du_rep,
-                                                 w.rep_u, w.rep_c, w.htab);
+        // large groups: hash sets and work list, then the rounds (key_a / key_b are free again)
+        uint32_t *count = w.totals + 8, *work_a = (uint32_t *)w.key_a, *work_b = (uint32_t *)w.key_b;
+        NR_CHECK_CUDA(cudaMemsetAsync(count, 0, 12, st));
+        k_large_init<<<nb, T, 0, st>>>(w.s_umi, w.du_first, w.grp_id, w.grp_first, w.totals,
+                                       w.du_rank_order, w.du_rep, w.rep_u, w.rep_c, w.htab, work_a, count);
+        int per_sm = 0;
+        NR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_large_rounds, 256, 0));
+        if (per_sm < 1) {
+            nr_set_error("nr_umi_collapse_device: k_large_rounds does not fit an SM");
+            return NR_ECUDA;
+        }
+        const uint32_t *c_first = w.du_first, *c_gid = w.grp_id, *c_gfirst = w.grp_first;
+        const uint32_t *c_pos = w.rep_u, *c_val = w.rep_c, *c_tab = w.htab;
+        void *args[] = {&c_first, &c_gid, &c_gfirst, &umi_len, &w.du_rep, &c_pos, &c_val, &c_tab,
+                        &work_a, &work_b, &count};
+        NR_CHECK_CUDA(cudaLaunchCooperativeKernel((void *)k_large_rounds, dim3(sms * std::min(per_sm, 4)),
+                                                  dim3(256), args, 0, st));
     }
     NR_CHECK_CUDA(cudaMemsetAsync(w.rep_reads, 0, (size_t)(n + 1) * 4, st));
     k_rep_reads<<<sms * 8, 256, 0, st>>>(w.du_first, w.du_rep, w.totals, w.rep_reads, w.rep_flag);
