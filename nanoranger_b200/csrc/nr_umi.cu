@@ -38,8 +38,9 @@ struct UmiWs {
     uint32_t *du_rep;                      // per distinct: distinct id of its representative
     uint32_t *rep_reads;                   // per distinct: reads of the cluster it represents
     uint32_t *rep_flag, *rep_pos;          // per distinct
-    uint32_t *rep_u, *rep_c;               // per distinct UMI of a large group: walk position / UMI word
-    uint32_t *htab;                        // 4 slots per distinct UMI: hash sets of representatives (huge groups)
+    uint32_t *rep_u, *rep_c;               // work lists of the large-group rounds (distinct ids)
+    uint4 *rec;                            // per distinct UMI of a large group: UMI, walk position, reads, group
+    uint32_t *htab;                        // 4 slots per distinct UMI: hash set UMI -> distinct id per large group
     uint32_t *totals;                      // [0] n distinct, [1] n groups, [2] n reps
     void *cub_tmp;
     size_t cub_bytes;
@@ -58,6 +59,7 @@ size_t carve(uint8_t *base, uint64_t n, UmiWs *w, size_t cub_bytes)
                         &w->rep_flag, &w->rep_pos, &w->rep_u, &w->rep_c};
     for (auto p : a32) *p = (uint32_t *)take(n4);
     w->htab = (uint32_t *)take(4 * n4);
+    w->rec = (uint4 *)take(4 * n4);
     w->key_a = (uint64_t *)take(n8);
     w->key_b = (uint64_t *)take(n8);
     w->totals = (uint32_t *)take(256);
@@ -131,22 +133,23 @@ __device__ __forceinline__ int hamming_2bit(uint32_t a, uint32_t b)
 }
 
 // walk order of the distinct UMIs of every group: (reads desc, umi asc).  Distinct ids are
-// umi-ascending inside a group, so a STABLE sort by (group, ~reads) gives it for all groups at once.
+// umi-ascending inside a group, so a STABLE sort by (group, n - reads) gives it for all groups at
+// once.  Both fields are < 2^cb (cb = bits of n), so the sort runs over 2 cb bits, not 64.
 __global__ void k_order_keys(const uint32_t *du_first, const uint32_t *grp_id, const uint32_t *totals,
-                             uint64_t n, uint64_t *key, uint32_t *val)
+                             uint64_t n, int cb, uint64_t *key, uint32_t *val)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint64_t k = ~0ull;
+    uint64_t k = ~0ull;                      // past the last distinct UMI: sorts behind everything
     if (i < totals[0]) {
         uint32_t f = du_first[i];
-        k = ((uint64_t)grp_id[f] << 32) | (uint64_t)(0xFFFFFFFFu - (du_first[i + 1] - f));
+        k = ((uint64_t)grp_id[f] << cb) | (uint64_t)(n - (du_first[i + 1] - f));
     }
     key[i] = k;
     val[i] = (uint32_t)i;
 }
 
-#define NR_UMI_LARGE 96      // groups with more distinct UMIs go to the block-wide kernel
+#define NR_UMI_LARGE 96      // groups with more distinct UMIs go to the hash-set rounds
 
 __device__ __forceinline__ bool umi_joins(uint32_t rep_umi, uint32_t rep_cnt, uint32_t u,
                                           uint32_t cnt, int max_dist)
@@ -154,51 +157,117 @@ __device__ __forceinline__ bool umi_joins(uint32_t rep_umi, uint32_t rep_cnt, ui
     return hamming_2bit(rep_umi, u) <= max_dist && rep_cnt + 1 >= 2 * cnt;
 }
 
-// one warp per small (barcode, gene) group: sequential walk, 32 representatives compared per step
-__global__ void __launch_bounds__(256)
-k_cluster_small(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ du_first,
-                const uint32_t *__restrict__ grp_first, const uint32_t *__restrict__ totals,
-                int max_dist, uint32_t *__restrict__ order, uint32_t *__restrict__ du_rep)
+// max_dist 0: every distinct UMI is its own representative
+__global__ void k_self(const uint32_t *__restrict__ totals, uint32_t *__restrict__ du_rep)
 {
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < totals[0]) du_rep[i] = i;
+}
+
+// Small (barcode, gene) groups, sequential walk.  Nearly every group of a gene-expression library
+// has a handful of distinct UMIs: up to NR_UMI_TINY are walked by ONE thread in registers (all
+// loads of the group in flight together).  Groups of up to NR_UMI_LARGE = 3 x 32 go onto a list
+// (they cluster in the deeply sequenced cells: the list spreads them over the grid) and are
+// walked by one warp each out of registers: lane l holds walk positions l, 32 + l, 64 + l; a step
+// broadcasts the UMI at position r and every lane compares it with the representatives among its
+// own positions (all earlier than r by construction); the lowest position that accepts it wins.
+// No memory access inside the walk.
+#define NR_UMI_TINY 8
+
+__global__ void __launch_bounds__(256)
+k_cluster_tiny(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ du_first,
+               const uint32_t *__restrict__ grp_first, const uint32_t *__restrict__ totals,
+               int max_dist, const uint32_t *__restrict__ order, uint32_t *__restrict__ du_rep,
+               uint32_t *__restrict__ medium, uint32_t *__restrict__ medium_count)
+{
     const uint32_t n_groups = totals[1];
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += warps) {
-        const uint32_t d0 = grp_first[g], d1 = grp_first[g + 1];
-        const uint32_t nd = d1 - d0;
-        if (max_dist <= 0 || nd == 1) {
-            for (uint32_t i = d0 + lane; i < d1; i += 32) du_rep[i] = i;
+    const uint32_t nthr = gridDim.x * blockDim.x;
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += nthr) {
+        const uint32_t d0 = grp_first[g], nd = grp_first[g + 1] - d0;
+        if (nd > NR_UMI_LARGE) continue;
+        if (nd > NR_UMI_TINY) {
+            medium[atomicAdd(medium_count, 1u)] = g;
             continue;
         }
-        if (nd > NR_UMI_LARGE) continue;
-        // representatives are kept compacted at the front of the walked prefix: order[d0..d0+nrep)
-        // is overwritten in place (a walked position is never read again once passed)
-        uint32_t nrep = 0;
-        for (uint32_t r = 0; r < nd; r++) {
-            const uint32_t d = order[d0 + r];
-            const uint32_t u = s_umi[du_first[d]];
-            const uint32_t cnt = du_first[d + 1] - du_first[d];
-            uint32_t found = 0xFFFFFFFFu;
-            for (uint32_t q0 = 0; q0 < nrep && found == 0xFFFFFFFFu; q0 += 32) {
-                uint32_t q = q0 + lane;
-                bool ok = false;
-                uint32_t e = 0;
-                if (q < nrep) {
-                    e = order[d0 + q];
-                    ok = umi_joins(s_umi[du_first[e]], du_first[e + 1] - du_first[e], u, cnt, max_dist);
-                }
-                uint32_t mask = __ballot_sync(0xffffffffu, ok);
-                if (mask) found = __shfl_sync(0xffffffffu, e, __ffs(mask) - 1);
-            }
-            __syncwarp();
-            if (found == 0xFFFFFFFFu) {
-                if (lane == 0) { order[d0 + nrep] = d; du_rep[d] = d; }
-                nrep++;
-            } else if (lane == 0) {
-                du_rep[d] = found;
-            }
-            __syncwarp();
+        uint32_t d[NR_UMI_TINY], f[NR_UMI_TINY], u[NR_UMI_TINY], c[NR_UMI_TINY];
+#pragma unroll
+        for (int r = 0; r < NR_UMI_TINY; r++) d[r] = (uint32_t)r < nd ? order[d0 + r] : 0u;
+#pragma unroll
+        for (int r = 0; r < NR_UMI_TINY; r++) {
+            f[r] = (uint32_t)r < nd ? du_first[d[r]] : 0u;
+            c[r] = (uint32_t)r < nd ? du_first[d[r] + 1] : 0u;
         }
+#pragma unroll
+        for (int r = 0; r < NR_UMI_TINY; r++) {
+            u[r] = (uint32_t)r < nd ? s_umi[f[r]] : 0u;
+            c[r] -= f[r];
+        }
+        uint32_t reps = 0;
+#pragma unroll
+        for (int r = 0; r < NR_UMI_TINY; r++) {
+            if ((uint32_t)r >= nd) break;
+            uint32_t rep = d[r];
+            bool found = false;
+#pragma unroll
+            for (int q = 0; q < r; q++)
+                if (!found && ((reps >> q) & 1u) && umi_joins(u[q], c[q], u[r], c[r], max_dist)) {
+                    rep = d[q];
+                    found = true;
+                }
+            if (!found) reps |= 1u << r;
+            du_rep[d[r]] = rep;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_cluster_medium(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ du_first,
+                 const uint32_t *__restrict__ grp_first, int max_dist,
+                 const uint32_t *__restrict__ order, uint32_t *__restrict__ du_rep,
+                 const uint32_t *__restrict__ medium, const uint32_t *__restrict__ medium_count)
+{
+    constexpr uint32_t FULL = 0xffffffffu, NONE = 0xFFFFFFFFu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_medium = *medium_count;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_medium; i += warps) {
+        const uint32_t g = medium[i];
+        const uint32_t gd0 = grp_first[g], gnd = grp_first[g + 1] - gd0;
+        uint32_t d[3], u[3], c[3], res[3], repm[3] = {0u, 0u, 0u};
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            const uint32_t r = 32u * t + lane;
+            d[t] = u[t] = c[t] = res[t] = 0u;
+            if (r < gnd) {
+                d[t] = order[gd0 + r];
+                const uint32_t f = du_first[d[t]];
+                c[t] = du_first[d[t] + 1] - f;
+                u[t] = s_umi[f];
+            }
+        }
+        for (uint32_t r = 0; r < gnd; r++) {
+            const uint32_t t = r >> 5, src = r & 31u;
+            const uint32_t ur = __shfl_sync(FULL, t == 0 ? u[0] : (t == 1 ? u[1] : u[2]), src);
+            const uint32_t cr = __shfl_sync(FULL, t == 0 ? c[0] : (t == 1 ? c[1] : c[2]), src);
+            uint32_t rep = NONE;
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const bool ok = ((repm[q] >> lane) & 1u) && umi_joins(u[q], c[q], ur, cr, max_dist);
+                const uint32_t m = __ballot_sync(FULL, ok);
+                if (rep == NONE && m) rep = __shfl_sync(FULL, d[q], __ffs(m) - 1);
+            }
+            if (rep == NONE) {
+                if (t == 0) repm[0] |= 1u << src; else if (t == 1) repm[1] |= 1u << src; else repm[2] |= 1u << src;
+            }
+            if (lane == src) {
+                const uint32_t mine = t == 0 ? d[0] : (t == 1 ? d[1] : d[2]);
+                const uint32_t v = rep == NONE ? mine : rep;
+                if (t == 0) res[0] = v; else if (t == 1) res[1] = v; else res[2] = v;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 3; t++)
+            if (32u * t + lane < gnd) du_rep[d[t]] = res[t];
     }
 }
 
@@ -228,79 +297,100 @@ __device__ __forceinline__ uint32_t umi_hash(uint32_t u, uint32_t bits)
     return (u * 0x9E3779B1u) >> (32u - bits);
 }
 
-struct LargeGroup {
-    uint32_t d0, nd, hbits;
-};
-
-__device__ __forceinline__ LargeGroup large_group_of(uint32_t d, const uint32_t *__restrict__ du_first,
-                                                     const uint32_t *__restrict__ grp_id,
-                                                     const uint32_t *__restrict__ grp_first)
+// per distinct UMI of a large group: x = UMI word, y = walk position in the group, z = reads,
+// w = group id.  One 16-byte load tells a prober whether a slot holds the neighbour it looks for
+// and whether that neighbour is eligible.
+__device__ __forceinline__ uint32_t large_hbits(uint32_t nd)
 {
-    const uint32_t g = grp_id[du_first[d]];
-    LargeGroup G;
-    G.d0 = grp_first[g];
-    G.nd = grp_first[g + 1] - G.d0;
-    G.hbits = 32u - (uint32_t)__clz((int)(2u * G.nd - 1u));   // smallest power of two >= 2 nd, of its 4 nd slots
-    return G;
+    return 32u - (uint32_t)__clz((int)(2u * nd - 1u));   // smallest power of two >= 2 nd, of the group's 4 nd slots
 }
 
 __global__ void __launch_bounds__(256)
 k_large_init(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ du_first,
              const uint32_t *__restrict__ grp_id, const uint32_t *__restrict__ grp_first,
              const uint32_t *__restrict__ totals, const uint32_t *__restrict__ order,
-             uint32_t *__restrict__ du_rep, uint32_t *__restrict__ pos, uint32_t *__restrict__ val,
-             uint32_t *__restrict__ htab, uint32_t *__restrict__ work, uint32_t *__restrict__ work_count)
+             uint32_t *__restrict__ du_rep, uint4 *__restrict__ rec, uint32_t *__restrict__ htab,
+             uint32_t *__restrict__ work, uint32_t *__restrict__ work_count)
 {
     constexpr uint32_t NONE = 0xFFFFFFFFu;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;      // global walk index
     if (i >= totals[0]) return;
     const uint32_t d = order[i];
-    const LargeGroup G = large_group_of(d, du_first, grp_id, grp_first);
-    if (G.nd <= NR_UMI_LARGE) return;
-    const uint32_t u = s_umi[du_first[d]];
-    pos[d] = i - G.d0;
-    val[d] = u;
+    const uint32_t f = du_first[d], g = grp_id[f];
+    const uint32_t d0 = grp_first[g], nd = grp_first[g + 1] - d0;
+    if (nd <= NR_UMI_LARGE) return;
+    const uint32_t u = s_umi[f];
+    rec[d] = make_uint4(u, i - d0, du_first[d + 1] - f, g);
     du_rep[d] = NONE;
-    uint32_t *tab = htab + 4ull * G.d0;
-    const uint32_t hmask = (1u << G.hbits) - 1u;
-    uint32_t slot = umi_hash(u, G.hbits);
+    uint32_t *tab = htab + 4ull * d0;
+    const uint32_t hbits = large_hbits(nd), hmask = (1u << hbits) - 1u;
+    uint32_t slot = umi_hash(u, hbits);
     while (atomicCAS(&tab[slot], NONE, d) != NONE) slot = (slot + 1u) & hmask;
     work[atomicAdd(work_count, 1u)] = d;
 }
 
-// one round for distinct UMI d of a large group; returns true when d is (now) decided
-__device__ __forceinline__ bool large_round(uint32_t d, const LargeGroup &G, uint32_t per,
-                                            const uint32_t *__restrict__ du_first,
-                                            uint32_t *__restrict__ du_rep,
-                                            const uint32_t *__restrict__ pos,
-                                            const uint32_t *__restrict__ val,
+// One round for the undecided UMI d, run by NR_UMI_LANES adjacent lanes (`sub` = lane within them;
+// the whole warp is converged here, lanes without an item pass valid = false).  Each lane looks up
+// every NR_UMI_LANES-th neighbour, all its table loads in flight together, then all the record
+// loads of the occupied slots; the few hits read the neighbour's state.  Returns true on lane 0
+// of the group when d is now decided.
+#define NR_UMI_LANES 8
+#define NR_UMI_PROBES 6       // per lane: NR_UMI_LANES * NR_UMI_PROBES >= 3 * 16 neighbours
+
+__device__ __forceinline__ bool large_round(uint32_t d, bool valid, uint32_t sub, uint32_t per,
+                                            const uint32_t *__restrict__ grp_first,
+                                            uint32_t *__restrict__ du_rep, const uint4 *__restrict__ rec,
                                             const uint32_t *__restrict__ htab)
 {
     constexpr uint32_t NONE = 0xFFFFFFFFu;
-    if (__ldcg(du_rep + d) != NONE) return true;
-    const uint32_t *tab = htab + 4ull * G.d0;
-    const uint32_t hmask = (1u << G.hbits) - 1u;
-    const uint32_t u = val[d], c = du_first[d + 1] - du_first[d], r = pos[d];
-    uint32_t rmin = NONE, rmin_d = NONE, qmin = NONE;
-    for (uint32_t k = 0; k < per; k++) {
-        const uint32_t key = u ^ ((k % 3u + 1u) << (2u * (k / 3u)));
-        uint32_t slot = umi_hash(key, G.hbits);
-        for (;;) {
-            const uint32_t dj = tab[slot];
-            if (dj == NONE) break;
-            if (val[dj] == key) {
-                const uint32_t pj = pos[dj];
-                if (pj < r && (du_first[dj + 1] - du_first[dj]) + 1 >= 2 * c) {
-                    const uint32_t st = __ldcg(du_rep + dj);
-                    if (st == dj) { if (pj < rmin) { rmin = pj; rmin_d = dj; } }
-                    else if (st == NONE) qmin = min(qmin, pj);
+    uint4 me = make_uint4(0, 0, 0, 0);
+    uint32_t d0 = 0, hbits = 1;
+    if (valid) {
+        me = __ldg(rec + d);
+        d0 = __ldg(grp_first + me.w);
+        hbits = large_hbits(__ldg(grp_first + me.w + 1) - d0);
+    }
+    const uint32_t *tab = htab + 4ull * d0;
+    const uint32_t hmask = (1u << hbits) - 1u;
+    uint32_t key[NR_UMI_PROBES], slot[NR_UMI_PROBES], dj[NR_UMI_PROBES];
+    uint4 rj[NR_UMI_PROBES];
+#pragma unroll
+    for (int j = 0; j < NR_UMI_PROBES; j++) {
+        const uint32_t k = sub + NR_UMI_LANES * j;
+        key[j] = me.x ^ ((k % 3u + 1u) << (2u * (k / 3u)));
+        slot[j] = umi_hash(key[j], hbits);
+        dj[j] = (valid && k < per) ? __ldg(tab + slot[j]) : NONE;
+    }
+#pragma unroll
+    for (int j = 0; j < NR_UMI_PROBES; j++)
+        if (dj[j] != NONE) rj[j] = __ldg(rec + dj[j]);
+    unsigned long long rbest = ~0ull;          // (position << 32 | distinct id) of the earliest representative
+    uint32_t qmin = NONE;                      // position of the earliest undecided eligible neighbour
+#pragma unroll
+    for (int j = 0; j < NR_UMI_PROBES; j++) {
+        uint32_t e = dj[j], sl = slot[j];
+        uint4 r = rj[j];
+        while (e != NONE) {
+            if (r.x == key[j]) {
+                if (r.y < me.y && r.z + 1 >= 2 * me.z) {
+                    const uint32_t st = __ldcg(du_rep + e);
+                    if (st == e) rbest = min(rbest, ((unsigned long long)r.y << 32) | e);
+                    else if (st == NONE) qmin = min(qmin, r.y);
                 }
                 break;
             }
-            slot = (slot + 1u) & hmask;
+            sl = (sl + 1u) & hmask;
+            e = __ldg(tab + sl);
+            if (e != NONE) r = __ldg(rec + e);
         }
     }
-    if (rmin != NONE && rmin < qmin) { __stcg(du_rep + d, rmin_d); return true; }
+#pragma unroll
+    for (int o = NR_UMI_LANES / 2; o > 0; o >>= 1) {
+        rbest = min(rbest, __shfl_xor_sync(0xffffffffu, rbest, o));
+        qmin = min(qmin, __shfl_xor_sync(0xffffffffu, qmin, o));
+    }
+    if (!valid || sub != 0) return false;
+    if (rbest != ~0ull && (uint32_t)(rbest >> 32) < qmin) { __stcg(du_rep + d, (uint32_t)rbest); return true; }
     if (qmin == NONE) { __stcg(du_rep + d, d); return true; }
     return false;
 }
@@ -308,13 +398,14 @@ __device__ __forceinline__ bool large_round(uint32_t d, const LargeGroup &G, uin
 // work_a / work_b: the undecided UMIs of this and the next round; count[3]: their lengths in
 // rotation (round r reads count[r % 3], appends to count[(r + 1) % 3], clears count[(r + 2) % 3])
 __global__ void __launch_bounds__(256)
-k_large_rounds(const uint32_t *__restrict__ du_first, const uint32_t *__restrict__ grp_id,
-               const uint32_t *__restrict__ grp_first, int umi_len, uint32_t *__restrict__ du_rep,
-               const uint32_t *__restrict__ pos, const uint32_t *__restrict__ val,
-               const uint32_t *__restrict__ htab, uint32_t *work_a, uint32_t *work_b, uint32_t *count)
+k_large_rounds(const uint32_t *__restrict__ grp_first, int umi_len, uint32_t *__restrict__ du_rep,
+               const uint4 *__restrict__ rec, const uint32_t *__restrict__ htab, uint32_t *work_a,
+               uint32_t *work_b, uint32_t *count)
 {
     cg::grid_group grid = cg::this_grid();
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t item0 = tid / NR_UMI_LANES, sub = tid % NR_UMI_LANES;
+    const uint32_t items = gridDim.x * blockDim.x / NR_UMI_LANES;
     const uint32_t per = 3u * (uint32_t)umi_len;
     for (uint32_t r = 0;; r++) {
         const uint32_t n_in = __ldcg(count + r % 3u);
@@ -322,11 +413,12 @@ k_large_rounds(const uint32_t *__restrict__ du_first, const uint32_t *__restrict
         if (tid == 0) __stcg(count + (r + 2u) % 3u, 0u);
         const uint32_t *in = (r & 1u) ? work_b : work_a;
         uint32_t *out = (r & 1u) ? work_a : work_b;
-        for (uint32_t i = tid; i < n_in; i += nthr) {
-            const uint32_t d = __ldcg(in + i);
-            const LargeGroup G = large_group_of(d, du_first, grp_id, grp_first);
-            if (!large_round(d, G, per, du_first, du_rep, pos, val, htab))
-                __stcg(out + atomicAdd(count + (r + 1u) % 3u, 1u), d);
+        for (uint32_t base = 0; base < n_in; base += items) {          // uniform trip count
+            const uint32_t i = base + item0;
+            const bool valid = i < n_in;
+            const uint32_t d = valid ? __ldcg(in + i) : 0u;
+            const bool done = large_round(d, valid, sub, per, grp_first, du_rep, rec, htab);
+            if (valid && sub == 0 && !done) __stcg(out + atomicAdd(count + (r + 1u) % 3u, 1u), d);
         }
         grid.sync();
     }
@@ -405,6 +497,18 @@ extern "C" int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_ge
     const unsigned nb = (unsigned)((n + T - 1) / T);
     const int N = (int)n;
 
+    // NR_UMI_TRACE=1: per-stage device times on stderr (synchronises; diagnosis only)
+    static const bool trace = getenv("NR_UMI_TRACE") != nullptr;
+    cudaEvent_t tev[8];
+    int ntev = 0;
+    const char *tname[8];
+    auto mark = [&](const char *stage) {          // `stage` starts here
+        if (!trace || ntev >= 8) return;
+        tname[ntev] = stage;
+        cudaEventCreate(&tev[ntev]);
+        cudaEventRecord(tev[ntev++], st);
+    };
+    mark("sorts");
     k_init<<<nb, T, 0, st>>>(d_umi, n, w.umi_a, w.idx_a);
     size_t need = 0;
     // all 32 bits of the UMI word: a caller may carry escape codes above bit 2 * umi_len (the host
@@ -426,6 +530,7 @@ extern "C" int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_ge
     tb = w.cub_bytes;
     NR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.key_a, w.key_b, w.idx_b, w.idx_a,
                                                   N, 0, 64, st));
+    mark("ids");
     // sorted order: key_b (barcode, gene), idx_a (source record)
     k_sorted<<<nb, T, 0, st>>>(w.key_b, d_umi, w.idx_a, n, w.s_bc, w.s_gene, w.s_umi, w.head_u,
                                w.head_g);
@@ -439,35 +544,46 @@ extern "C" int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_ge
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    mark("walk order");
     if (max_dist > 0) {
         // walk order for every group at once (key_a/key_b and umi_a are free again here)
-        k_order_keys<<<nb, T, 0, st>>>(w.du_first, w.grp_id, w.totals, n, w.key_a, w.umi_a);
+        int cb = 1;
+        while ((n >> cb) != 0) cb++;                     // n < 2^cb: reads (>= 1) and group ids fit
+        k_order_keys<<<nb, T, 0, st>>>(w.du_first, w.grp_id, w.totals, n, cb, w.key_a, w.umi_a);
         tb = w.cub_bytes;
         NR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.key_a, w.key_b, w.umi_a,
-                                                      w.du_rank_order, N, 0, 64, st));
+                                                      w.du_rank_order, N, 0, 2 * cb, st));
     }
-    k_cluster_small<<<sms * 8, 256, 0, st>>>(w.s_umi, w.du_first, w.grp_first, w.totals, max_dist,
-                                             w.du_rank_order, w.du_rep);
-    if (max_dist > 0) {
+    mark("small groups");
+    if (max_dist <= 0) {
+        k_self<<<nb, T, 0, st>>>(w.totals, w.du_rep);
+    } else {
+        // totals[8..10]: work-list lengths of the large-group rounds, totals[11]: medium groups
+        uint32_t *count = w.totals + 8, *work_a = w.rep_u, *work_b = w.rep_c;
+        NR_CHECK_CUDA(cudaMemsetAsync(count, 0, 16, st));
+        k_cluster_tiny<<<sms * 8, 256, 0, st>>>(w.s_umi, w.du_first, w.grp_first, w.totals, max_dist,
+                                                w.du_rank_order, w.du_rep, work_b, count + 3);
+        k_cluster_medium<<<sms * 8, 256, 0, st>>>(w.s_umi, w.du_first, w.grp_first, max_dist,
+                                                  w.du_rank_order, w.du_rep, work_b, count + 3);
+        mark("large: table + list");
         NR_CHECK_CUDA(cudaMemsetAsync(w.htab, 0xFF, (size_t)(n + 1) * 16, st));
-        // large groups: hash sets and work list, then the rounds (key_a / key_b are free again)
-        uint32_t *count = w.totals + 8, *work_a = (uint32_t *)w.key_a, *work_b = (uint32_t *)w.key_b;
-        NR_CHECK_CUDA(cudaMemsetAsync(count, 0, 12, st));
+        // large groups: hash sets and work list, then the rounds
         k_large_init<<<nb, T, 0, st>>>(w.s_umi, w.du_first, w.grp_id, w.grp_first, w.totals,
-                                       w.du_rank_order, w.du_rep, w.rep_u, w.rep_c, w.htab, work_a, count);
+                                       w.du_rank_order, w.du_rep, w.rec, w.htab, work_a, count);
+        mark("large: rounds");
         int per_sm = 0;
         NR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_large_rounds, 256, 0));
         if (per_sm < 1) {
             nr_set_error("nr_umi_collapse_device: k_large_rounds does not fit an SM");
             return NR_ECUDA;
         }
-        const uint32_t *c_first = w.du_first, *c_gid = w.grp_id, *c_gfirst = w.grp_first;
-        const uint32_t *c_pos = w.rep_u, *c_val = w.rep_c, *c_tab = w.htab;
-        void *args[] = {&c_first, &c_gid, &c_gfirst, &umi_len, &w.du_rep, &c_pos, &c_val, &c_tab,
-                        &work_a, &work_b, &count};
-        NR_CHECK_CUDA(cudaLaunchCooperativeKernel((void *)k_large_rounds, dim3(sms * std::min(per_sm, 4)),
+        const uint32_t *c_gfirst = w.grp_first, *c_tab = w.htab;
+        const uint4 *c_rec = w.rec;
+        void *args[] = {&c_gfirst, &umi_len, &w.du_rep, &c_rec, &c_tab, &work_a, &work_b, &count};
+        NR_CHECK_CUDA(cudaLaunchCooperativeKernel((void *)k_large_rounds, dim3(sms * std::min(per_sm, 6)),
                                                   dim3(256), args, 0, st));
     }
+    mark("emit");
     NR_CHECK_CUDA(cudaMemsetAsync(w.rep_reads, 0, (size_t)(n + 1) * 4, st));
     k_rep_reads<<<sms * 8, 256, 0, st>>>(w.du_first, w.du_rep, w.totals, w.rep_reads, w.rep_flag);
     // rep_flag is defined for the first n_distinct entries only; the scan also runs over the
@@ -479,5 +595,19 @@ extern "C" int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_ge
                                     d_n_groups);
     k_scatter_rep<<<nb, T, 0, st>>>(w.idx_a, w.du_id, w.du_rep, w.du_first, w.s_umi, n, d_rep_umi);
     NR_CHECK_CUDA(cudaGetLastError());
+    if (trace) {
+        const int last = ntev;
+        cudaEvent_t end;
+        cudaEventCreate(&end);
+        cudaEventRecord(end, st);
+        cudaEventSynchronize(end);
+        for (int i = 0; i < last; i++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, tev[i], i + 1 < last ? tev[i + 1] : end);
+            fprintf(stderr, "[nr_umi] %-28s %8.1f us\n", tname[i], ms * 1e3f);
+            cudaEventDestroy(tev[i]);
+        }
+        cudaEventDestroy(end);
+    }
     return NR_OK;
 }

@@ -41,13 +41,16 @@ d = [torch.from_numpy(a.view(np.int32)).to(dev) for a in (cell, gene, umi)]
 for md in (1, 0):
     r = U.collapse_device(*d, 12, md)
     torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    ev[0].record()
-    for _ in range(5):
+    ts = []
+    for _ in range(20):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
         r = U.collapse_device(*d, 12, md)
-    ev[1].record()
-    torch.cuda.synchronize()
-    print(f"max_dist {md}: {ev[0].elapsed_time(ev[1]) / 5:.3f} ms per collapse, {r['n_groups']} molecules", flush=True)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ts.append(ev[0].elapsed_time(ev[1]))
+    print(f"max_dist {md}: median {np.median(ts):.3f} ms, min {min(ts):.3f} ms per collapse (20 runs), "
+          f"{r['n_groups']} molecules", flush=True)
     if check and md == 1:
         sys.path.insert(0, ROOT)
         from oracle import oracle as O
