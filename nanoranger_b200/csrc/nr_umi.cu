@@ -12,7 +12,7 @@
 // Pipeline (all on `stream`, no host synchronisation):
 //   1  LSD radix sort: by umi (2 * umi_len bits), then stable by (barcode << 32 | gene)
 //   2  head flags + scans -> distinct-UMI ids, group ids; run lengths -> reads per distinct UMI
-//   3  small groups: one warp (or block) walks the distinct UMIs in rank order and picks the
+//   3  small groups: one thread / one warp ranks the distinct UMIs, walks them and picks the
 //      representatives; large groups: hash sets + parallel rounds over the whole grid (below)
 //   4  reads per representative, compaction of the representatives into the group table,
 //      scatter of the representative UMI back to input order
@@ -34,7 +34,6 @@ struct UmiWs {
     uint32_t *du_id, *grp_id;              // per sorted record
     uint32_t *du_first;                    // per distinct: first sorted position (+ sentinel)
     uint32_t *grp_first;                   // per group: first distinct id (+ sentinel)
-    uint32_t *du_rank_order;               // per distinct: distinct ids of its group in walk order
     uint32_t *du_rep;                      // per distinct: distinct id of its representative
     uint32_t *rep_reads;                   // per distinct: reads of the cluster it represents
     uint32_t *rep_flag, *rep_pos;          // per distinct
@@ -55,7 +54,7 @@ size_t carve(uint8_t *base, uint64_t n, UmiWs *w, size_t cub_bytes)
     size_t n4 = (size_t)(n + 1) * 4, n8 = (size_t)(n + 1) * 8;
     uint32_t **a32[] = {&w->umi_a, &w->umi_b, &w->idx_a, &w->idx_b, &w->s_bc, &w->s_gene, &w->s_umi,
                         &w->head_u, &w->head_g, &w->du_id, &w->grp_id, &w->du_first,
-                        &w->grp_first, &w->du_rank_order, &w->du_rep, &w->rep_reads,
+                        &w->grp_first, &w->du_rep, &w->rep_reads,
                         &w->rep_flag, &w->rep_pos, &w->rep_u, &w->rep_c};
     for (auto p : a32) *p = (uint32_t *)take(n4);
     w->htab = (uint32_t *)take(4 * n4);
@@ -132,23 +131,9 @@ __device__ __forceinline__ int hamming_2bit(uint32_t a, uint32_t b)
     return __popc(x);
 }
 
-// walk order of the distinct UMIs of every group: (reads desc, umi asc).  Distinct ids are
-// umi-ascending inside a group, so a STABLE sort by (group, n - reads) gives it for all groups at
-// once.  Both fields are < 2^cb (cb = bits of n), so the sort runs over 2 cb bits, not 64.
-__global__ void k_order_keys(const uint32_t *du_first, const uint32_t *grp_id, const uint32_t *totals,
-                             uint64_t n, int cb, uint64_t *key, uint32_t *val)
-{
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint64_t k = ~0ull;                      // past the last distinct UMI: sorts behind everything
-    if (i < totals[0]) {
-        uint32_t f = du_first[i];
-        k = ((uint64_t)grp_id[f] << cb) | (uint64_t)(n - (du_first[i + 1] - f));
-    }
-    key[i] = k;
-    val[i] = (uint32_t)i;
-}
-
+// Walk order of the distinct UMIs of a group: (reads desc, umi asc).  Distinct ids are
+// umi-ascending inside a group, so "a is walked before b" <=> reads(a) > reads(b), or the reads are
+// equal and id(a) < id(b): no kernel needs the order materialised.
 #define NR_UMI_LARGE 96      // groups with more distinct UMIs go to the hash-set rounds
 
 __device__ __forceinline__ bool umi_joins(uint32_t rep_umi, uint32_t rep_cnt, uint32_t u,
@@ -165,20 +150,21 @@ __global__ void k_self(const uint32_t *__restrict__ totals, uint32_t *__restrict
 }
 
 // Small (barcode, gene) groups, sequential walk.  Nearly every group of a gene-expression library
-// has a handful of distinct UMIs: up to NR_UMI_TINY are walked by ONE thread in registers (all
-// loads of the group in flight together).  Groups of up to NR_UMI_LARGE = 3 x 32 go onto a list
-// (they cluster in the deeply sequenced cells: the list spreads them over the grid) and are
-// walked by one warp each out of registers: lane l holds walk positions l, 32 + l, 64 + l; a step
-// broadcasts the UMI at position r and every lane compares it with the representatives among its
-// own positions (all earlier than r by construction); the lowest position that accepts it wins.
-// No memory access inside the walk.
+// has a handful of distinct UMIs: up to NR_UMI_TINY are ranked and walked by ONE thread in
+// registers (all loads of the group in flight together).  Groups of up to NR_UMI_LARGE = 3 x 32 go
+// onto a list (they cluster in the deeply sequenced cells: the list spreads them over the grid)
+// and are walked by one warp each: the lanes rank the UMIs against each other, a pass through
+// shared memory puts them in walk order, lane l then holds walk positions l, 32 + l, 64 + l; a
+// step broadcasts the UMI at position r and every lane compares it with the representatives
+// among its own positions (all earlier than r by construction); the lowest position that accepts
+// it wins.  No global memory access inside the walk.
 #define NR_UMI_TINY 8
 
 __global__ void __launch_bounds__(256)
 k_cluster_tiny(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ du_first,
                const uint32_t *__restrict__ grp_first, const uint32_t *__restrict__ totals,
-               int max_dist, const uint32_t *__restrict__ order, uint32_t *__restrict__ du_rep,
-               uint32_t *__restrict__ medium, uint32_t *__restrict__ medium_count)
+               int max_dist, uint32_t *__restrict__ du_rep, uint32_t *__restrict__ medium,
+               uint32_t *__restrict__ medium_count)
 {
     const uint32_t n_groups = totals[1];
     const uint32_t nthr = gridDim.x * blockDim.x;
@@ -189,60 +175,94 @@ k_cluster_tiny(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ 
             medium[atomicAdd(medium_count, 1u)] = g;
             continue;
         }
-        uint32_t d[NR_UMI_TINY], f[NR_UMI_TINY], u[NR_UMI_TINY], c[NR_UMI_TINY];
-#pragma unroll
-        for (int r = 0; r < NR_UMI_TINY; r++) d[r] = (uint32_t)r < nd ? order[d0 + r] : 0u;
-#pragma unroll
-        for (int r = 0; r < NR_UMI_TINY; r++) {
-            f[r] = (uint32_t)r < nd ? du_first[d[r]] : 0u;
-            c[r] = (uint32_t)r < nd ? du_first[d[r] + 1] : 0u;
+        if (nd == 1) {
+            du_rep[d0] = d0;
+            continue;
         }
+        uint32_t f[NR_UMI_TINY + 1], u[NR_UMI_TINY], c[NR_UMI_TINY], rank[NR_UMI_TINY];
+#pragma unroll
+        for (int r = 0; r <= NR_UMI_TINY; r++) f[r] = (uint32_t)r <= nd ? du_first[d0 + r] : 0u;
 #pragma unroll
         for (int r = 0; r < NR_UMI_TINY; r++) {
             u[r] = (uint32_t)r < nd ? s_umi[f[r]] : 0u;
-            c[r] -= f[r];
+            c[r] = (uint32_t)r < nd ? f[r + 1] - f[r] : 0u;       // absent: 0 reads, ranked last
         }
-        uint32_t reps = 0;
 #pragma unroll
         for (int r = 0; r < NR_UMI_TINY; r++) {
-            if ((uint32_t)r >= nd) break;
-            uint32_t rep = d[r];
-            bool found = false;
+            uint32_t k = 0;
 #pragma unroll
-            for (int q = 0; q < r; q++)
-                if (!found && ((reps >> q) & 1u) && umi_joins(u[q], c[q], u[r], c[r], max_dist)) {
-                    rep = d[q];
-                    found = true;
+            for (int q = 0; q < NR_UMI_TINY; q++)
+                k += (c[q] > c[r] || (c[q] == c[r] && q < r)) ? 1u : 0u;
+            rank[r] = k;
+        }
+        uint32_t reps = 0;
+        for (uint32_t step = 0; step < nd; step++) {
+            uint32_t ue = 0, ce = 0, e = 0;
+#pragma unroll
+            for (int r = 0; r < NR_UMI_TINY; r++)
+                if (rank[r] == step) { ue = u[r]; ce = c[r]; e = (uint32_t)r; }
+            uint32_t best = NR_UMI_TINY, rep = e;
+#pragma unroll
+            for (int q = 0; q < NR_UMI_TINY; q++)
+                if (((reps >> q) & 1u) && rank[q] < best && umi_joins(u[q], c[q], ue, ce, max_dist)) {
+                    best = rank[q];
+                    rep = (uint32_t)q;
                 }
-            if (!found) reps |= 1u << r;
-            du_rep[d[r]] = rep;
+            if (rep == e) reps |= 1u << e;
+            du_rep[d0 + e] = d0 + rep;
         }
     }
 }
 
 __global__ void __launch_bounds__(256)
 k_cluster_medium(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ du_first,
-                 const uint32_t *__restrict__ grp_first, int max_dist,
-                 const uint32_t *__restrict__ order, uint32_t *__restrict__ du_rep,
+                 const uint32_t *__restrict__ grp_first, int max_dist, uint32_t *__restrict__ du_rep,
                  const uint32_t *__restrict__ medium, const uint32_t *__restrict__ medium_count)
 {
     constexpr uint32_t FULL = 0xffffffffu, NONE = 0xFFFFFFFFu;
-    const uint32_t lane = threadIdx.x & 31u;
+    __shared__ uint32_t s_walk[8][3][NR_UMI_LARGE];        // per warp: id, UMI, reads by walk position
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     const uint32_t n_medium = *medium_count;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_medium; i += warps) {
         const uint32_t g = medium[i];
         const uint32_t gd0 = grp_first[g], gnd = grp_first[g + 1] - gd0;
         uint32_t d[3], u[3], c[3], res[3], repm[3] = {0u, 0u, 0u};
+        // by id (= UMI ascending): lane l holds ids gd0 + l, + 32, + 64
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            const uint32_t e = 32u * t + lane;
+            u[t] = c[t] = 0u;
+            if (e < gnd) {
+                const uint32_t f = du_first[gd0 + e];
+                c[t] = du_first[gd0 + e + 1] - f;
+                u[t] = s_umi[f];
+            }
+        }
+        uint32_t rank[3] = {0u, 0u, 0u};
+        for (uint32_t j = 0; j < gnd; j++) {
+            const uint32_t tj = j >> 5;
+            const uint32_t cj = __shfl_sync(FULL, tj == 0 ? c[0] : (tj == 1 ? c[1] : c[2]), j & 31u);
+#pragma unroll
+            for (int t = 0; t < 3; t++) rank[t] += (cj > c[t] || (cj == c[t] && j < 32u * t + lane)) ? 1u : 0u;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 3; t++)
+            if (32u * t + lane < gnd) {
+                s_walk[wib][0][rank[t]] = gd0 + 32u * t + lane;
+                s_walk[wib][1][rank[t]] = u[t];
+                s_walk[wib][2][rank[t]] = c[t];
+            }
+        __syncwarp();
 #pragma unroll
         for (int t = 0; t < 3; t++) {
             const uint32_t r = 32u * t + lane;
             d[t] = u[t] = c[t] = res[t] = 0u;
             if (r < gnd) {
-                d[t] = order[gd0 + r];
-                const uint32_t f = du_first[d[t]];
-                c[t] = du_first[d[t] + 1] - f;
-                u[t] = s_umi[f];
+                d[t] = s_walk[wib][0][r];
+                u[t] = s_walk[wib][1][r];
+                c[t] = s_walk[wib][2][r];
             }
         }
         for (uint32_t r = 0; r < gnd; r++) {
@@ -277,7 +297,7 @@ k_cluster_medium(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict_
 // neighbours at earlier walk positions, and a UMI of len bases has 3 * len neighbours.  So:
 //   init    every distinct UMI of a large group goes into the group's hash set (UMI -> distinct id)
 //           and is marked undecided;
-//   rounds  one cooperative launch filling the GPU; thread = one undecided UMI of the work list:
+//   rounds  one cooperative launch filling the GPU; 8 lanes = one undecided UMI of the work list:
 //           look the 3 * len neighbours up; among the eligible ones at earlier positions let r =
 //           earliest representative, q = earliest undecided.  r < q: join r (everything before r
 //           is known not to be a representative).  No undecided and no representative: become a
@@ -297,9 +317,9 @@ __device__ __forceinline__ uint32_t umi_hash(uint32_t u, uint32_t bits)
     return (u * 0x9E3779B1u) >> (32u - bits);
 }
 
-// per distinct UMI of a large group: x = UMI word, y = walk position in the group, z = reads,
-// w = group id.  One 16-byte load tells a prober whether a slot holds the neighbour it looks for
-// and whether that neighbour is eligible.
+// rec[], per distinct UMI of a large group: x = UMI word, y = reads, z = group id.  One 16-byte
+// load tells a prober whether a slot holds the neighbour it looks for, whether that neighbour is
+// eligible and whether it is walked earlier.
 __device__ __forceinline__ uint32_t large_hbits(uint32_t nd)
 {
     return 32u - (uint32_t)__clz((int)(2u * nd - 1u));   // smallest power of two >= 2 nd, of the group's 4 nd slots
@@ -308,19 +328,18 @@ __device__ __forceinline__ uint32_t large_hbits(uint32_t nd)
 __global__ void __launch_bounds__(256)
 k_large_init(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ du_first,
              const uint32_t *__restrict__ grp_id, const uint32_t *__restrict__ grp_first,
-             const uint32_t *__restrict__ totals, const uint32_t *__restrict__ order,
+             const uint32_t *__restrict__ totals,
              uint32_t *__restrict__ du_rep, uint4 *__restrict__ rec, uint32_t *__restrict__ htab,
              uint32_t *__restrict__ work, uint32_t *__restrict__ work_count)
 {
     constexpr uint32_t NONE = 0xFFFFFFFFu;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;      // global walk index
-    if (i >= totals[0]) return;
-    const uint32_t d = order[i];
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= totals[0]) return;
     const uint32_t f = du_first[d], g = grp_id[f];
     const uint32_t d0 = grp_first[g], nd = grp_first[g + 1] - d0;
     if (nd <= NR_UMI_LARGE) return;
     const uint32_t u = s_umi[f];
-    rec[d] = make_uint4(u, i - d0, du_first[d + 1] - f, g);
+    rec[d] = make_uint4(u, du_first[d + 1] - f, g, 0u);
     du_rep[d] = NONE;
     uint32_t *tab = htab + 4ull * d0;
     const uint32_t hbits = large_hbits(nd), hmask = (1u << hbits) - 1u;
@@ -347,8 +366,8 @@ __device__ __forceinline__ bool large_round(uint32_t d, bool valid, uint32_t sub
     uint32_t d0 = 0, hbits = 1;
     if (valid) {
         me = __ldg(rec + d);
-        d0 = __ldg(grp_first + me.w);
-        hbits = large_hbits(__ldg(grp_first + me.w + 1) - d0);
+        d0 = __ldg(grp_first + me.z);
+        hbits = large_hbits(__ldg(grp_first + me.z + 1) - d0);
     }
     const uint32_t *tab = htab + 4ull * d0;
     const uint32_t hmask = (1u << hbits) - 1u;
@@ -364,18 +383,22 @@ __device__ __forceinline__ bool large_round(uint32_t d, bool valid, uint32_t sub
 #pragma unroll
     for (int j = 0; j < NR_UMI_PROBES; j++)
         if (dj[j] != NONE) rj[j] = __ldg(rec + dj[j]);
-    unsigned long long rbest = ~0ull;          // (position << 32 | distinct id) of the earliest representative
-    uint32_t qmin = NONE;                      // position of the earliest undecided eligible neighbour
+    // walk-order keys (~reads << 32 | distinct id; smaller = earlier) of the earliest representative
+    // and of the earliest undecided UMI among the eligible neighbours walked before d
+    constexpr unsigned long long LAST = ~0ull;
+    const unsigned long long mine = ((unsigned long long)(~me.y) << 32) | d;
+    unsigned long long rbest = LAST, qmin = LAST;
 #pragma unroll
     for (int j = 0; j < NR_UMI_PROBES; j++) {
         uint32_t e = dj[j], sl = slot[j];
         uint4 r = rj[j];
         while (e != NONE) {
             if (r.x == key[j]) {
-                if (r.y < me.y && r.z + 1 >= 2 * me.z) {
+                const unsigned long long theirs = ((unsigned long long)(~r.y) << 32) | e;
+                if (theirs < mine && r.y + 1 >= 2 * me.y) {
                     const uint32_t st = __ldcg(du_rep + e);
-                    if (st == e) rbest = min(rbest, ((unsigned long long)r.y << 32) | e);
-                    else if (st == NONE) qmin = min(qmin, r.y);
+                    if (st == e) rbest = min(rbest, theirs);
+                    else if (st == NONE) qmin = min(qmin, theirs);
                 }
                 break;
             }
@@ -390,8 +413,8 @@ __device__ __forceinline__ bool large_round(uint32_t d, bool valid, uint32_t sub
         qmin = min(qmin, __shfl_xor_sync(0xffffffffu, qmin, o));
     }
     if (!valid || sub != 0) return false;
-    if (rbest != ~0ull && (uint32_t)(rbest >> 32) < qmin) { __stcg(du_rep + d, (uint32_t)rbest); return true; }
-    if (qmin == NONE) { __stcg(du_rep + d, d); return true; }
+    if (rbest < qmin) { __stcg(du_rep + d, (uint32_t)rbest); return true; }
+    if (qmin == LAST) { __stcg(du_rep + d, d); return true; }
     return false;
 }
 
@@ -544,16 +567,6 @@ extern "C" int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_ge
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    mark("walk order");
-    if (max_dist > 0) {
-        // walk order for every group at once (key_a/key_b and umi_a are free again here)
-        int cb = 1;
-        while ((n >> cb) != 0) cb++;                     // n < 2^cb: reads (>= 1) and group ids fit
-        k_order_keys<<<nb, T, 0, st>>>(w.du_first, w.grp_id, w.totals, n, cb, w.key_a, w.umi_a);
-        tb = w.cub_bytes;
-        NR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.key_a, w.key_b, w.umi_a,
-                                                      w.du_rank_order, N, 0, 2 * cb, st));
-    }
     mark("small groups");
     if (max_dist <= 0) {
         k_self<<<nb, T, 0, st>>>(w.totals, w.du_rep);
@@ -562,14 +575,14 @@ extern "C" int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_ge
         uint32_t *count = w.totals + 8, *work_a = w.rep_u, *work_b = w.rep_c;
         NR_CHECK_CUDA(cudaMemsetAsync(count, 0, 16, st));
         k_cluster_tiny<<<sms * 8, 256, 0, st>>>(w.s_umi, w.du_first, w.grp_first, w.totals, max_dist,
-                                                w.du_rank_order, w.du_rep, work_b, count + 3);
+                                                w.du_rep, work_b, count + 3);
         k_cluster_medium<<<sms * 8, 256, 0, st>>>(w.s_umi, w.du_first, w.grp_first, max_dist,
-                                                  w.du_rank_order, w.du_rep, work_b, count + 3);
+                                                  w.du_rep, work_b, count + 3);
         mark("large: table + list");
         NR_CHECK_CUDA(cudaMemsetAsync(w.htab, 0xFF, (size_t)(n + 1) * 16, st));
         // large groups: hash sets and work list, then the rounds
         k_large_init<<<nb, T, 0, st>>>(w.s_umi, w.du_first, w.grp_id, w.grp_first, w.totals,
-                                       w.du_rank_order, w.du_rep, w.rec, w.htab, work_a, count);
+                                       w.du_rep, w.rec, w.htab, work_a, count);
         mark("large: rounds");
         int per_sm = 0;
         NR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_large_rounds, 256, 0));
