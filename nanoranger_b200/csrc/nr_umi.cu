@@ -214,80 +214,110 @@ k_cluster_tiny(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ 
     }
 }
 
+// the walk of one medium group by one warp; NS = 32-lane slots in use (1..3), uniform per warp
+template <int NS>
+__device__ __forceinline__ void medium_walk(uint32_t gd0, uint32_t gnd, const uint32_t (&u_id)[3],
+                                            const uint32_t (&c_id)[3], int max_dist, uint32_t lane,
+                                            uint32_t (*s_walk)[NR_UMI_LARGE], uint32_t *__restrict__ du_rep)
+{
+    constexpr uint32_t FULL = 0xffffffffu, NONE = 0xFFFFFFFFu;
+    auto pick = [](const uint32_t (&a)[NS], uint32_t t) {
+        uint32_t v = a[0];
+#pragma unroll
+        for (int q = 1; q < NS; q++) v = t == (uint32_t)q ? a[q] : v;
+        return v;
+    };
+    uint32_t d[NS], u[NS], c[NS], res[NS], repm[NS], rank[NS];
+#pragma unroll
+    for (int t = 0; t < NS; t++) { u[t] = u_id[t]; c[t] = c_id[t]; rank[t] = 0u; repm[t] = 0u; }
+    for (uint32_t j = 0; j < gnd; j++) {
+        const uint32_t cj = __shfl_sync(FULL, pick(c, j >> 5), j & 31u);
+#pragma unroll
+        for (int t = 0; t < NS; t++) rank[t] += (cj > c[t] || (cj == c[t] && j < 32u * t + lane)) ? 1u : 0u;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < NS; t++)
+        if (32u * t + lane < gnd) {
+            s_walk[0][rank[t]] = gd0 + 32u * t + lane;
+            s_walk[1][rank[t]] = u[t];
+            s_walk[2][rank[t]] = c[t];
+        }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < NS; t++) {
+        const uint32_t r = 32u * t + lane;
+        d[t] = u[t] = c[t] = res[t] = 0u;
+        if (r < gnd) {
+            d[t] = s_walk[0][r];
+            u[t] = s_walk[1][r];
+            c[t] = s_walk[2][r];
+        }
+    }
+    for (uint32_t r = 0; r < gnd; r++) {
+        const uint32_t t = r >> 5, src = r & 31u;
+        const uint32_t ur = __shfl_sync(FULL, pick(u, t), src);
+        const uint32_t cr = __shfl_sync(FULL, pick(c, t), src);
+        uint32_t rep = NONE;
+#pragma unroll
+        for (int q = 0; q < NS; q++) {
+            const bool ok = ((repm[q] >> lane) & 1u) && umi_joins(u[q], c[q], ur, cr, max_dist);
+            const uint32_t m = __ballot_sync(FULL, ok);
+            if (rep == NONE && m) rep = __shfl_sync(FULL, d[q], __ffs(m) - 1);
+        }
+#pragma unroll
+        for (int q = 0; q < NS; q++) {
+            if (rep == NONE && t == (uint32_t)q) repm[q] |= 1u << src;
+            if (lane == src && t == (uint32_t)q) res[q] = rep == NONE ? d[q] : rep;
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < NS; t++)
+        if (32u * t + lane < gnd) du_rep[d[t]] = res[t];
+}
+
 __global__ void __launch_bounds__(256)
 k_cluster_medium(const uint32_t *__restrict__ s_umi, const uint32_t *__restrict__ du_first,
                  const uint32_t *__restrict__ grp_first, int max_dist, uint32_t *__restrict__ du_rep,
                  const uint32_t *__restrict__ medium, const uint32_t *__restrict__ medium_count)
 {
-    constexpr uint32_t FULL = 0xffffffffu, NONE = 0xFFFFFFFFu;
     __shared__ uint32_t s_walk[8][3][NR_UMI_LARGE];        // per warp: id, UMI, reads by walk position
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     const uint32_t n_medium = *medium_count;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_medium; i += warps) {
+    // by id (= UMI ascending): lane l holds ids gd0 + l, + 32, + 64; the next group's loads are
+    // issued before the current group is walked
+    auto fetch = [&](uint32_t i, uint32_t &gd0, uint32_t &gnd, uint32_t (&u)[3], uint32_t (&c)[3]) {
+        gd0 = gnd = 0u;
+#pragma unroll
+        for (int t = 0; t < 3; t++) u[t] = c[t] = 0u;
+        if (i >= n_medium) return;
         const uint32_t g = medium[i];
-        const uint32_t gd0 = grp_first[g], gnd = grp_first[g + 1] - gd0;
-        uint32_t d[3], u[3], c[3], res[3], repm[3] = {0u, 0u, 0u};
-        // by id (= UMI ascending): lane l holds ids gd0 + l, + 32, + 64
+        gd0 = grp_first[g];
+        gnd = grp_first[g + 1] - gd0;
 #pragma unroll
         for (int t = 0; t < 3; t++) {
             const uint32_t e = 32u * t + lane;
-            u[t] = c[t] = 0u;
             if (e < gnd) {
                 const uint32_t f = du_first[gd0 + e];
                 c[t] = du_first[gd0 + e + 1] - f;
                 u[t] = s_umi[f];
             }
         }
-        uint32_t rank[3] = {0u, 0u, 0u};
-        for (uint32_t j = 0; j < gnd; j++) {
-            const uint32_t tj = j >> 5;
-            const uint32_t cj = __shfl_sync(FULL, tj == 0 ? c[0] : (tj == 1 ? c[1] : c[2]), j & 31u);
+    };
+    uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t gd0, gnd, u[3], c[3];
+    fetch(i, gd0, gnd, u, c);
+    while (i < n_medium) {
+        uint32_t n_gd0, n_gnd, n_u[3], n_c[3];
+        fetch(i + warps, n_gd0, n_gnd, n_u, n_c);
+        if (gnd <= 32) medium_walk<1>(gd0, gnd, u, c, max_dist, lane, s_walk[wib], du_rep);
+        else if (gnd <= 64) medium_walk<2>(gd0, gnd, u, c, max_dist, lane, s_walk[wib], du_rep);
+        else medium_walk<3>(gd0, gnd, u, c, max_dist, lane, s_walk[wib], du_rep);
+        i += warps;
+        gd0 = n_gd0; gnd = n_gnd;
 #pragma unroll
-            for (int t = 0; t < 3; t++) rank[t] += (cj > c[t] || (cj == c[t] && j < 32u * t + lane)) ? 1u : 0u;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < 3; t++)
-            if (32u * t + lane < gnd) {
-                s_walk[wib][0][rank[t]] = gd0 + 32u * t + lane;
-                s_walk[wib][1][rank[t]] = u[t];
-                s_walk[wib][2][rank[t]] = c[t];
-            }
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < 3; t++) {
-            const uint32_t r = 32u * t + lane;
-            d[t] = u[t] = c[t] = res[t] = 0u;
-            if (r < gnd) {
-                d[t] = s_walk[wib][0][r];
-                u[t] = s_walk[wib][1][r];
-                c[t] = s_walk[wib][2][r];
-            }
-        }
-        for (uint32_t r = 0; r < gnd; r++) {
-            const uint32_t t = r >> 5, src = r & 31u;
-            const uint32_t ur = __shfl_sync(FULL, t == 0 ? u[0] : (t == 1 ? u[1] : u[2]), src);
-            const uint32_t cr = __shfl_sync(FULL, t == 0 ? c[0] : (t == 1 ? c[1] : c[2]), src);
-            uint32_t rep = NONE;
-#pragma unroll
-            for (int q = 0; q < 3; q++) {
-                const bool ok = ((repm[q] >> lane) & 1u) && umi_joins(u[q], c[q], ur, cr, max_dist);
-                const uint32_t m = __ballot_sync(FULL, ok);
-                if (rep == NONE && m) rep = __shfl_sync(FULL, d[q], __ffs(m) - 1);
-            }
-            if (rep == NONE) {
-                if (t == 0) repm[0] |= 1u << src; else if (t == 1) repm[1] |= 1u << src; else repm[2] |= 1u << src;
-            }
-            if (lane == src) {
-                const uint32_t mine = t == 0 ? d[0] : (t == 1 ? d[1] : d[2]);
-                const uint32_t v = rep == NONE ? mine : rep;
-                if (t == 0) res[0] = v; else if (t == 1) res[1] = v; else res[2] = v;
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < 3; t++)
-            if (32u * t + lane < gnd) du_rep[d[t]] = res[t];
+        for (int t = 0; t < 3; t++) { u[t] = n_u[t]; c[t] = n_c[t]; }
     }
 }
 
@@ -567,7 +597,7 @@ extern "C" int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_ge
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    mark("small groups");
+    mark("tiny groups");
     if (max_dist <= 0) {
         k_self<<<nb, T, 0, st>>>(w.totals, w.du_rep);
     } else {
@@ -576,6 +606,7 @@ extern "C" int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_ge
         NR_CHECK_CUDA(cudaMemsetAsync(count, 0, 16, st));
         k_cluster_tiny<<<sms * 8, 256, 0, st>>>(w.s_umi, w.du_first, w.grp_first, w.totals, max_dist,
                                                 w.du_rep, work_b, count + 3);
+        mark("medium groups");
         k_cluster_medium<<<sms * 8, 256, 0, st>>>(w.s_umi, w.du_first, w.grp_first, max_dist,
                                                   w.du_rep, work_b, count + 3);
         mark("large: table + list");
