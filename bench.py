@@ -348,7 +348,8 @@ def measure_kinnex(args, ctx, batch, steps, warmup):
             mark(3)
             mark(4)
             bc, gene_r, umi_r = rec["bc"], rec["gene"], rec["umi"]
-        r = U.collapse_device(bc, gene_r, umi_r, 12, args.max_dist)
+        r = U.collapse_device(bc, gene_r, umi_r, 12, args.max_dist, bc_bits=U.key_bits(n_cells),
+                              gene_bits=U.key_bits(n_genes), umi_bits=24)
         mark(5)
         info.update(n_records=rec["n_records"], n_groups=r["n_groups"], short=rec["n_short_umi"],
                     received=int(bc.numel()))

@@ -136,6 +136,18 @@ int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_gene, const u
                            uint64_t *d_n_groups, uint32_t *d_g_bc, uint32_t *d_g_gene,
                            uint32_t *d_g_umi, uint32_t *d_g_reads, void *d_workspace,
                            size_t workspace_bytes, void *stream);
+/* The same with declared key widths: every barcode idx < 2^bc_bits, gene id < 2^gene_bits, UMI
+ * word < 2^umi_bits (umi_bits >= 2 * umi_len; 32 keeps the escape codes).  The sorts then run over
+ * those bits only -- one radix sort of a 64-bit (barcode, gene, umi) key when bc_bits + gene_bits +
+ * umi_bits <= 64 (a 3M-barcode whitelist, 65 536 genes, 12-nt UMIs: 62 bits), else two.  A record
+ * that does not fit its declared width is not sorted wrongly in silence: n_groups[0] = ~0 and
+ * the other outputs are undefined.  nr_umi_collapse_device = widths 32, 32, 32. */
+int nr_umi_collapse_device_keyed(const uint32_t *d_bc, const uint32_t *d_gene, const uint32_t *d_umi,
+                                 uint64_t n, int umi_len, int max_dist, int bc_bits, int gene_bits,
+                                 int umi_bits, uint32_t *d_rep_umi, uint64_t *d_n_groups,
+                                 uint32_t *d_g_bc, uint32_t *d_g_gene, uint32_t *d_g_umi,
+                                 uint32_t *d_g_reads, void *d_workspace, size_t workspace_bytes,
+                                 void *stream);
 size_t nr_umi_workspace_bytes(uint64_t n);
 
 /* ---- matcher results -> UMI records (device-resident pipelines) ------------------------------

@@ -32,7 +32,7 @@ SYMBOLS = (
     "nr_last_error", "nr_version", "nr_whitelist_create", "nr_whitelist_destroy",
     "nr_whitelist_size", "nr_whitelist_has_index", "nr_whitelist_device_bytes", "nr_pack_device",
     "nr_match_device", "nr_match_workspace_bytes", "nr_match_host", "nr_host_alloc",
-    "nr_host_free", "nr_umi_collapse_device", "nr_umi_workspace_bytes", "nr_int_peak",
+    "nr_host_free", "nr_umi_collapse_device", "nr_umi_collapse_device_keyed", "nr_umi_workspace_bytes", "nr_int_peak",
     "nr_int_peak_dual", "nr_match_device_counted", "nr_match_counters",
     "nr_umi_records_device", "nr_umi_records_workspace_bytes", "nr_umi_partition_device",
     "nr_umi_unzip_device", "nr_hw_search_device", "nr_hw_search_host",
@@ -82,6 +82,9 @@ def lib() -> C.CDLL:
     L.nr_host_free.restype = None
     L.nr_umi_collapse_device.argtypes = [vp, vp, vp, u64, i32, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.nr_umi_collapse_device.restype = i32
+    L.nr_umi_collapse_device_keyed.argtypes = [vp, vp, vp, u64, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp,
+                                               vp, sz, vp]
+    L.nr_umi_collapse_device_keyed.restype = i32
     L.nr_umi_workspace_bytes.argtypes = [u64]
     L.nr_umi_workspace_bytes.restype = sz
     L.nr_umi_records_device.argtypes = [vp] * 9 + [u64, i32, i32] + [vp] * 6 + [sz, vp]

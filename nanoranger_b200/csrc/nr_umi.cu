@@ -75,37 +75,67 @@ size_t cub_temp_bytes(uint64_t n)
     return align_up((size_t)n * 16 + (size_t)(n / 64 + 1) * 64 + (8u << 20));
 }
 
-__global__ void k_init(const uint32_t *umi, uint64_t n, uint32_t *umi_a, uint32_t *idx_a)
-{
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { umi_a[i] = umi[i]; idx_a[i] = (uint32_t)i; }
-}
+// key widths a caller may declare (nr_umi_collapse_device_keyed): a value that does not fit raises
+// *bad, which k_emit turns into n_groups = ~0
+__device__ __forceinline__ bool fits(uint32_t v, int bits) { return bits >= 32 || (v >> bits) == 0u; }
 
-__global__ void k_gather_key(const uint32_t *bc, const uint32_t *gene, const uint32_t *idx,
-                             uint64_t n, uint64_t *key)
-{
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { uint32_t s = idx[i]; key[i] = ((uint64_t)bc[s] << 32) | gene[s]; }
-}
-
-__global__ void k_sorted(const uint64_t *key, const uint32_t *umi_in, const uint32_t *idx,
-                         uint64_t n, uint32_t *s_bc, uint32_t *s_gene, uint32_t *s_umi,
-                         uint32_t *head_u, uint32_t *head_g)
+__global__ void k_init(const uint32_t *umi, uint64_t n, int umi_bits, uint32_t *umi_a, uint32_t *idx_a,
+                       uint32_t *bad)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint64_t k = key[i];
-    uint32_t u = umi_in[idx[i]];
-    s_bc[i] = (uint32_t)(k >> 32); s_gene[i] = (uint32_t)k; s_umi[i] = u;
-    bool hg = true, hu = true;
-    if (i > 0) {
-        hg = key[i - 1] != k;
-        hu = hg || umi_in[idx[i - 1]] != u;
-    }
-    head_u[i] = hu; head_g[i] = hg;
+    const uint32_t u = umi[i];
+    umi_a[i] = u; idx_a[i] = (uint32_t)i;
+    if (!fits(u, umi_bits)) *bad = 1u;
 }
 
-// after inclusive scans: ids = scan - 1; record first positions of distinct UMIs and groups
+__global__ void k_gather_key(const uint32_t *bc, const uint32_t *gene, const uint32_t *idx,
+                             uint64_t n, int bc_bits, int gene_bits, uint64_t *key, uint32_t *bad)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = idx[i], b = bc[s], g = gene[s];
+    key[i] = ((uint64_t)b << gene_bits) | g;
+    if (!fits(b, bc_bits) || !fits(g, gene_bits)) *bad = 1u;
+}
+
+// (barcode, gene, umi) in ONE key when the declared widths add up to <= 64 bits
+__global__ void k_compose(const uint32_t *bc, const uint32_t *gene, const uint32_t *umi, uint64_t n,
+                          int bc_bits, int gene_bits, int umi_bits, uint64_t *key, uint32_t *idx,
+                          uint32_t *bad)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t b = bc[i], g = gene[i], u = umi[i];
+    key[i] = ((((uint64_t)b << gene_bits) | g) << umi_bits) | u;
+    idx[i] = (uint32_t)i;
+    if (!fits(b, bc_bits) || !fits(g, gene_bits) || !fits(u, umi_bits)) *bad = 1u;
+}
+
+// sorted records + head flags.  umi_bits < 0: key = (barcode, gene), the UMI comes through idx;
+// else key = (barcode, gene, umi)
+__global__ void k_sorted(const uint64_t *key, const uint32_t *umi_in, const uint32_t *idx,
+                         uint64_t n, int gene_bits, int umi_bits, uint32_t *s_bc, uint32_t *s_gene,
+                         uint32_t *s_umi, uint32_t *head_u, uint32_t *head_g)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t gmask = (1ull << gene_bits) - 1ull;
+    uint64_t k = key[i], kp = i > 0 ? key[i - 1] : 0ull;
+    uint32_t u, up = 0;
+    if (umi_bits < 0) {
+        u = umi_in[idx[i]];
+        if (i > 0) up = umi_in[idx[i - 1]];
+    } else {
+        const uint64_t umask = (1ull << umi_bits) - 1ull;
+        u = (uint32_t)(k & umask); up = (uint32_t)(kp & umask);
+        k >>= umi_bits; kp >>= umi_bits;
+    }
+    s_bc[i] = (uint32_t)(k >> gene_bits); s_gene[i] = (uint32_t)(k & gmask); s_umi[i] = u;
+    const bool hg = i == 0 || kp != k;
+    head_u[i] = hg || up != u; head_g[i] = hg;
+}
+
 __global__ void k_ids(const uint32_t *scan_u, const uint32_t *scan_g, uint64_t n, uint32_t *du_id,
                       uint32_t *grp_id, uint32_t *du_first, uint32_t *grp_first, uint32_t *totals)
 {
@@ -499,7 +529,7 @@ __global__ void k_emit(const uint32_t *s_bc, const uint32_t *s_gene, const uint3
             uint32_t o = rep_pos[i] - 1, s = du_first[i];
             g_bc[o] = s_bc[s]; g_gene[o] = s_gene[s]; g_umi[o] = s_umi[s]; g_reads[o] = rep_reads[i];
         }
-        if (i == nd - 1) *n_groups = rep_pos[i];
+        if (i == nd - 1) *n_groups = totals[12] ? ~0ull : (uint64_t)rep_pos[i];
     }
 }
 
@@ -519,11 +549,12 @@ extern "C" size_t nr_umi_workspace_bytes(uint64_t n)
     return carve(nullptr, n, &w, cub_temp_bytes(n));
 }
 
-extern "C" int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_gene,
-                                      const uint32_t *d_umi, uint64_t n, int umi_len, int max_dist,
-                                      uint32_t *d_rep_umi, uint64_t *d_n_groups, uint32_t *d_g_bc,
-                                      uint32_t *d_g_gene, uint32_t *d_g_umi, uint32_t *d_g_reads,
-                                      void *d_workspace, size_t workspace_bytes, void *stream)
+extern "C" int nr_umi_collapse_device_keyed(const uint32_t *d_bc, const uint32_t *d_gene,
+                                            const uint32_t *d_umi, uint64_t n, int umi_len, int max_dist,
+                                            int bc_bits, int gene_bits, int umi_bits,
+                                            uint32_t *d_rep_umi, uint64_t *d_n_groups, uint32_t *d_g_bc,
+                                            uint32_t *d_g_gene, uint32_t *d_g_umi, uint32_t *d_g_reads,
+                                            void *d_workspace, size_t workspace_bytes, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (!d_n_groups) { nr_set_error("nr_umi_collapse_device: null pointer"); return NR_EINVAL; }
@@ -538,6 +569,11 @@ extern "C" int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_ge
     }
     if (umi_len < 1 || umi_len > 16 || max_dist < 0 || max_dist > 1 || n >= (1ull << 31)) {
         nr_set_error("nr_umi_collapse_device: umi_len 1..16, max_dist 0..1, n < 2^31");
+        return NR_EINVAL;
+    }
+    if (bc_bits < 1 || bc_bits > 32 || gene_bits < 1 || gene_bits > 32 || umi_bits < 2 * umi_len ||
+        umi_bits > 32) {
+        nr_set_error("nr_umi_collapse_device_keyed: bc_bits, gene_bits 1..32, umi_bits 2 * umi_len..32");
         return NR_EINVAL;
     }
     if (workspace_bytes < nr_umi_workspace_bytes(n)) {
@@ -562,14 +598,13 @@ extern "C" int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_ge
         cudaEventRecord(tev[ntev++], st);
     };
     mark("sorts");
-    k_init<<<nb, T, 0, st>>>(d_umi, n, w.umi_a, w.idx_a);
-    size_t need = 0;
-    // all 32 bits of the UMI word: a caller may carry escape codes above bit 2 * umi_len (the host
-    // path's N-containing UMIs), and equal words must end up adjacent whatever their width
+    uint32_t *bad = w.totals + 12;
+    NR_CHECK_CUDA(cudaMemsetAsync(bad, 0, 4, st));
+    const int key_bits = bc_bits + gene_bits, all_bits = key_bits + umi_bits;
+    const bool one_sort = all_bits <= 64;
+    size_t need = 0, need2 = 0, need3 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, need, w.umi_a, w.umi_b, w.idx_a, w.idx_b, N, 0, 32, st);
-    size_t need2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, need2, w.key_a, w.key_b, w.idx_b, w.idx_a, N, 0, 64, st);
-    size_t need3 = 0;
     cub::DeviceScan::InclusiveSum(nullptr, need3, w.head_u, w.head_u, N, st);
     if (need > w.cub_bytes || need2 > w.cub_bytes || need3 > w.cub_bytes) {
         nr_set_error("nr_umi_collapse_device: CUB needs %zu bytes of temporary storage, have %zu",
@@ -577,16 +612,27 @@ extern "C" int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_ge
         return NR_ENOMEM;
     }
     size_t tb = w.cub_bytes;
-    NR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.umi_a, w.umi_b, w.idx_a, w.idx_b,
-                                                  N, 0, 32, st));
-    k_gather_key<<<nb, T, 0, st>>>(d_bc, d_gene, w.idx_b, n, w.key_a);
-    tb = w.cub_bytes;
-    NR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.key_a, w.key_b, w.idx_b, w.idx_a,
-                                                  N, 0, 64, st));
+    if (one_sort) {
+        // declared widths fit one 64-bit key: a single radix sort over all_bits bits
+        k_compose<<<nb, T, 0, st>>>(d_bc, d_gene, d_umi, n, bc_bits, gene_bits, umi_bits, w.key_a, w.idx_b, bad);
+        NR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.key_a, w.key_b, w.idx_b, w.idx_a,
+                                                      N, 0, all_bits, st));
+    } else {
+        // LSD: by umi, then stable by (barcode, gene).  The default width is all 32 bits of the UMI
+        // word: a caller may carry escape codes above bit 2 * umi_len (the host path's N-containing
+        // UMIs), and equal words must end up adjacent whatever their width
+        k_init<<<nb, T, 0, st>>>(d_umi, n, umi_bits, w.umi_a, w.idx_a, bad);
+        NR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.umi_a, w.umi_b, w.idx_a, w.idx_b,
+                                                      N, 0, umi_bits, st));
+        k_gather_key<<<nb, T, 0, st>>>(d_bc, d_gene, w.idx_b, n, bc_bits, gene_bits, w.key_a, bad);
+        tb = w.cub_bytes;
+        NR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.key_a, w.key_b, w.idx_b, w.idx_a,
+                                                      N, 0, key_bits, st));
+    }
     mark("ids");
     // sorted order: key_b (barcode, gene), idx_a (source record)
-    k_sorted<<<nb, T, 0, st>>>(w.key_b, d_umi, w.idx_a, n, w.s_bc, w.s_gene, w.s_umi, w.head_u,
-                               w.head_g);
+    k_sorted<<<nb, T, 0, st>>>(w.key_b, d_umi, w.idx_a, n, gene_bits, one_sort ? umi_bits : -1, w.s_bc,
+                               w.s_gene, w.s_umi, w.head_u, w.head_g);
     tb = w.cub_bytes;
     NR_CHECK_CUDA(cub::DeviceScan::InclusiveSum(w.cub_tmp, tb, w.head_u, w.head_u, N, st));
     tb = w.cub_bytes;
@@ -654,4 +700,15 @@ extern "C" int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_ge
         cudaEventDestroy(end);
     }
     return NR_OK;
+}
+
+extern "C" int nr_umi_collapse_device(const uint32_t *d_bc, const uint32_t *d_gene,
+                                      const uint32_t *d_umi, uint64_t n, int umi_len, int max_dist,
+                                      uint32_t *d_rep_umi, uint64_t *d_n_groups, uint32_t *d_g_bc,
+                                      uint32_t *d_g_gene, uint32_t *d_g_umi, uint32_t *d_g_reads,
+                                      void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    return nr_umi_collapse_device_keyed(d_bc, d_gene, d_umi, n, umi_len, max_dist, 32, 32, 32, d_rep_umi,
+                                        d_n_groups, d_g_bc, d_g_gene, d_g_umi, d_g_reads, d_workspace,
+                                        workspace_bytes, stream);
 }

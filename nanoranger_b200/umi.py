@@ -39,10 +39,19 @@ def unpack_umis(codes: np.ndarray, umi_len: int) -> list[str]:
     return [bytes(r).decode("ascii") for r in a]
 
 
-def collapse_device(d_bc, d_gene, d_umi, umi_len: int, max_dist: int = 0):
+def key_bits(n_values: int) -> int:
+    """bits that hold every id in [0, n_values)"""
+    return max(1, int(n_values - 1).bit_length())
+
+
+def collapse_device(d_bc, d_gene, d_umi, umi_len: int, max_dist: int = 0, bc_bits: int = 32,
+                    gene_bits: int = 32, umi_bits: int = 32):
     """torch uint32-as-int32 tensors on one GPU -> dict of device tensors:
     rep_umi [n], n_groups (int), g_bc / g_gene / g_umi / g_reads [n_groups] sorted by
-    (bc, gene, umi).  Stream-ordered; the only synchronisation is reading n_groups."""
+    (bc, gene, umi).  Stream-ordered; the only synchronisation is reading n_groups.
+    bc_bits / gene_bits / umi_bits: declared key widths (key_bits(len(whitelist)),
+    key_bits(n_genes), 2 * umi_len when no escape codes are used): the sorts run over those bits
+    only; a record that does not fit raises ValueError."""
     import torch
     n = d_bc.numel()
     dev = d_bc.device
@@ -53,22 +62,26 @@ def collapse_device(d_bc, d_gene, d_umi, umi_len: int, max_dist: int = 0):
     ws = torch.empty(max(int(L.nr_umi_workspace_bytes(n)), 1), dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream(dev).cuda_stream
     with torch.cuda.device(dev):
-        _lib.check(L.nr_umi_collapse_device(
+        _lib.check(L.nr_umi_collapse_device_keyed(
             d_bc.data_ptr(), d_gene.data_ptr(), d_umi.data_ptr(), n, umi_len, max_dist,
+            bc_bits, gene_bits, umi_bits,
             rep.data_ptr(), ng.data_ptr(), g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(),
-            g[3].data_ptr(), ws.data_ptr(), ws.numel(), st), "nr_umi_collapse_device")
+            g[3].data_ptr(), ws.data_ptr(), ws.numel(), st), "nr_umi_collapse_device_keyed")
     k = int(ng.item())
+    if k < 0:
+        raise ValueError(f"collapse_device: a record does not fit the declared key widths "
+                         f"(bc_bits={bc_bits}, gene_bits={gene_bits}, umi_bits={umi_bits})")
     return {"rep_umi": rep, "n_groups": k, "g_bc": g[0][:k], "g_gene": g[1][:k],
             "g_umi": g[2][:k], "g_reads": g[3][:k]}
 
 
-def collapse_host(bc, gene, umi, umi_len: int, max_dist: int = 0, device: int = 0):
-    """numpy in, numpy out (uint32 arrays)."""
+def collapse_host(bc, gene, umi, umi_len: int, max_dist: int = 0, device: int = 0, **widths):
+    """numpy in, numpy out (uint32 arrays).  widths: bc_bits / gene_bits / umi_bits of collapse_device."""
     import torch
     dev = torch.device("cuda", device)
     t = [torch.from_numpy(np.ascontiguousarray(x, np.uint32).view(np.int32)).to(dev)
          for x in (bc, gene, umi)]
-    r = collapse_device(t[0], t[1], t[2], umi_len, max_dist)
+    r = collapse_device(t[0], t[1], t[2], umi_len, max_dist, **widths)
     out = {"n_groups": r["n_groups"]}
     for k in ("rep_umi", "g_bc", "g_gene", "g_umi", "g_reads"):
         out[k] = r[k].cpu().numpy().view(np.uint32)
@@ -186,16 +199,17 @@ def unzip_device(rows):
     return tuple(t[:m] for t in out)
 
 
-def collapse_distributed(d_bc, d_gene, d_umi, umi_len: int, max_dist: int = 0, group=None):
+def collapse_distributed(d_bc, d_gene, d_umi, umi_len: int, max_dist: int = 0, group=None, **widths):
     """UMI collapse over all ranks of `group` (one process per GPU, NCCL): partition the local
     records by owner rank on the device, ONE variable-count all-to-all of 16-byte rows, local
     collapse of the barcodes this rank owns.  -> collapse_device() dict for the owned barcodes.
-    With no process group (single GPU) this is collapse_device()."""
+    With no process group (single GPU) this is collapse_device().  widths: bc_bits / gene_bits /
+    umi_bits of collapse_device."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return collapse_device(d_bc, d_gene, d_umi, umi_len, max_dist)
+        return collapse_device(d_bc, d_gene, d_umi, umi_len, max_dist, **widths)
     world = dist.get_world_size(group)
     rows, counts = partition_device(d_bc, d_gene, d_umi, world)
     got = exchange_records(rows, counts, group)
     bc, gene, umi, _ = unzip_device(got)
-    return collapse_device(bc, gene, umi, umi_len, max_dist)
+    return collapse_device(bc, gene, umi, umi_len, max_dist, **widths)

@@ -189,3 +189,30 @@ def test_umi_collapse_group_size_boundaries(cuda_device, oracle):
     bc, gene, um = (np.asarray(a, np.uint32)[p] for a in (bc, gene, um))
     _check(oracle, bc, gene, um, 12, 1)
     _check(oracle, bc, gene, um, 12, 0)
+
+
+def test_umi_collapse_declared_key_widths(cuda_device, oracle):
+    """nr_umi_collapse_device_keyed: one 64-bit sort (widths add up to <= 64), two narrower sorts
+    (> 64), both equal to the oracle; a record wider than declared is reported, not mis-sorted."""
+    from nanoranger_b200 import umi as U
+    rng = np.random.default_rng(5)
+    n = 200_000
+    bc = rng.integers(0, 3000, n).astype(np.uint32)
+    gene = rng.integers(0, 500, n).astype(np.uint32)
+    um = rng.integers(0, 1 << 10, n).astype(np.uint32) << np.uint32(7)       # 12-nt words, 17 bits used
+    k, rep = oracle.umi_cluster(bc, gene, um, 1)
+    for widths in (dict(bc_bits=12, gene_bits=9, umi_bits=24),                # 45 bits: one sort
+                   dict(bc_bits=32, gene_bits=9, umi_bits=24),                # 65 bits: two sorts
+                   dict(bc_bits=12, gene_bits=32, umi_bits=32)):
+        r = U.collapse_host(bc, gene, um, 12, 1, **widths)
+        assert r["n_groups"] == k and np.array_equal(r["rep_umi"], rep), widths
+    full = U.collapse_host(bc, gene, um, 12, 1)
+    one = U.collapse_host(bc, gene, um, 12, 1, bc_bits=12, gene_bits=9, umi_bits=24)
+    for f in ("g_bc", "g_gene", "g_umi", "g_reads"):
+        assert np.array_equal(full[f], one[f]), f
+    for widths in (dict(bc_bits=11, gene_bits=9, umi_bits=24), dict(bc_bits=12, gene_bits=8, umi_bits=24),
+                   dict(bc_bits=32, gene_bits=8, umi_bits=32)):
+        with pytest.raises(ValueError):
+            U.collapse_host(bc, gene, um, 12, 1, **widths)
+    with pytest.raises(Exception):
+        U.collapse_host(bc, gene, um, 12, 1, umi_bits=16)                     # < 2 * umi_len

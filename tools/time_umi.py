@@ -3,7 +3,7 @@ The synthetic library of bench.py (10 000 cells, zipf genes, <= 6 molecules per 
 drawn `depth` times as deep, a substitution error lands in `p_err` of the UMIs, and the records of
 the cells rank 0 of `depth` ranks would own are collapsed (max_dist 1) and, with --check, compared
 with the CPU oracle's sequential walk.
-  python tools/time_umi.py [depth] [--check]"""
+  python tools/time_umi.py [depth] [--check] [--keyed]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -38,14 +38,15 @@ print(f"depth {depth}: {n} records, {len(cnt)} (cell, gene) groups, deepest {cnt
 
 dev = torch.device("cuda:0")
 d = [torch.from_numpy(a.view(np.int32)).to(dev) for a in (cell, gene, umi)]
+widths = dict(bc_bits=U.key_bits(n_cells), gene_bits=U.key_bits(n_genes), umi_bits=24) if "--keyed" in sys.argv else {}
 for md in (1, 0):
-    r = U.collapse_device(*d, 12, md)
+    r = U.collapse_device(*d, 12, md, **widths)
     torch.cuda.synchronize()
     ts = []
     for _ in range(20):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         ev[0].record()
-        r = U.collapse_device(*d, 12, md)
+        r = U.collapse_device(*d, 12, md, **widths)
         ev[1].record()
         torch.cuda.synchronize()
         ts.append(ev[0].elapsed_time(ev[1]))
