@@ -169,16 +169,17 @@ def test_umi_collapse_huge_group_hash_path(cuda_device, oracle):
 
 
 def test_umi_collapse_group_size_boundaries(cuda_device, oracle):
-    """groups of exactly 1..10, 31..34, 63..66, 95..98 and 300 distinct UMIs (one thread / one warp
-    with 1, 2, 3 register slots / the hash-set rounds), drawn from a tight UMI space so that most
+    """groups of exactly 1..10, 31..34, 63..66, 95..98, 300, 2048 and 2049 distinct UMIs (one thread /
+    one warp with 1, 2, 3 register slots / one block in shared memory / the grid-wide hash-set
+    rounds), drawn from a tight UMI space so that most
     UMIs have neighbours, with many equal read counts (the walk order then falls back on the UMI
     value) and a few dominant UMIs that absorb their neighbours."""
     rng = np.random.default_rng(99)
-    sizes = list(range(1, 11)) + [31, 32, 33, 34, 63, 64, 65, 66, 95, 96, 97, 98, 300]
+    sizes = list(range(1, 11)) + [31, 32, 33, 34, 63, 64, 65, 66, 95, 96, 97, 98, 300, 2048, 2049]
     bc, gene, um = [], [], []
-    for rep in range(6):
+    for rep in range(4):
         for gi, nd in enumerate(sizes):
-            space = 1 << (2 * (4 if nd <= 98 else 5))          # 4-nt / 5-nt UMIs inside a 12-nt word
+            space = 1 << (2 * (4 if nd <= 98 else (5 if nd <= 300 else 6)))   # 4 / 5 / 6-nt UMIs inside a 12-nt word
             u = rng.choice(space, size=nd, replace=False).astype(np.uint32)
             reads = np.where(rng.random(nd) < 0.15, rng.integers(5, 40, nd), rng.integers(1, 4, nd))
             for x, k in zip(u, reads):
