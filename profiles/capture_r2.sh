@@ -11,7 +11,7 @@ mkdir -p $OUT
 python profiles/prof_all.py > $OUT/prof_all_plain.log 2> $OUT/prof_all_plain.err || { echo "plain run failed"; tail -5 $OUT/prof_all_plain.err; exit 1; }
 ncu --set full --metrics smsp__inst_executed_pipe_alu.sum,smsp__inst_executed_pipe_fma.sum,smsp__inst_executed_pipe_lsu.sum,smsp__thread_inst_executed.sum \
     --clock-control none \
-    -k regex:'nr_pack_kernel|nr_match_|nr_deep_|k_cluster|k_rec_|k_part_|nr_hw_search' \
+    -k regex:'nr_pack_kernel|nr_match_|nr_deep_|k_cluster|k_large|k_rec_|k_part_|nr_hw_search' \
     -f -o $OUT/prof_all python profiles/prof_all.py > $OUT/prof_all_ncu.log 2>&1
 tail -3 $OUT/prof_all_ncu.log
 # the report itself is too large to travel (gpurun_out is capped at 64 MiB): keep the raw page

@@ -107,7 +107,8 @@ kb, km, kn = wlk.pack_device(ks, ko)
 res = wlk.match_device(kb, km, kn, min_score=14, mode=NR_MODE_FILTERED)
 rec = U.records_device(kb, km, kn, res, 14, 12, gene=kg, with_src=False)
 rows, counts = U.partition_device(rec["bc"], rec["gene"], rec["umi"], 8)
-r = U.collapse_device(rec["bc"], rec["gene"], rec["umi"], 12, 1)
+r = U.collapse_device(rec["bc"], rec["gene"], rec["umi"], 12, 1, bc_bits=U.key_bits(n_cells), gene_bits=U.key_bits(n_genes),
+                      umi_bits=24)
 torch.cuda.synchronize()
 print("KINNEX records", rec["n_records"], "molecules", r["n_groups"], flush=True)
 wlk.close()
