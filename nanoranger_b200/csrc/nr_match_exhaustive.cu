@@ -14,6 +14,7 @@
 
 #include "nr_common.cuh"
 #include "nr_ex_common.cuh"
+#include "nr_bitslice_core.h"
 
 namespace {
 
@@ -300,6 +301,119 @@ nr_match_exhaustive_generic_kernel(const uint32_t *__restrict__ wlo,
     }
 }
 
+
+// ---- bit-parallel: 32 entries per thread in the bit lanes (nr_bitslice_core.h) ----------------
+// The weighted form of Myers/Hyyro: every cell carries two 2-bit differences per lane, one cell of
+// 32 entries is ten LOP3 (a DPX cell pair is two instructions for TWO entries).  A thread takes a
+// word of 32 consecutive entries, transposes their packed columns in registers and leaves the
+// four match masks of every column in shared memory ([base][column][thread]: conflict-free);
+// a cell is then one LDS + the cell function.  The read's byte codes are block-uniform.  L = 16
+// and L = 32 (slide-seq), with or without N columns; other core lengths keep the DPX kernel.
+template <int L, bool HAS_N, int T>
+__global__ void __launch_bounds__(T, 2)
+nr_match_bitsliced_kernel(const uint32_t *__restrict__ wlo, const uint32_t *__restrict__ whi,
+                          const uint32_t *__restrict__ wnm, uint32_t n, int padL, int padR,
+                          const uint4 *__restrict__ bases, const uint8_t *__restrict__ meta,
+                          const uint64_t *__restrict__ nmask, const uint32_t *__restrict__ list,
+                          const uint32_t *__restrict__ list_count, uint64_t n_cand, int min_score,
+                          int32_t *__restrict__ o_idx, int8_t *__restrict__ o_score,
+                          uint8_t *__restrict__ o_nbest, uint8_t *__restrict__ o_flags,
+                          uint8_t *__restrict__ o_umi, ExScratch sc)
+{
+    extern __shared__ uint32_t tabs[];          // eq [4][L][T], then (HAS_N) the N planes [L][T]
+    __shared__ uint8_t cf[NR_MAX_QUERY], cr[NR_MAX_QUERY];
+    __shared__ Best shb[32];
+    __shared__ int sh_flag;
+    const uint64_t total = list ? (uint64_t)*list_count : n_cand;
+    const uint32_t nwords = (n + 31u) >> 5;
+    const uint32_t S = ex_slices(total, sc);
+    const uint32_t per = (nwords + S - 1) / S;
+    uint32_t *eq = tabs + threadIdx.x;
+    uint32_t *nmp = tabs + 4 * L * T + threadIdx.x;
+    for (uint64_t w = blockIdx.x; w < total * S; w += gridDim.x) {
+        const uint64_t it = w / S;
+        const uint32_t g_lo = (uint32_t)(w % S) * per;
+        const uint32_t g_hi = min(nwords, g_lo + per);
+        const uint64_t cand = list ? (uint64_t)list[it] : it;
+        const uint8_t mt = meta[cand];
+        if (mt == 0xFF) {
+            if (threadIdx.x == 0) {
+                o_idx[cand] = -1; o_score[cand] = NR_SCORE_BELOW; o_nbest[cand] = 0;
+                o_flags[cand] = NR_FLAG_TOO_LONG | NR_FLAG_BELOW | NR_FLAG_NO_UMI;
+                o_umi[cand] = NR_UMI_NONE;
+            }
+            continue;
+        }
+        const int m = mt & 0x7F;
+        __syncthreads();
+        load_codes(bases, (mt & 0x80) ? nmask : nullptr, cand, m, cf, cr);
+        __syncthreads();
+        Best b; b.score = -1000; b.cnt = 0; b.key = 0xFFFFFFFFu;
+        for (uint32_t g = g_lo + threadIdx.x; g < g_hi; g += T) {
+            const uint32_t base = g << 5;
+            const bool whole = base + 32u <= n;
+            uint32_t r[32];
+            if (HAS_N) {
+#pragma unroll
+                for (int k = 0; k < 32; k++) r[k] = wnm[min(base + k, n - 1)];
+                nr_bs_transpose32(r);
+#pragma unroll
+                for (int j = 0; j < L; j++) nmp[j * T] = r[j];
+            }
+            if (whole) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(wlo + base);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint4 v = __ldg(src + k);
+                    r[4 * k] = v.x; r[4 * k + 1] = v.y; r[4 * k + 2] = v.z; r[4 * k + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 32; k++) r[k] = wlo[min(base + k, n - 1)];
+            }
+            nr_bs_transpose32(r);
+            nr_bs_build_eq16<L, HAS_N>(r, 0, eq, nmp, T);
+            if (L == 32) {
+#pragma unroll
+                for (int k = 0; k < 32; k++) r[k] = whi[min(base + k, n - 1)];
+                nr_bs_transpose32(r);
+                nr_bs_build_eq16<L, HAS_N>(r, L == 32 ? 16 : 0, eq, nmp, T);
+            }
+            const uint32_t valid = whole ? 0xFFFFFFFFu : ((1u << (n - base)) - 1u);
+#pragma unroll 1
+            for (int strand = 0; strand < 2; strand++) {
+                uint32_t M[NR_BS_PLANES];
+                nr_bs_word_strand<L, HAS_N>(eq, nmp, T, strand ? cr : cf, m, padL, padR, M);
+                int v;
+                const uint32_t at = nr_bs_lane_min(M, valid, &v);
+                best_merge(b, L - v, (uint32_t)__popc(at),
+                           ((base + (uint32_t)(__ffs((int)at) - 1)) << 1) | (uint32_t)strand);
+            }
+        }
+        Best r = block_reduce_best(b, shb);
+        if (ex_merge(r, w, it, S, sc, &sh_flag) && threadIdx.x == 0)
+            write_result(r, cand, m, cf, wlo, L == 32 ? whi : nullptr, HAS_N ? wnm : nullptr, L, padL,
+                         padR, min_score, o_idx, o_score, o_nbest, o_flags, o_umi);
+    }
+}
+
+template <int L, bool HAS_N, int T>
+int launch_bitsliced(const nr_whitelist *wl, unsigned grid, const void *d_bases, const uint8_t *d_meta,
+                     const uint64_t *d_nmask, const uint32_t *d_list, const uint32_t *d_list_count,
+                     uint64_t n_cand, int min_score, int32_t *d_idx, int8_t *d_score, uint8_t *d_nbest,
+                     uint8_t *d_flags, uint8_t *d_umi, const ExScratch &sc, cudaStream_t stream)
+{
+    const size_t smem = (size_t)(HAS_N ? 5 : 4) * L * T * sizeof(uint32_t);
+    NR_CHECK_CUDA(cudaFuncSetAttribute(nr_match_bitsliced_kernel<L, HAS_N, T>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nr_match_bitsliced_kernel<L, HAS_N, T><<<grid, T, smem, stream>>>(
+        wl->d_lo, wl->d_hi, wl->d_nm, (uint32_t)wl->n, (int)wl->pad_l, (int)wl->pad_r,
+        (const uint4 *)d_bases, d_meta, d_nmask, d_list, d_list_count, n_cand, min_score, d_idx,
+        d_score, d_nbest, d_flags, d_umi, sc);
+    NR_CHECK_CUDA(cudaGetLastError());
+    return NR_OK;
+}
+
 }  // namespace
 
 // host launcher shared with the C API: either all n_cand candidates, or the device-resident
@@ -320,6 +434,24 @@ int nr_launch_exhaustive(const nr_whitelist *wl, const void *d_bases, const uint
     sc.done = d_scratch ? (uint32_t *)d_scratch : nullptr;
     sc.part = d_scratch ? (uint4 *)((uint8_t *)d_scratch + NR_EX_MAXGRID * sizeof(uint32_t)) : nullptr;
     static const bool force_generic = getenv("NR_FORCE_GENERIC_EXHAUSTIVE") != nullptr;   // experiments only
+    // the DPX kernels of round 1 stay selectable for A/B timing (tools/time_exhaustive.py)
+    static const bool force_dpx = getenv("NR_EXHAUSTIVE_DPX") != nullptr || force_generic;
+    if (!force_dpx && (wl->L == 16 || wl->L == 32)) {
+        const bool hn = wl->has_n && wl->d_nm;
+        if (wl->L == 16)
+            return hn ? launch_bitsliced<16, true, 256>(wl, grid, d_bases, d_meta, d_nmask, d_list, d_list_count,
+                                                        n_cand, min_score, d_idx, d_score, d_nbest, d_flags,
+                                                        d_umi, sc, stream)
+                      : launch_bitsliced<16, false, 256>(wl, grid, d_bases, d_meta, d_nmask, d_list, d_list_count,
+                                                         n_cand, min_score, d_idx, d_score, d_nbest, d_flags,
+                                                         d_umi, sc, stream);
+        return hn ? launch_bitsliced<32, true, 128>(wl, grid, d_bases, d_meta, d_nmask, d_list, d_list_count,
+                                                    n_cand, min_score, d_idx, d_score, d_nbest, d_flags, d_umi,
+                                                    sc, stream)
+                  : launch_bitsliced<32, false, 128>(wl, grid, d_bases, d_meta, d_nmask, d_list, d_list_count,
+                                                     n_cand, min_score, d_idx, d_score, d_nbest, d_flags, d_umi,
+                                                     sc, stream);
+    }
     if (wl->L == 16 && !wl->has_n && !force_generic) {
         nr_match_exhaustive16_kernel<<<grid, 256, 0, stream>>>(
             wl->d_lo, (uint32_t)wl->n, (int)wl->pad_l, (int)wl->pad_r, (const uint4 *)d_bases,
