@@ -34,7 +34,7 @@ if ROOT not in sys.path:
 CELLS_PER_CANDIDATE_737K = 737280 * 16 * 50      # SURVEY.md section 8d "equivalent cell updates"
 # kernels one step launches (nr_pack_device + nr_match_device in NR_MODE_FILTERED), in stream order
 STEP_KERNELS = ("nr_pack_kernel", "nr_match_filtered_kernel<main pass>", "nr_match_filtered_kernel<N pass>",
-                "nr_match_deep_kernel<K=3>", "nr_match_deep_kernel<K=5>", "nr_match_exhaustive16_kernel",
+                "nr_match_deep_kernel<K=3>", "nr_match_deep_kernel<K=5>", "nr_match_bitsliced_kernel<16>",
                 "nr_deep_finalize_kernel")
 P_N = 1e-3                                       # per-base probability of an N in the synthetic flanks
 
@@ -654,7 +654,7 @@ def run_flanks(args, ctx):
         ms_dp = e0.elapsed_time(e1)
         dp_cells = float(dp_meta.to(torch.int64).bitwise_and(0x7F).sum().item()) * len(wl_ascii) * 16 * 2
         dp_mask = torch.from_numpy(a_np[:n_dp]).to(dev)
-        dp = {"value": dp_cells / (ms_dp * 1e-3) / 1e9 * world, "kernel": "nr_match_exhaustive16_kernel",
+        dp = {"value": dp_cells / (ms_dp * 1e-3) / 1e9 * world, "kernel": "nr_match_bitsliced_kernel<16> (bit-parallel, 32 entries per thread; round 1's DPX kernel: 9.7e3 GCUPS)",
               "sample": f"first {n_dp} candidates of the batch per GPU, both strands, every whitelist entry",
               "ms": ms_dp, "candidates_per_sec": world * n_dp / (ms_dp * 1e-3),
               "agrees_with_filtered_on_assigned": bool(np.array_equal(dp_out.idx.cpu().numpy()[a_np[:n_dp]],
