@@ -43,10 +43,6 @@ struct nr_whitelist {
     uint32_t *d_rank[4];
     uint2 *d_ents[4];
     uint32_t *d_kstart[4];
-    // word directory + dropped-quarter bytes of the rows (nr_filter_core.h: nr_dir_start): the
-    // filtered kernel's path for whitelists of millions of entries, whose rows do not fit L2
-    uint4 *d_dir[4];     // 2^19 entries each
-    uint8_t *d_q8[4];    // n each
     // anchored seed filter (nr_anchor_core.h): cores = 8 columns + constant linker + tail (slide-seq)
     int has_anchor;
     int anchor_lk;                // linker columns

@@ -205,34 +205,6 @@ NR_HD uint32_t nr_core_key(uint32_t core, int j)
     }
 }
 
-// the core again from its key with quarter j removed and that quarter's byte
-NR_HD uint32_t nr_core_insert(uint32_t key, int j, uint32_t q)
-{
-    switch (j) {
-    case 0: return (key << 8) | q;
-    case 1: return (key & 0xFFu) | (q << 8) | ((key & 0xFFFF00u) << 8);
-    case 2: return (key & 0xFFFFu) | (q << 16) | ((key & 0xFF0000u) << 8);
-    default: return key | (q << 24);
-    }
-}
-
-// ---- word directory of a key table (dense whitelists) ------------------------------------------
-// One 16-byte entry per bitmap word of 32 keys: x = rows in front of the word (bit 31: some key of
-// the word has more than 3 rows -- use rank / kstart), y / z = low / high bit of every key's row
-// count (0 = key absent, 1..3), w = distinct keys in front of the word.  Rows are sorted by key,
-// so a hit's rows start at x + the counts of the keys below it in the word: no access to kstart,
-// and with the dropped quarter of every row in a byte array (q8) none to the {entry, core} rows
-// either until a row has passed verification.
-NR_HD uint32_t nr_dir_start(uint32_t x, uint32_t y, uint32_t z, uint32_t bit)
-{
-    const uint32_t below = (1u << bit) - 1u;
-    return (x & 0x7FFFFFFFu) + (uint32_t)nr_popc32(y & below) + 2u * (uint32_t)nr_popc32(z & below);
-}
-NR_HD uint32_t nr_dir_rows(uint32_t y, uint32_t z, uint32_t bit)
-{
-    return ((y >> bit) & 1u) + 2u * ((z >> bit) & 1u);
-}
-
 // slot positions worth probing for a read of length m: first..last inclusive
 NR_HD int nr_slot_first(int m, int padR) { int a = m - padR - 22; return a > -2 ? a : -2; }
 NR_HD int nr_slot_last(int m, int padL) { int a = m - 10, b = padL + 3; return a < b ? a : b; }

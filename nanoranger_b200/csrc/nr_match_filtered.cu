@@ -29,7 +29,6 @@
 // Candidates the filter cannot take (contain N, shorter than NR_FILTER_MIN_LEN, more than 32
 // co-optimal pairs) are appended to a device list that the exhaustive kernel resolves.
 #include <atomic>
-#include <cstdlib>
 #include <type_traits>
 #include <utility>
 
@@ -43,7 +42,6 @@
 #endif
 #define NR_QCAP 480                        // queue slots per warp
 #define NR_VQCAP 64                        // N pass: rows waiting for the N-aware automaton, per warp
-#define NR_FILTER_DIR_MIN_ENTRIES (1ull << 21)   // whitelists from this size on use the word directory
 
 struct nr_filter_params {
     const uint32_t *bits[4];      // key bitmap, 2^19 words per dropped quarter, contiguous:
@@ -51,8 +49,6 @@ struct nr_filter_params {
     const uint32_t *rank[4];      // distinct keys below each bitmap word
     const uint2 *ents[4];
     const uint32_t *kstart[4];
-    const uint4 *dir[4];          // word directory and dropped-quarter bytes (DIR variant of the
-    const uint8_t *q8[4];         // kernel: whitelists of millions of entries), see nr_filter_core.h
     uint32_t n;
     int padL, padR;
     const uint4 *bases;
@@ -100,8 +96,6 @@ struct Tables {
     const uint32_t *rank[4];
     const uint2 *ents[4];
     const uint32_t *kstart[4];
-    const uint4 *dir[4];
-    const uint8_t *q8[4];
 };
 
 struct WarpSmem {
@@ -186,10 +180,7 @@ __device__ __forceinline__ void flush_vq(const nr_filter_params &P, WarpSmemN &s
 
 // Take up to 32 queued bitmap hits, expand each into the index rows that share its key
 // (kstart gives first row and count), and verify the rows 32 at a time, one row per lane.
-// DIR: the rows of a hit come from the word directory (one 16-byte read instead of bitmap word +
-// rank + two kstart words) and a row is verified against the core rebuilt from the hit's key and
-// the row's dropped-quarter byte; the {entry, core} row is only read once it has passed.
-template <bool COUNT, bool NMODE, bool DIR>
+template <bool COUNT, bool NMODE>
 __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmemT<NMODE> &sm, Acc &acc, int m,
                                       const uint32_t *s_probes, const Tables &T4)
 {
@@ -206,31 +197,17 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmemT<NMODE
     const int h_strand = (int)((item >> 24) & 1u);
     const int h_p = (int)(item >> 25) - 16;
     const uint32_t d = (uint32_t)t.drop;
-    uint32_t start = 0, rows = 0, hkey = 0;
+    uint32_t start = 0, rows = 0;
     if (have && h_p + nr_probe_first(t) >= 0 && h_p + nr_probe_end(t) <= m) {
         const uint32_t key = nr_probe_key(nr_window64(sm.rdp[h_strand], h_p), t);
-        hkey = key;
-        bool by_rank = true;
-        uint32_t rank_w = 0;
-        if constexpr (DIR) {
-            const uint4 dr = __ldcg(T4.dir[d] + (key >> 5));
-            by_rank = (dr.x >> 31) != 0u;
-            rank_w = dr.w;
-            if (!by_rank) {
-                start = nr_dir_start(dr.x, dr.y, dr.z, key & 31u);
-                rows = nr_dir_rows(dr.y, dr.z, key & 31u);
-            }
-        }
-        if (by_rank) {
-            const uint32_t w = __ldg(T4.bits[0] + (((d << 24) | key) >> 5));
-            // rank / kstart / rows are touched once per hit: keep them out of L1 (L2 only) so that the
-            // bitmap sectors stay
-            const uint32_t kr = (DIR ? rank_w : __ldcg(T4.rank[d] + (key >> 5))) +
-                                (uint32_t)__popc(w & ((1u << (key & 31u)) - 1u));
-            const uint32_t *ks = T4.kstart[d] + kr;
-            start = __ldcg(ks);
-            rows = __ldcg(ks + 1) - start;
-        }
+        const uint32_t w = __ldg(T4.bits[0] + (((d << 24) | key) >> 5));
+        // rank / kstart / rows are touched once per hit: keep them out of L1 (L2 only) so that the
+        // bitmap sectors stay
+        const uint32_t kr = __ldcg(T4.rank[d] + (key >> 5)) +
+                            (uint32_t)__popc(w & ((1u << (key & 31u)) - 1u));
+        const uint32_t *ks = T4.kstart[d] + kr;
+        start = __ldcg(ks);
+        rows = __ldcg(ks + 1) - start;
         if (COUNT) acc.c_hits++;
     }
     // exclusive prefix of the row counts
@@ -256,7 +233,6 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmemT<NMODE
         const uint32_t o_start = __shfl_sync(0xffffffffu, start, lo);
         const uint32_t o_excl = __shfl_sync(0xffffffffu, excl, lo);
         const uint32_t o_item = __shfl_sync(0xffffffffu, item, lo);
-        const uint32_t o_key = DIR ? __shfl_sync(0xffffffffu, hkey, lo) : 0u;
         int cost = 3, u = -1;
         uint32_t k = 0, vcore = 0, vwhere = 0;
         if (active) {
@@ -264,14 +240,7 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmemT<NMODE
             const uint32_t od = (uint32_t)ot.drop;
             const int strand = (int)((o_item >> 24) & 1u);
             const int p = (int)(o_item >> 25) - 16;
-            const uint32_t row = o_start + (g - o_excl);
-            uint2 e;
-            if constexpr (DIR) {
-                e.x = 0xFFFFFFFFu;      // entry index: read below, for the rows that pass
-                e.y = nr_core_insert(o_key, (int)od, (uint32_t)__ldcg(T4.q8[od] + row));
-            } else {
-                e = __ldcg(T4.ents[od] + row);
-            }
+            const uint2 e = __ldcg(T4.ents[od] + o_start + (g - o_excl));
             if constexpr (NMODE) {
                 // reads with N: diagonal walk with the N rows as wildcards here (sm.rdp holds a
                 // substituted variant; the N rows ignore their base), the N-aware automaton later
@@ -280,9 +249,6 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmemT<NMODE
                 vwhere = (uint32_t)strand | ((uint32_t)(p + 16) << 1);
             } else {
                 cost = nr_verify16(sm.rdp[strand], m, e.y, P.padL, P.padR, p, ot, &u);
-            }
-            if constexpr (DIR) {
-                if (cost < 3) e.x = __ldcg(&T4.ents[od][row].x);
             }
             k = (e.x << 1) | (uint32_t)strand;
             if (COUNT) { acc.c_ver++; if (!NMODE) acc.c_pass += cost < 3; }
@@ -379,7 +345,7 @@ __device__ __forceinline__ uint64_t probe_range(const uint32_t *__restrict__ bit
 
 // Place the hits of one work item (per-lane probe mask at (strand, p)) in the warp's queue,
 // draining it as often as needed.
-template <bool COUNT, bool NMODE, bool DIR>
+template <bool COUNT, bool NMODE>
 __device__ __forceinline__ void enqueue(const nr_filter_params &P, WarpSmemT<NMODE> &sm, Acc &acc, int m,
                                         const uint32_t *s_probes, const Tables &T4, uint64_t mask,
                                         int strand, int p)
@@ -394,7 +360,7 @@ __device__ __forceinline__ void enqueue(const nr_filter_params &P, WarpSmemT<NMO
         const uint32_t b = __ballot_sync(0xffffffffu, mine_all != 0);
         if (b == 0u) return;
         const int total = __popc(b);
-        while (acc.qn + total > NR_QCAP) drain<COUNT, NMODE, DIR>(P, sm, acc, m, s_probes, T4);
+        while (acc.qn + total > NR_QCAP) drain<COUNT, NMODE>(P, sm, acc, m, s_probes, T4);
         if (mine_all)
             sm.queue[acc.qn + __popc(b & ((1u << lane) - 1u))] =
                 where | ((uint32_t)(__ffsll((long long)mask) - 1) << 16);
@@ -416,7 +382,7 @@ __device__ __forceinline__ void enqueue(const nr_filter_params &P, WarpSmemT<NMO
             if ((int)lane >= o) incl += v;
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
-        while (acc.qn + total > NR_QCAP) drain<COUNT, NMODE, DIR>(P, sm, acc, m, s_probes, T4);
+        while (acc.qn + total > NR_QCAP) drain<COUNT, NMODE>(P, sm, acc, m, s_probes, T4);
         int pos = acc.qn + incl - mine;
         // queue item = (probe, strand, slot position); the key, its rank and its rows are worked
         // out in drain(), one hit per lane
@@ -434,7 +400,7 @@ __device__ __forceinline__ void enqueue(const nr_filter_params &P, WarpSmemT<NMO
 // -1) over all slots of both strands of the read staged in sm.rdp, drained at the end.
 // NMODE: the staged read is substituted variant `v`; slots that cannot reach a substituted N
 // position are skipped (nr_filter_core.h).
-template <bool COUNT, bool NMODE, bool DIR>
+template <bool COUNT, bool NMODE>
 __device__ __forceinline__ void run_stage(const nr_filter_params &P, WarpSmemT<NMODE> &sm, Acc &acc, int m,
                                           const uint32_t *s_probes, const Tables &s_tab,
                                           const uint32_t *__restrict__ bits_all, int stage, int p0,
@@ -466,7 +432,7 @@ __device__ __forceinline__ void run_stage(const nr_filter_params &P, WarpSmemT<N
             mask = probe_range<NR_PROBES_COST1>(bits_all, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_MAIN - NR_PROBES_COST1>{});
             if (COUNT) c_probes_n += slot_ok ? NR_PROBES_MAIN - NR_PROBES_COST1 : 0;
         }
-        enqueue<COUNT, NMODE, DIR>(P, sm, acc, m, s_probes, s_tab, mask, strand, p);
+        enqueue<COUNT, NMODE>(P, sm, acc, m, s_probes, s_tab, mask, strand, p);
     }
     if (stage == 2 && edge) {
         // one-column start overhang + interior insertion (slot -1 only)
@@ -481,9 +447,9 @@ __device__ __forceinline__ void run_stage(const nr_filter_params &P, WarpSmemT<N
             mask = (uint64_t)((w >> (key & 31u)) & 1u) << ti;
             if (COUNT) c_probes_n++;
         }
-        enqueue<COUNT, NMODE, DIR>(P, sm, acc, m, s_probes, s_tab, mask, strand, -1);
+        enqueue<COUNT, NMODE>(P, sm, acc, m, s_probes, s_tab, mask, strand, -1);
     }
-    while (acc.qn > 0) drain<COUNT, NMODE, DIR>(P, sm, acc, m, s_probes, s_tab);
+    while (acc.qn > 0) drain<COUNT, NMODE>(P, sm, acc, m, s_probes, s_tab);
 }
 
 // stage both strands of the packed read w4, padded, in shared memory
@@ -505,7 +471,7 @@ __device__ __forceinline__ void stage_read(WarpSmem &sm, const uint32_t w4[4], i
 // NR_FILTER_MIN_LEN bases) are handed to the N pass through list_n when there is one.
 // NMODE = true: the N pass over list_n -- reads with one or two N as substituted variants
 // (nr_filter_core.h), reads with more N on to the next tier.
-template <bool COUNT, bool NMODE, bool DIR>
+template <bool COUNT, bool NMODE>
 __global__ void __launch_bounds__(NR_FWARPS * 32, NR_FBLOCKS)
 nr_match_filtered_kernel(const nr_filter_params P)
 {
@@ -517,7 +483,6 @@ nr_match_filtered_kernel(const nr_filter_params P)
     if (threadIdx.x < 4) {
         s_tab.bits[threadIdx.x] = P.bits[threadIdx.x]; s_tab.rank[threadIdx.x] = P.rank[threadIdx.x];
         s_tab.ents[threadIdx.x] = P.ents[threadIdx.x]; s_tab.kstart[threadIdx.x] = P.kstart[threadIdx.x];
-        s_tab.dir[threadIdx.x] = P.dir[threadIdx.x]; s_tab.q8[threadIdx.x] = P.q8[threadIdx.x];
     }
     __syncthreads();
     const uint32_t lane = nr_lane();
@@ -607,7 +572,7 @@ nr_match_filtered_kernel(const nr_filter_params P)
 #pragma unroll 1
                     for (int stage = 0; stage < 3; stage++) {
                         if (acc.best < stage) break;
-                        run_stage<COUNT, false, DIR>(P, sm, acc, m, s_probes, s_tab, bits_all, stage, p0,
+                        run_stage<COUNT, false>(P, sm, acc, m, s_probes, s_tab, bits_all, stage, p0,
                                                 nP, edge, 0, 0, -1, c_probes_n);
                     }
                 } else {
@@ -627,7 +592,7 @@ nr_match_filtered_kernel(const nr_filter_params P)
                             uint32_t wv[4];
                             nr_nvar_apply(w4, n0, n1, v, wv);
                             stage_read(sm, wv, m);
-                            run_stage<COUNT, true, DIR>(P, sm, acc, m, s_probes, s_tab, bits_all, stage, p0,
+                            run_stage<COUNT, true>(P, sm, acc, m, s_probes, s_tab, bits_all, stage, p0,
                                                    nP, edge, v, n0, n1, c_probes_n);
                         }
                         // the rows parked by all variants of the round (any variant's bases serve:
@@ -722,29 +687,24 @@ int nr_launch_filtered(const nr_whitelist *wl, const void *d_bases, const uint8_
     P.list = d_list; P.list_count = d_list_count; P.counters = d_counters;
     P.list_n = d_list_n; P.list_n_count = d_list_n_count; P.nmask = d_nmask;
     P.tile_next = d_tile_next;
-    // dense whitelists (millions of entries: rank / kstart / rows exceed L2) take the word-directory
-    // variant; NR_FILTER_DIR=0 / 1 overrides the choice (A/B timing, tools/time_3m.py)
-    static const char *dir_env = getenv("NR_FILTER_DIR");
-    const bool use_dir = wl->d_dir[0] && (dir_env ? dir_env[0] == '1' : wl->n >= NR_FILTER_DIR_MIN_ENTRIES);
-    for (int j = 0; j < 4; j++) { P.dir[j] = wl->d_dir[j]; P.q8[j] = wl->d_q8[j]; }
-    using kernel_t = void (*)(const nr_filter_params);
-    const int ci = d_counters ? 1 : 0, di = use_dir ? 1 : 0;
-    static const kernel_t main_k[2][2] = {
-        {nr_match_filtered_kernel<false, false, false>, nr_match_filtered_kernel<false, false, true>},
-        {nr_match_filtered_kernel<true, false, false>, nr_match_filtered_kernel<true, false, true>}};
-    static const kernel_t n_k[2][2] = {
-        {nr_match_filtered_kernel<false, true, false>, nr_match_filtered_kernel<false, true, true>},
-        {nr_match_filtered_kernel<true, true, false>, nr_match_filtered_kernel<true, true, true>}};
     int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, wl->device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, main_k[ci][di], NR_FWARPS * 32, 0);
+    if (d_counters)
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nr_match_filtered_kernel<true, false>,
+                                                      NR_FWARPS * 32, 0);
+    else
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nr_match_filtered_kernel<false, false>,
+                                                      NR_FWARPS * 32, 0);
     if (per_sm < 1) per_sm = 1;
     uint64_t tiles = (n_cand + 31) / 32;
     uint64_t want = (tiles + NR_FWARPS - 1) / NR_FWARPS;
     uint64_t cap = (uint64_t)sms * (uint64_t)per_sm;
     unsigned grid = (unsigned)(want < cap ? want : cap);
     if (grid_out) *grid_out = (int)grid;
-    main_k[ci][di]<<<grid, NR_FWARPS * 32, 0, stream>>>(P);
+    if (d_counters)
+        nr_match_filtered_kernel<true, false><<<grid, NR_FWARPS * 32, 0, stream>>>(P);
+    else
+        nr_match_filtered_kernel<false, false><<<grid, NR_FWARPS * 32, 0, stream>>>(P);
     NR_CHECK_CUDA(cudaGetLastError());
     if (d_list_n) {
         // the N pass: how many reads it gets is only known on the device; a grid sized for one
@@ -753,7 +713,10 @@ int nr_launch_filtered(const nr_whitelist *wl, const void *d_bases, const uint8_
         // (each of its reads is a latency chain of several probe stages: the more warps the better)
         uint64_t want_n = (want + 1) / 2;
         unsigned grid_n = (unsigned)(want_n < cap ? (want_n ? want_n : 1) : cap);
-        n_k[ci][di]<<<grid_n, NR_FWARPS * 32, 0, stream>>>(P);
+        if (d_counters)
+            nr_match_filtered_kernel<true, true><<<grid_n, NR_FWARPS * 32, 0, stream>>>(P);
+        else
+            nr_match_filtered_kernel<false, true><<<grid_n, NR_FWARPS * 32, 0, stream>>>(P);
         NR_CHECK_CUDA(cudaGetLastError());
     }
     return NR_OK;

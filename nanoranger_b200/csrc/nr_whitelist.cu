@@ -46,8 +46,7 @@ __global__ void nr_index_keys_kernel(const uint32_t *__restrict__ lo, uint32_t n
 __global__ void nr_index_fill_kernel(const uint32_t *__restrict__ lo, uint32_t n,
                                      const uint32_t *__restrict__ keys,
                                      const uint32_t *__restrict__ vals, uint32_t *__restrict__ bits,
-                                     uint2 *__restrict__ ents, uint32_t *__restrict__ heads, int j,
-                                     uint8_t *__restrict__ q8)
+                                     uint2 *__restrict__ ents, uint32_t *__restrict__ heads)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -59,9 +58,7 @@ __global__ void nr_index_fill_kernel(const uint32_t *__restrict__ lo, uint32_t n
             atomicOr(&bits[(size_t)l * 4 * NR_BM_WORDS + (kl >> 5)], 1u << (kl & 31u));
         }
         uint32_t e = vals[i];
-        const uint32_t core = lo[e];
-        ents[i] = make_uint2(e, core);
-        q8[i] = (uint8_t)((core >> (8 * j)) & 0xFFu);
+        ents[i] = make_uint2(e, lo[e]);
         heads[i] = (i == 0 || keys[i - 1] != k) ? 1u : 0u;
     }
 }
@@ -81,7 +78,7 @@ __global__ void nr_index_kstart_kernel(const uint32_t *__restrict__ keys,
 // rank[w] = number of distinct keys < 32 w  (w in 0..2^19 inclusive)
 __global__ void nr_index_rank_kernel(const uint32_t *__restrict__ keys,
                                      const uint32_t *__restrict__ hs, uint32_t n,
-                                     uint32_t *__restrict__ rank, uint4 *__restrict__ dir)
+                                     uint32_t *__restrict__ rank)
 {
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w > NR_BM_WORDS) return;
@@ -91,24 +88,7 @@ __global__ void nr_index_rank_kernel(const uint32_t *__restrict__ keys,
         uint32_t mid = (a + b) >> 1;
         if ((uint64_t)keys[mid] < target) a = mid + 1; else b = mid;
     }
-    const uint32_t r = (a == n) ? hs[n - 1] : hs[a] - 1;
-    rank[w] = r;
-    if (w < NR_BM_WORDS) dir[w] = make_uint4(a, 0u, 0u, r);     // rows / distinct keys in front of the word
-}
-
-// row counts of the keys into the word directory (after nr_index_rank_kernel wrote x and w)
-__global__ void nr_index_dir_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ hs,
-                                    const uint32_t *__restrict__ kstart, uint32_t n,
-                                    uint4 *__restrict__ dir)
-{
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || (i != 0 && keys[i - 1] == keys[i])) return;
-    const uint32_t k = keys[i];
-    const uint32_t cnt = kstart[hs[i]] - i;
-    uint32_t *d = reinterpret_cast<uint32_t *>(dir + (k >> 5));
-    if (cnt > 3u) { atomicOr(d, 0x80000000u); return; }
-    if (cnt & 1u) atomicOr(d + 1, 1u << (k & 31u));
-    if (cnt & 2u) atomicOr(d + 2, 1u << (k & 31u));
+    rank[w] = (a == n) ? hs[n - 1] : hs[a] - 1;
 }
 
 static int code_of(char c)
@@ -197,28 +177,24 @@ extern "C" int nr_whitelist_create(const char *cores, uint64_t n, uint32_t core_
         for (int j = 0; j < 4; j++) {
             if (cudaMalloc(&w->d_rank[j], bmb) != cudaSuccess ||
                 cudaMalloc(&w->d_ents[j], n * sizeof(uint2)) != cudaSuccess ||
-                cudaMalloc(&w->d_kstart[j], (n + 1) * sizeof(uint32_t)) != cudaSuccess ||
-                cudaMalloc(&w->d_dir[j], (size_t)NR_BM_WORDS * sizeof(uint4)) != cudaSuccess ||
-                cudaMalloc(&w->d_q8[j], n) != cudaSuccess) {
+                cudaMalloc(&w->d_kstart[j], (n + 1) * sizeof(uint32_t)) != cudaSuccess) {
                 cudaFree(d_keys); cudaFree(d_vals); cudaFree(d_heads);
                 nr_set_error("cudaMalloc seed index");
                 return fail(NR_ENOMEM);
             }
-            w->bytes += (size_t)(1 + NR_BM_LAYOUTS) * bmb + n * sizeof(uint2) + (n + 1) * sizeof(uint32_t) +
-                        (size_t)NR_BM_WORDS * sizeof(uint4) + n;
+            w->bytes += (size_t)(1 + NR_BM_LAYOUTS) * bmb + n * sizeof(uint2) + (n + 1) * sizeof(uint32_t);
             nr_index_keys_kernel<<<blocks, 256>>>(w->d_lo, nn, j, d_keys, d_vals);
             thrust::stable_sort_by_key(thrust::device, thrust::device_pointer_cast(d_keys),
                                        thrust::device_pointer_cast(d_keys) + n,
                                        thrust::device_pointer_cast(d_vals));
             nr_index_fill_kernel<<<blocks, 256>>>(w->d_lo, nn, d_keys, d_vals, w->d_bits[j],
-                                                  w->d_ents[j], d_heads, j, w->d_q8[j]);
+                                                  w->d_ents[j], d_heads);
             thrust::inclusive_scan(thrust::device, thrust::device_pointer_cast(d_heads),
                                    thrust::device_pointer_cast(d_heads) + n,
                                    thrust::device_pointer_cast(d_heads));
             nr_index_kstart_kernel<<<blocks, 256>>>(d_keys, d_heads, nn, w->d_kstart[j]);
             nr_index_rank_kernel<<<(NR_BM_WORDS + 1 + 255) / 256, 256>>>(d_keys, d_heads, nn,
-                                                                         w->d_rank[j], w->d_dir[j]);
-            nr_index_dir_kernel<<<blocks, 256>>>(d_keys, d_heads, w->d_kstart[j], nn, w->d_dir[j]);
+                                                                         w->d_rank[j]);
         }
         cudaError_t e = cudaDeviceSynchronize();
         cudaFree(d_keys); cudaFree(d_vals); cudaFree(d_heads);
@@ -323,10 +299,7 @@ extern "C" void nr_whitelist_destroy(nr_whitelist_t *w)
     cudaFree(w->d_deep_ent_suf); cudaFree(w->d_deep_ent_idx);
     cudaFree(w->d_deep_suf_start); cudaFree(w->d_deep_sent_pre); cudaFree(w->d_deep_sent_idx);
     cudaFree(w->d_deep_pmid_rep); cudaFree(w->d_deep_smid_rep);
-    for (int j = 0; j < 4; j++) {
-        cudaFree(w->d_rank[j]); cudaFree(w->d_ents[j]); cudaFree(w->d_kstart[j]);
-        cudaFree(w->d_dir[j]); cudaFree(w->d_q8[j]);
-    }
+    for (int j = 0; j < 4; j++) { cudaFree(w->d_rank[j]); cudaFree(w->d_ents[j]); cudaFree(w->d_kstart[j]); }
     delete w;
     if (prev >= 0) cudaSetDevice(prev);
 }

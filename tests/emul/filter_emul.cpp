@@ -285,46 +285,4 @@ int nr_emul_filtered_n(const uint32_t *wl, int64_t n, int padL, int padR, const 
     return 0;
 }
 
-// Word directory of a key table (nr_filter_core.h: nr_dir_start / nr_dir_rows / nr_core_insert),
-// built here the way nr_whitelist.cu builds it on the device and read back the way the DIR variant
-// of the kernel reads it; compared with a plain scan of the sorted rows.  cores: n sorted-or-not
-// 32-bit cores; j: dropped quarter.  Returns the number of disagreements (0 expected).
-int nr_emul_dir_check(const uint32_t *cores, int64_t n, int j)
-{
-    std::vector<std::pair<uint32_t, uint32_t>> rows(n);      // (key, core), sorted by key (stable)
-    for (int64_t i = 0; i < n; i++) rows[i] = {nr_core_key(cores[i], j), cores[i]};
-    std::stable_sort(rows.begin(), rows.end(), [](auto &a, auto &b) { return a.first < b.first; });
-    const size_t W = (size_t)1 << 19;
-    std::vector<uint32_t> dx(W, 0), dy(W, 0), dz(W, 0);
-    std::vector<uint8_t> q8(n);
-    int64_t i = 0;
-    for (size_t w = 0; w < W; w++) {            // x = rows in front of the word
-        while (i < n && (rows[i].first >> 5) < w) i++;
-        dx[w] = (uint32_t)i;
-    }
-    for (i = 0; i < n;) {
-        int64_t e = i;
-        while (e < n && rows[e].first == rows[i].first) e++;
-        const uint32_t k = rows[i].first, cnt = (uint32_t)(e - i);
-        if (cnt > 3) dx[k >> 5] |= 0x80000000u;
-        else { if (cnt & 1) dy[k >> 5] |= 1u << (k & 31); if (cnt & 2) dz[k >> 5] |= 1u << (k & 31); }
-        for (int64_t r = i; r < e; r++) q8[r] = (uint8_t)((rows[r].second >> (8 * j)) & 0xFFu);
-        i = e;
-    }
-    int bad = 0;
-    for (i = 0; i < n;) {
-        int64_t e = i;
-        while (e < n && rows[e].first == rows[i].first) e++;
-        const uint32_t k = rows[i].first;
-        if (!(dx[k >> 5] >> 31)) {
-            if (nr_dir_start(dx[k >> 5], dy[k >> 5], dz[k >> 5], k & 31) != (uint32_t)i) bad++;
-            if (nr_dir_rows(dy[k >> 5], dz[k >> 5], k & 31) != (uint32_t)(e - i)) bad++;
-        }
-        for (int64_t r = i; r < e; r++)
-            if (nr_core_insert(k, j, q8[r]) != rows[r].second) bad++;
-        i = e;
-    }
-    return bad;
-}
-
 }  // extern "C"

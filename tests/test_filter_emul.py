@@ -316,24 +316,3 @@ def test_filter_n_reads_all_small_cost_variants(oracle, emul):
         ref, out, cnt = run_emul_n(emul, oracle, wl, cands, 30, 40)
         n_hi += check(ref, out, cands, wl)
     assert n_hi > 500
-
-
-@pytest.mark.parametrize("n", [3000, 400000])
-def test_word_directory_arithmetic(emul, n):
-    """nr_dir_start / nr_dir_rows / nr_core_insert (the DIR variant of the kernel, whitelists of
-    millions of entries) against a plain scan of the key-sorted rows: random cores -- dense enough
-    at 400 000 that words hold several keys and keys several rows -- plus crowded families that
-    differ in one quarter only (more than 3 rows per key: words marked irregular)."""
-    rng = np.random.default_rng(n)
-    cores = rng.integers(0, 1 << 22 if n > 10000 else 1 << 32, n, dtype=np.uint64).astype(np.uint32)
-    if n > 10000:
-        cores = (cores * np.uint32(1021)).astype(np.uint32) & np.uint32(0x3F3F3F3F)     # few distinct quarters
-    fam = rng.integers(0, 1 << 32, 40, dtype=np.uint64).astype(np.uint32)
-    extra = []
-    for j in range(4):
-        for f in fam[10 * j:10 * j + 10]:
-            for q in rng.integers(0, 256, int(rng.integers(2, 30))):
-                extra.append((int(f) & ~(0xFF << (8 * j))) | (int(q) << (8 * j)))
-    cores = np.unique(np.concatenate([cores, np.array(extra, np.uint32)]))
-    for j in range(4):
-        assert emul.nr_emul_dir_check(P(cores, C.c_uint32), C.c_int64(len(cores)), j) == 0
