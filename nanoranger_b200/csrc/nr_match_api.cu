@@ -107,6 +107,10 @@ int resolve_chain(const nr_whitelist *wl, const void *d_bases, const uint8_t *d_
         ex_list = listC; ex_cnt = cntC;
     } else if (from_all) {
         ex_list = nullptr; ex_cnt = nullptr;
+    } else {
+        // no deep tier on this whitelist: everything the filter left is the brute-force kernel's
+        // (list C's count is what nr_match_tier_counts reports for it)
+        NR_CHECK_CUDA(cudaMemcpyAsync(cntC, cntA, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     }
     int rc = nr_launch_exhaustive(wl, d_bases, d_meta, d_nmask, ex_list, ex_cnt, n, min_score, d_idx,
                                   d_score, d_nbest, d_flags, d_umi_q, sms * 2, ws + 128, st);

@@ -27,6 +27,9 @@
 //   merge    best cost / pairs attaining it / smallest pair, per thread, then over the block
 // The winner's UMI column and flags come from the same scalar pair DP the exhaustive kernel uses.
 // Candidates without any pair at cost <= K (or with more than 63 bases) go to the next tier's list.
+#include <cstdlib>
+#include <cstring>
+
 #include "nr_common.cuh"
 #include "nr_deep_core.h"
 #include "nr_ex_common.cuh"
@@ -523,10 +526,25 @@ size_t nr_deep_scratch_bytes(const nr_whitelist *wl, int K)
     return (size_t)sms * ((pb + 255) & ~(size_t)255);
 }
 
-// whether the tier can run at all on this whitelist (group minima must fit shared memory)
+// Whether the tier runs on this whitelist: the group minima must fit shared memory, and meeting in
+// the middle must share enough to beat the bit-parallel brute-force kernel it stands in front of.
+// One pass steps the plane automaton through `cols` group columns per strand (~60 instructions
+// each) where the brute force runs n * L entry columns (~18 each, 32 entries per instruction):
+// 737K-august-2016 has 11 K group columns against 11.8 M entry columns (and nearly every read a
+// pair at cost <= 3), a 17 K-entry slide-seq list 2e5 against 5.7e5 -- there a pass costs as much
+// as the brute force and most reads below the threshold fall through both passes anyway.
+// NR_DEEP_TIER=always / never overrides the rule (tests, A/B timing).
 int nr_deep_usable(const nr_whitelist *wl)
 {
-    return wl->has_deep && ((size_t)wl->deep_gpre + wl->deep_gsuf) <= DEEP_SMEM_MAX;
+    const char *e = getenv("NR_DEEP_TIER");
+    if (e && !strcmp(e, "never")) return 0;
+    if (!wl->has_deep || ((size_t)wl->deep_gpre + wl->deep_gsuf) > DEEP_SMEM_MAX) return 0;
+    if (e && !strcmp(e, "always")) return 1;
+    const int L = (int)wl->L, s = wl->deep_s, s1 = wl->deep_s1, u1 = wl->deep_u1;
+    const uint64_t cols = (uint64_t)wl->deep_gpmid * (uint64_t)s1 + (uint64_t)wl->deep_gpre * (uint64_t)(s - s1) +
+                          (uint64_t)wl->deep_gsmid * (uint64_t)u1 +
+                          (uint64_t)wl->deep_gsuf * (uint64_t)(L - s - u1);
+    return cols * 8 <= wl->n * (uint64_t)L;
 }
 
 // Enqueue the deep tier (K = 3 or 5) on `stream`: candidates of (d_list, d_list_count) -- or all

@@ -35,10 +35,12 @@ def test_auto_737k_every_score_exact(cuda_device, oracle):
 
 
 @pytest.mark.parametrize("pad_l,pad_r,qlen", [(30, 40, 50), (4, 17, 35), (2, 3, 30), (30, 40, 63)])
-def test_auto_small_whitelists_all_tiers(cuda_device, oracle, pad_l, pad_r, qlen):
+def test_auto_small_whitelists_all_tiers(cuda_device, oracle, pad_l, pad_r, qlen, monkeypatch):
     """small whitelists: most random reads have no pair at cost <= 3, so K = 5 and the brute-force
-    kernel get work too."""
+    kernel get work too.  (Left to itself the API skips the deep tier on a list that shares this
+    little -- nr_deep_usable's cost rule -- hence NR_DEEP_TIER=always; the rule has its own test.)"""
     from nanoranger_b200 import NR_MODE_AUTO, Whitelist
+    monkeypatch.setenv("NR_DEEP_TIER", "always")
     rng = np.random.default_rng(300 + qlen)
     wl_strs = tie_rich_whitelist(rng, 3000)
     seqs = mixed_candidates(rng, wl_strs, 2500, pad_l, qlen, with_n=0.1)
@@ -52,10 +54,11 @@ def test_auto_small_whitelists_all_tiers(cuda_device, oracle, pad_l, pad_r, qlen
     assert t["deep_k3"] + t["deep_k5"] + t["brute_force"] == t["left_by_filter"]
 
 
-def test_auto_without_seed_index_goes_through_deep_tier(cuda_device, oracle):
+def test_auto_without_seed_index_goes_through_deep_tier(cuda_device, oracle, monkeypatch):
     """cores no seed filter covers (20 columns, N columns in some entries): no seed index, AUTO =
-    deep tier over every candidate."""
+    deep tier over every candidate (forced: 4 000 random cores share too little for the cost rule)."""
     from nanoranger_b200 import NR_MODE_AUTO, Whitelist
+    monkeypatch.setenv("NR_DEEP_TIER", "always")
     rng = np.random.default_rng(9)
     bcs = set()
     while len(bcs) < 4000:
@@ -79,6 +82,44 @@ def test_auto_without_seed_index_goes_through_deep_tier(cuda_device, oracle):
     compare(ref, res, 18, exact_below=True, label="auto 20-column cores")
     t = wl.tier_counts(ws)
     assert t["deep_k3"] > 1000, t
+
+
+def test_deep_tier_cost_rule(cuda_device, oracle, monkeypatch):
+    """nr_deep_usable: a small random list shares too little between its entries for meeting in the
+    middle to beat the bit-parallel brute-force kernel -- AUTO sends what the filter leaves straight
+    there; the 737K list keeps the deep tier; NR_DEEP_TIER=never / always override.  Bit-exact in
+    every combination."""
+    from nanoranger_b200 import NR_MODE_AUTO, Whitelist, synth, whitelists
+    rng = np.random.default_rng(12)
+    wl_strs = tie_rich_whitelist(rng, 3000)
+    seqs = mixed_candidates(rng, wl_strs, 1200, 30, 50, with_n=0.1)
+    wl = Whitelist(wl_strs, 30, 40)
+    ref = _oracle(oracle, wl_strs, 30, 40, seqs)
+    for setting, deep in ((None, False), ("always", True), ("never", False)):
+        if setting is None:
+            monkeypatch.delenv("NR_DEEP_TIER", raising=False)
+        else:
+            monkeypatch.setenv("NR_DEEP_TIER", setting)
+        res, ws = _run_device(wl, seqs, 14, NR_MODE_AUTO)
+        compare(ref, res, 14, exact_below=True, label=f"small list, NR_DEEP_TIER={setting}")
+        t = wl.tier_counts(ws)
+        assert (t["deep_k3"] + t["deep_k5"] > 0) == deep, (setting, t)
+        assert t["deep_k3"] + t["deep_k5"] + t["brute_force"] == t["left_by_filter"]
+    wl_a = whitelists.load_737k()
+    d = synth.make_candidates(wl_a, 400, seed=5, frac_negative=0.5)
+    seqs = synth.to_strings(d["seqs"], d["offsets"])
+    wl = Whitelist(wl_a, 30, 40)
+    cc, cl = oracle.encode_many(seqs, 64)
+    ref = oracle.match(oracle._CODE[wl_a], 30, 40, cc, cl)
+    for setting, deep in ((None, True), ("never", False)):
+        if setting is None:
+            monkeypatch.delenv("NR_DEEP_TIER", raising=False)
+        else:
+            monkeypatch.setenv("NR_DEEP_TIER", setting)
+        res, ws = _run_device(wl, seqs, 14, NR_MODE_AUTO)
+        compare(ref, res, 14, exact_below=True, label=f"737K, NR_DEEP_TIER={setting}")
+        t = wl.tier_counts(ws)
+        assert (t["deep_k3"] + t["deep_k5"] > 0) == deep, (setting, t)
 
 
 @pytest.mark.parametrize("mode_name", ["filtered", "auto"])

@@ -21,11 +21,26 @@ dev = torch.device("cuda:0")
 d_seqs = torch.from_numpy(buf.copy()).to(dev); d_off = torch.from_numpy(off.view(np.int64).copy()).to(dev)
 bases, meta, nmask = wl.pack_device(d_seqs, d_off)
 ws = wl.workspace(n, dev)
-for mode, name in ((NR_MODE_FILTERED, "filtered"), (NR_MODE_AUTO, "auto")):
-    out = wl.match_device(bases, meta, nmask, min_score=30, mode=mode, workspace=ws)
+def timed(mode, reps=4, warm=2):
+    for _ in range(warm):
+        out = wl.match_device(bases, meta, nmask, min_score=30, mode=mode, workspace=ws)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); out = wl.match_device(bases, meta, nmask, min_score=30, mode=mode, workspace=ws); e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    print(f"slide-seq {name}: {n} candidates x {len(cores)} entries: {ms:.1f} ms, {n/ms*1e3:.3e} cand/s, "
-          f"assigned {float(out.assigned(30).float().mean()):.3f}, tiers {wl.tier_counts(ws)}")
+    e0.record()
+    for _ in range(reps):
+        out = wl.match_device(bases, meta, nmask, min_score=30, mode=mode, workspace=ws)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, out
+
+
+# AUTO three ways: the API's own choice (nr_deep_usable's cost rule), deep tier forced, deep tier off
+for mode, name, deep in ((NR_MODE_FILTERED, "filtered", None), (NR_MODE_AUTO, "auto", None),
+                         (NR_MODE_AUTO, "auto", "always"), (NR_MODE_AUTO, "auto", "never")):
+    if deep is None:
+        os.environ.pop("NR_DEEP_TIER", None)
+    else:
+        os.environ["NR_DEEP_TIER"] = deep
+    ms, out = timed(mode)
+    print(f"slide-seq {name} (NR_DEEP_TIER={deep}): {n} candidates x {len(cores)} entries: {ms:.1f} ms, "
+          f"{n/ms*1e3:.3e} cand/s, assigned {float(out.assigned(30).float().mean()):.3f}, "
+          f"tiers {wl.tier_counts(ws)}", flush=True)
