@@ -739,6 +739,13 @@ def run_flanks(args, ctx):
                 "peak_gbs": pk.get("hbm_gbs"), "peak_kind": pk_kind,
                 "frac": alg_bytes * B / (ms_step * 1e-3) / 1e9 / pk.get("hbm_gbs")},
     }
+    if dp is not None and rank == 0:
+        # the bit-parallel kernel against the same ALU-pipe peak.  A thread executes 13.7 ALU-pipe
+        # instructions per word of 32 cells (profiles/r2b_bitsliced_ncu.md: 16.5 instructions per
+        # cell word issued, 83 % of them on the ALU pipe; the row loop alone is 11.4: 157 LOP3 per
+        # 16 cells + 25 per row for the last column), i.e. 13.7 / 32 lane-operations per cell
+        dp["alu_inst_per_32_cells"] = 13.7
+        dp["frac_of_alu_peak"] = dp["value"] / world * (13.7 / 32.0) / lanes_peak
     line = {
         "metric": "barcode_candidates_per_sec", "value": value, "unit": "candidates/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,

@@ -43,9 +43,9 @@ def short(name):
 PHASES = [
     ("flanks-filtered", ["nr_pack_kernel", "nr_match_filtered_kernel<0, 0>", "nr_match_filtered_kernel<0, 1>",
                          "nr_match_deep_kernel", "nr_match_deep_kernel", "nr_deep_finalize_kernel",
-                         "nr_match_exhaustive16_kernel",
+                         "nr_match_bitsliced_kernel",
                          "nr_match_filtered_kernel<1, 0>", "nr_match_filtered_kernel<1, 1>", "nr_match_deep_kernel",
-                         "nr_match_deep_kernel", "nr_deep_finalize_kernel", "nr_match_exhaustive16_kernel"]),
+                         "nr_match_deep_kernel", "nr_deep_finalize_kernel", "nr_match_bitsliced_kernel"]),
 ]
 
 
