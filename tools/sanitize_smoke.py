@@ -19,6 +19,20 @@ for mode in (NR_MODE_FILTERED, NR_MODE_AUTO):
 res_c = wl.match_device(bases, meta, nmask, min_score=14, counted=True)
 ex = wl.match_device(bases[:40], meta[:40], nmask[:40], min_score=14, mode=NR_MODE_EXHAUSTIVE)
 h = wl.match_host(seqs, min_score=14, mode=NR_MODE_FILTERED)
+# 32-column cores with N columns: anchored filter, then the bit-parallel brute force (<32, N>);
+# a ragged whitelist (n % 32 != 0) and a batch smaller than the grid (whitelist slicing)
+import gzip
+from nanoranger_b200.whitelists import LINKER_SLIDESEQ
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+bcs = gzip.open(os.path.join(R, "tests", "golden", "slideseq_whitelist.txt.gz"), "rt").read().split()[:3001]
+wl_s = np.frombuffer("".join(b[:8] + LINKER_SLIDESEQ + b[8:] for b in bcs).encode(), np.uint8).reshape(len(bcs), 32)
+ds = synth.make_candidates(wl_s, 500, seed=5, geometry="slideseq", p_n=0.01)
+sseqs = synth.to_strings(ds["seqs"], ds["offsets"])
+wls = Whitelist(wl_s, 15, 24)
+for mode in (NR_MODE_AUTO, NR_MODE_EXHAUSTIVE):
+    wls.match_host(sseqs, min_score=30, mode=mode)
+wls.match_host(sseqs[:7], min_score=30, mode=NR_MODE_EXHAUSTIVE)
+wls.close()
 gene = torch.arange(len(seqs), dtype=torch.int32, device=dev) % 5
 rec = U.records_device(bases, meta, nmask, res, 14, 12, gene=gene)
 rows, counts = U.partition_device(rec["bc"], rec["gene"], rec["umi"], 4)
