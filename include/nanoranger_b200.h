@@ -48,9 +48,11 @@ extern "C" {
 
 /* matcher modes */
 #define NR_MODE_AUTO 0        /* exact at every score: seed filter where the whitelist geometry
-                                 allows it, deep tier (meet in the middle) for what it leaves,
+                                 allows it, deep tier (meet in the middle) for what it leaves
+                                 where the whitelist shares enough columns for it to pay,
                                  brute-force DP for the rest                                     */
-#define NR_MODE_EXHAUSTIVE 1  /* brute-force DP over every (entry, strand) pair                  */
+#define NR_MODE_EXHAUSTIVE 1  /* brute-force DP over every (entry, strand) pair (bit-parallel,
+                                 32 entries per thread, for 16- and 32-column cores)             */
 #define NR_MODE_FILTERED 2    /* lossless seed filter + exact verification; exact for
                                  score >= min_score; requires a seed index
                                  (nr_whitelist_has_index) and min_score >= L - 2                 */
@@ -252,7 +254,8 @@ int nr_match_counters(const void *d_workspace, uint64_t *c5, void *stream);
  * 32 co-optimal pairs, and in NR_MODE_AUTO every read below the threshold) or, on whitelists
  * without a seed index, 0; t[1] resolved by the deep tier at cost <= 3, t[2] at cost <= 5
  * (meet-in-the-middle over the whole whitelist, nr_match_deep.cu); t[3] left to the brute-force
- * DP kernel.  These are the reads whose scores fill the low tail of `_barcode_scores.csv`
+ * DP kernel (all of t[0] on whitelists where the deep tier does not pay: nr_match_deep.cu,
+ * nr_deep_usable).  These are the reads whose scores fill the low tail of `_barcode_scores.csv`
  * (utils.py:698, 728-730). */
 int nr_match_tier_counts(const void *d_workspace, uint64_t *t4, void *stream);
 
