@@ -42,6 +42,7 @@
 #endif
 #define NR_QCAP 480                        // queue slots per warp
 #define NR_VQCAP 64                        // N pass: rows waiting for the N-aware automaton, per warp
+#define NR_COV_SPAN 20                     // a probe's key reads bases p .. p + 19 at most
 
 struct nr_filter_params {
     const uint32_t *bits[4];      // key bitmap, 2^19 words per dropped quarter, contiguous:
@@ -199,7 +200,13 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmemT<NMODE
     const uint32_t d = (uint32_t)t.drop;
     uint32_t start = 0, rows = 0;
     if (have && h_p + nr_probe_first(t) >= 0 && h_p + nr_probe_end(t) <= m) {
-        const uint32_t key = nr_probe_key(nr_window64(sm.rdp[h_strand], h_p), t);
+        uint64_t hW = nr_window64(sm.rdp[h_strand], h_p);
+        if constexpr (NMODE) {
+            // hits of the merged variant pass carry their variant: sm.rdp holds the base variant
+            const int hv = (int)(item & 15u);
+            if (hv) hW = nr_nvar_window(hW, h_p, hv, __ffsll((long long)sm.nm[h_strand]) - 1, -1);
+        }
+        const uint32_t key = nr_probe_key(hW, t);
         const uint32_t w = __ldg(T4.bits[0] + (((d << 24) | key) >> 5));
         // rank / kstart / rows are touched once per hit: keep them out of L1 (L2 only) so that the
         // bitmap sectors stay
@@ -235,6 +242,7 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmemT<NMODE
         const uint32_t o_item = __shfl_sync(0xffffffffu, item, lo);
         int cost = 3, u = -1;
         uint32_t k = 0, vcore = 0, vwhere = 0;
+        bool park = false;
         if (active) {
             const nr_probe_t ot = probe_unpack(s_probes[(o_item >> 16) & 63u]);
             const uint32_t od = (uint32_t)ot.drop;
@@ -242,30 +250,35 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmemT<NMODE
             const int p = (int)(o_item >> 25) - 16;
             const uint2 e = __ldcg(T4.ents[od] + o_start + (g - o_excl));
             if constexpr (NMODE) {
-                // reads with N: diagonal walk with the N rows as wildcards here (sm.rdp holds a
-                // substituted variant; the N rows ignore their base), the N-aware automaton later
-                cost = nr_prefilter16n(sm.rdp[strand], sm.nm[strand], m, e.y, p, ot) ? 0 : 3;
-                vcore = e.y;
-                vwhere = (uint32_t)strand | ((uint32_t)(p + 16) << 1);
+                // reads with N.  Rows whose diagonal walk is exact and reads no N (nr_lv_clean) are
+                // verified like rows of a plain read; the others: diagonal walk with the N rows as
+                // wildcards here (sm.rdp holds a substituted variant; the N rows ignore their base),
+                // the N-aware automaton later
+                if (nr_lv_clean(sm.nm[strand], m, p, ot)) {
+                    cost = nr_verify16(sm.rdp[strand], m, e.y, P.padL, P.padR, p, ot, &u);
+                } else {
+                    park = nr_prefilter16n(sm.rdp[strand], sm.nm[strand], m, e.y, p, ot);
+                    vcore = e.y;
+                    vwhere = (uint32_t)strand | ((uint32_t)(p + 16) << 1);
+                }
             } else {
                 cost = nr_verify16(sm.rdp[strand], m, e.y, P.padL, P.padR, p, ot, &u);
             }
             k = (e.x << 1) | (uint32_t)strand;
-            if (COUNT) { acc.c_ver++; if (!NMODE) acc.c_pass += cost < 3; }
+            if (COUNT) { acc.c_ver++; acc.c_pass += cost < 3; }
         }
         if constexpr (NMODE) {
             // park the survivors of the wildcard walk; score them a full warp at a time
-            const uint32_t bal = __ballot_sync(0xffffffffu, cost < 3);
+            const uint32_t bal = __ballot_sync(0xffffffffu, park);
             if (bal) {
-                if (cost < 3)
+                if (park)
                     sm.vq[acc.vn + __popc(bal & ((1u << lane) - 1u))] = make_uint4(k >> 1, vcore, vwhere, 0u);
                 acc.vn += __popc(bal);
                 __syncwarp();
                 if (acc.vn > NR_VQCAP - 32) flush_vq<COUNT>(P, sm, acc, m);
             }
-        } else {
-            merge_batch(acc, cost, k, u);
         }
+        merge_batch(acc, cost, k, u);
     }
 }
 
@@ -348,12 +361,13 @@ __device__ __forceinline__ uint64_t probe_range(const uint32_t *__restrict__ bit
 template <bool COUNT, bool NMODE>
 __device__ __forceinline__ void enqueue(const nr_filter_params &P, WarpSmemT<NMODE> &sm, Acc &acc, int m,
                                         const uint32_t *s_probes, const Tables &T4, uint64_t mask,
-                                        int strand, int p)
+                                        int strand, int p, int v = 0)
 {
     const uint32_t lane = nr_lane();
     // an item with more hits than the queue holds (dense key bitmaps: whitelists of millions of
     // entries) is queued in four probe ranges of <= 9 x 32 hits
-    const uint32_t where = ((uint32_t)strand << 24) | ((uint32_t)(p + 16) << 25);
+    // item = variant (N pass, merged variant stage) | probe << 16 | strand << 24 | (slot + 16) << 25
+    const uint32_t where = (uint32_t)v | ((uint32_t)strand << 24) | ((uint32_t)(p + 16) << 25);
     const int mine_all = __popcll(mask);
     // common case: no lane holds more than one hit -> positions from one ballot
     if (!__any_sync(0xffffffffu, mine_all > 1)) {
@@ -405,7 +419,7 @@ __device__ __forceinline__ void run_stage(const nr_filter_params &P, WarpSmemT<N
                                           const uint32_t *s_probes, const Tables &s_tab,
                                           const uint32_t *__restrict__ bits_all, int stage, int p0,
                                           int nP, bool edge, int v, int n0, int n1,
-                                          unsigned long long &c_probes_n)
+                                          unsigned long long &c_probes_n, const uint64_t *s_cov = nullptr)
 {
     const uint32_t lane = nr_lane();
     const int nslots = nP > 0 ? 2 * nP : 0;
@@ -432,6 +446,12 @@ __device__ __forceinline__ void run_stage(const nr_filter_params &P, WarpSmemT<N
             mask = probe_range<NR_PROBES_COST1>(bits_all, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_MAIN - NR_PROBES_COST1>{});
             if (COUNT) c_probes_n += slot_ok ? NR_PROBES_MAIN - NR_PROBES_COST1 : 0;
         }
+        if (NMODE && v != 0) {
+            // probes whose key does not read a substituted position only repeat an earlier lookup
+            const int a0 = (strand ? m - 1 - n0 : n0) - p, a1 = n1 < 0 ? -1 : (strand ? m - 1 - n1 : n1) - p;
+            if ((v & 3) != 0) mask &= (a0 >= 0 && a0 < NR_COV_SPAN) ? s_cov[a0] : 0ull;
+            if ((v >> 2) != 0) mask &= (a1 >= 0 && a1 < NR_COV_SPAN) ? s_cov[a1] : 0ull;
+        }
         enqueue<COUNT, NMODE>(P, sm, acc, m, s_probes, s_tab, mask, strand, p);
     }
     if (stage == 2 && edge) {
@@ -450,6 +470,49 @@ __device__ __forceinline__ void run_stage(const nr_filter_params &P, WarpSmemT<N
         enqueue<COUNT, NMODE>(P, sm, acc, m, s_probes, s_tab, mask, strand, -1);
     }
     while (acc.qn > 0) drain<COUNT, NMODE>(P, sm, acc, m, s_probes, s_tab);
+}
+
+// N pass, reads with ONE N: stage `stage` (0 or 1) of the three substituted variants in one go.
+// Lane = (variant, strand, slot) over the slots whose probes can read the N (0 <= N - p < span);
+// the variant's window is the base variant's (staged in sm.rdp) with the base XORed in, the hits
+// carry the variant for drain(), and probes whose key does not read the N are masked
+// (nr_filter_core.h: nr_nvar_window, nr_nvar_probe_needed).
+template <bool COUNT>
+__device__ __forceinline__ void run_variants_1n(const nr_filter_params &P, WarpSmemN &sm, Acc &acc, int m,
+                                                const uint32_t *s_probes, const Tables &s_tab,
+                                                const uint32_t *__restrict__ bits_all, int stage, int p0,
+                                                int p1, int n0, const uint64_t *s_cov,
+                                                unsigned long long &c_probes_n)
+{
+    const uint32_t lane = nr_lane();
+    const int pos0 = n0, pos1 = m - 1 - n0;                  // the N on either strand
+    const int lo0 = max(p0, pos0 - (NR_COV_SPAN - 1)), hi0 = min(p1, pos0);
+    const int lo1 = max(p0, pos1 - (NR_COV_SPAN - 1)), hi1 = min(p1, pos1);
+    const int cnt0 = max(0, hi0 - lo0 + 1), cnt1 = max(0, hi1 - lo1 + 1);
+    const int per = cnt0 + cnt1, nitems = 3 * per;
+#pragma unroll 1
+    for (int it0 = 0; it0 < nitems; it0 += 32) {
+        const int id = it0 + (int)lane;
+        const bool ok = id < nitems;
+        const int vi = ok ? id / per : 0;
+        const int rem = id - vi * per;
+        const int v = vi + 1;
+        const int strand = rem >= cnt0 ? 1 : 0;
+        const int p = strand ? lo1 + rem - cnt0 : lo0 + rem;
+        const int rel = (strand ? pos1 : pos0) - p;           // 0 .. NR_COV_SPAN - 1 when ok
+        const uint64_t W = ok ? (nr_window64(sm.rdp[strand], p) ^ ((uint64_t)v << (2 * rel))) : 0ull;
+        uint64_t mask;
+        if (stage == 0) {
+            mask = probe_range<0>(bits_all, W, ok, std::make_integer_sequence<int, NR_PROBES_COST0>{});
+            if (COUNT) c_probes_n += ok ? NR_PROBES_COST0 : 0;
+        } else {
+            mask = probe_range<NR_PROBES_COST0>(bits_all, W, ok, std::make_integer_sequence<int, NR_PROBES_COST1 - NR_PROBES_COST0>{});
+            if (COUNT) c_probes_n += ok ? NR_PROBES_COST1 - NR_PROBES_COST0 : 0;
+        }
+        if (ok) mask &= s_cov[rel];
+        enqueue<COUNT, true>(P, sm, acc, m, s_probes, s_tab, mask, strand, p, ok ? v : 0);
+    }
+    while (acc.qn > 0) drain<COUNT, true>(P, sm, acc, m, s_probes, s_tab);
 }
 
 // stage both strands of the packed read w4, padded, in shared memory
@@ -478,6 +541,15 @@ nr_match_filtered_kernel(const nr_filter_params P)
     __shared__ WarpSmemT<NMODE> smem[NR_FWARPS];
     __shared__ uint32_t s_probes[64];
     __shared__ Tables s_tab;
+    // N pass: for every position r relative to a slot, the probes whose key reads base p + r
+    __shared__ uint64_t s_cov[NMODE ? NR_COV_SPAN : 1];
+    if (NMODE && threadIdx.x >= 64 && threadIdx.x < 64 + NR_COV_SPAN) {
+        const int r = (int)threadIdx.x - 64;
+        uint64_t c = 0;
+        for (int T = 0; T < NR_PROBES_ALL; T++)
+            if ((nr_probe_cover(c_probes[T]) >> r) & 1u) c |= 1ull << T;
+        s_cov[r] = c;
+    }
     if (threadIdx.x < 64)
         s_probes[threadIdx.x] = threadIdx.x < NR_PROBES_ALL ? probe_pack(c_probes[threadIdx.x]) : 0u;
     if (threadIdx.x < 4) {
@@ -582,6 +654,24 @@ nr_match_filtered_kernel(const nr_filter_params P)
                     const int n1 = n_n == 2 ? 63 - __clzll((long long)nm) : -1;
                     if (lane == 0) { sm.nm[0] = nm; sm.nm[1] = __brevll(nm) >> (64 - m); }
                     const int nvar = nr_nvar_count(n_n);
+                    if (n_n == 1) {
+                        // one N (nearly every read of this pass): the base variant is staged once;
+                        // its stage `round`, then stage `round - 1` of the three substituted variants
+                        // together, their windows derived from the staged one
+                        uint32_t wv[4];
+                        nr_nvar_apply(w4, n0, -1, 0, wv);
+                        stage_read(sm, wv, m);
+#pragma unroll 1
+                        for (int round = 0; round < 3; round++) {
+                            if (acc.best < round) break;
+                            run_stage<COUNT, true>(P, sm, acc, m, s_probes, s_tab, bits_all, round, p0, nP,
+                                                   edge, 0, n0, -1, c_probes_n, s_cov);
+                            if (round >= 1)
+                                run_variants_1n<COUNT>(P, sm, acc, m, s_probes, s_tab, bits_all, round - 1, p0,
+                                                       p1, n0, s_cov, c_probes_n);
+                            flush_vq<COUNT>(P, sm, acc, m);
+                        }
+                    } else {
 #pragma unroll 1
                     for (int round = 0; round < 3; round++) {
                         if (acc.best < round) break;
@@ -593,11 +683,12 @@ nr_match_filtered_kernel(const nr_filter_params P)
                             nr_nvar_apply(w4, n0, n1, v, wv);
                             stage_read(sm, wv, m);
                             run_stage<COUNT, true>(P, sm, acc, m, s_probes, s_tab, bits_all, stage, p0,
-                                                   nP, edge, v, n0, n1, c_probes_n);
+                                                   nP, edge, v, n0, n1, c_probes_n, s_cov);
                         }
                         // the rows parked by all variants of the round (any variant's bases serve:
                         // variants differ at the N rows only, and those ignore their base)
                         flush_vq<COUNT>(P, sm, acc, m);
+                    }
                     }
                 }
 
