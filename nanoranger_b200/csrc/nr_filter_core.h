@@ -329,37 +329,6 @@ NR_HD bool nr_nvar_slot_needed(int v, int p, int n0s, int n1s)   // N positions 
     if ((v >> 2) != 0 && !nr_slot_reaches(p, n1s)) return false;
     return true;
 }
-// Read positions (relative to the slot) the key of probe t is made of: bit r set for base p + r.
-// The interior base a "5-mer minus one" quarter drops is not part of the key.
-NR_HD uint32_t nr_probe_cover(const nr_probe_t &t)
-{
-    const int o[3] = {t.o0, t.o1, t.o2};
-    uint32_t c = 0;
-    for (int k = 0; k < 3; k++)
-        c |= (t.var == k ? (0x1Fu & ~(1u << t.del)) : 0xFu) << o[k];
-    return c;
-}
-// A probe whose key does not read a substituted position has the same key as in the variant with
-// that substitution zeroed, which looks it up in the same or an earlier round, and the rows it
-// nominates are scored against the ORIGINAL read either way: the lookup would only repeat work.
-NR_HD bool nr_nvar_probe_needed(int v, int p, const nr_probe_t &t, int n0s, int n1s)
-{
-    const uint32_t c = nr_probe_cover(t);
-    if ((v & 3) != 0) { const int r = n0s - p; if (r < 0 || r > 31 || !((c >> r) & 1u)) return false; }
-    if ((v >> 2) != 0) { const int r = n1s - p; if (r < 0 || r > 31 || !((c >> r) & 1u)) return false; }
-    return true;
-}
-// window of variant v from the window W0 of the variant with base 0 at the N's (base 0 of the
-// windows = read position p of the slot's strand; n0s / n1s on that strand, n1s < 0: one N).  On
-// the reverse-complement strand the N carries 3 - b = 3 ^ b where the forward strand carries b,
-// and the base-0 variant carries 3 there: an XOR on either strand.
-NR_HD uint64_t nr_nvar_window(uint64_t W0, int p, int v, int n0s, int n1s)
-{
-    const int r0 = n0s - p, r1 = n1s - p;
-    if ((v & 3) != 0 && r0 >= 0 && r0 < 32) W0 ^= (uint64_t)(v & 3) << (2 * r0);
-    if ((v >> 2) != 0 && n1s >= 0 && r1 >= 0 && r1 < 32) W0 ^= (uint64_t)((v >> 2) & 3) << (2 * r1);
-    return W0;
-}
 // the four packed words of variant v (n1 < 0: one N)
 NR_HD void nr_nvar_apply(const uint32_t in[4], int n0, int n1, int v, uint32_t out[4])
 {
@@ -561,27 +530,9 @@ NR_HD int nr_score16n(const uint32_t *rdp, uint64_t nm, int m, uint32_t core, in
                        nr_rows_last(p, m), umi);
 }
 
-// Where the pinned end of the probe is in the read interior nr_verify16 is exact from the 19 bases
-// next to it alone (forward: rows pinned - 1 .. pinned + 17, backward: pinned - 18 .. pinned) plus
-// the lengths of the read's prefix and suffix: with no N among those rows the read's N's do not
-// enter, and the row can be verified like a row of a read without N.
-NR_HD bool nr_lv_clean(uint64_t nm, int m, int p, const nr_probe_t &t)
-{
-    const int fwd = t.drop != 0;
-    const int pinned = fwd ? p : p + nr_probe_end(t);
-    const int interior = fwd ? (pinned >= 0 && pinned + 18 <= m) : (pinned >= 19 && pinned <= m);
-    if (!interior) return false;
-    int lo = fwd ? pinned - 1 : pinned - 18, hi = fwd ? pinned + 17 : pinned;     // inclusive
-    if (lo < 0) lo = 0;
-    if (hi > 63) hi = 63;
-    const uint64_t span = (hi - lo + 1 >= 64) ? ~0ull : ((1ull << (hi - lo + 1)) - 1ull);
-    return ((nm >> lo) & span) == 0ull;
-}
-
 NR_HD int nr_verify16n(const uint32_t *rdp, uint64_t nm, int m, uint32_t core, int padL, int padR,
                        int p, const nr_probe_t &t, int *umi)
 {
-    if (nr_lv_clean(nm, m, p, t)) return nr_verify16(rdp, m, core, padL, padR, p, t, umi);
     if (!nr_prefilter16n(rdp, nm, m, core, p, t)) { *umi = -1; return 3; }
     return nr_score16n(rdp, nm, m, core, padL, padR, p, umi);
 }

@@ -42,7 +42,6 @@
 #endif
 #define NR_QCAP 480                        // queue slots per warp
 #define NR_VQCAP 64                        // N pass: rows waiting for the N-aware automaton, per warp
-#define NR_COV_SPAN 20                     // a probe's key reads bases p .. p + 19 at most
 
 struct nr_filter_params {
     const uint32_t *bits[4];      // key bitmap, 2^19 words per dropped quarter, contiguous:
@@ -152,16 +151,6 @@ __device__ __forceinline__ void merge_batch(Acc &acc, int cost, uint32_t k, int 
     }
 }
 
-// nr_verify16 as a real function: the N pass is bound by instruction fetch and drain() is inlined
-// in five places.  Returns cost | (umi + 1) << 2.
-__device__ __noinline__ int verify16_call(const uint32_t *rdp, int m, uint32_t core, int padL, int padR,
-                                          int p, uint32_t probe_packed)
-{
-    int u;
-    const int c = nr_verify16(rdp, m, core, padL, padR, p, probe_unpack(probe_packed), &u);
-    return (c & 3) | ((u + 1) << 2);
-}
-
 // N pass: score up to 32 waiting rows with the N-aware automaton, one row per lane.  The automaton
 // costs ~800 instructions per row and only a lane or two of a verification batch survive the
 // wildcard walk: scoring them where they arise would run it at 2 active lanes (ncu), so survivors
@@ -210,13 +199,7 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmemT<NMODE
     const uint32_t d = (uint32_t)t.drop;
     uint32_t start = 0, rows = 0;
     if (have && h_p + nr_probe_first(t) >= 0 && h_p + nr_probe_end(t) <= m) {
-        uint64_t hW = nr_window64(sm.rdp[h_strand], h_p);
-        if constexpr (NMODE) {
-            // hits of the merged variant pass carry their variant: sm.rdp holds the base variant
-            const int hv = (int)(item & 15u);
-            if (hv) hW = nr_nvar_window(hW, h_p, hv, __ffsll((long long)sm.nm[h_strand]) - 1, -1);
-        }
-        const uint32_t key = nr_probe_key(hW, t);
+        const uint32_t key = nr_probe_key(nr_window64(sm.rdp[h_strand], h_p), t);
         const uint32_t w = __ldg(T4.bits[0] + (((d << 24) | key) >> 5));
         // rank / kstart / rows are touched once per hit: keep them out of L1 (L2 only) so that the
         // bitmap sectors stay
@@ -252,7 +235,6 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmemT<NMODE
         const uint32_t o_item = __shfl_sync(0xffffffffu, item, lo);
         int cost = 3, u = -1;
         uint32_t k = 0, vcore = 0, vwhere = 0;
-        bool park = false;
         if (active) {
             const nr_probe_t ot = probe_unpack(s_probes[(o_item >> 16) & 63u]);
             const uint32_t od = (uint32_t)ot.drop;
@@ -260,58 +242,31 @@ __device__ __forceinline__ void drain(const nr_filter_params &P, WarpSmemT<NMODE
             const int p = (int)(o_item >> 25) - 16;
             const uint2 e = __ldcg(T4.ents[od] + o_start + (g - o_excl));
             if constexpr (NMODE) {
-                // reads with N.  Rows whose diagonal walk is exact and reads no N (nr_lv_clean) are
-                // verified like rows of a plain read; the others: diagonal walk with the N rows as
-                // wildcards here (sm.rdp holds a substituted variant; the N rows ignore their base),
-                // the N-aware automaton later
-                if (nr_lv_clean(sm.nm[strand], m, p, ot)) {
-                    const int cu = verify16_call(sm.rdp[strand], m, e.y, P.padL, P.padR, p, s_probes[(o_item >> 16) & 63u]);
-                    cost = cu & 3;
-                    u = (cu >> 2) - 1;
-                } else {
-                    park = nr_prefilter16n(sm.rdp[strand], sm.nm[strand], m, e.y, p, ot);
-                    vcore = e.y;
-                    vwhere = (uint32_t)strand | ((uint32_t)(p + 16) << 1);
-                }
+                // reads with N: diagonal walk with the N rows as wildcards here (sm.rdp holds a
+                // substituted variant; the N rows ignore their base), the N-aware automaton later
+                cost = nr_prefilter16n(sm.rdp[strand], sm.nm[strand], m, e.y, p, ot) ? 0 : 3;
+                vcore = e.y;
+                vwhere = (uint32_t)strand | ((uint32_t)(p + 16) << 1);
             } else {
                 cost = nr_verify16(sm.rdp[strand], m, e.y, P.padL, P.padR, p, ot, &u);
             }
             k = (e.x << 1) | (uint32_t)strand;
-            if (COUNT) { acc.c_ver++; acc.c_pass += cost < 3; }
+            if (COUNT) { acc.c_ver++; if (!NMODE) acc.c_pass += cost < 3; }
         }
         if constexpr (NMODE) {
             // park the survivors of the wildcard walk; score them a full warp at a time
-            const uint32_t bal = __ballot_sync(0xffffffffu, park);
+            const uint32_t bal = __ballot_sync(0xffffffffu, cost < 3);
             if (bal) {
-                if (park)
+                if (cost < 3)
                     sm.vq[acc.vn + __popc(bal & ((1u << lane) - 1u))] = make_uint4(k >> 1, vcore, vwhere, 0u);
                 acc.vn += __popc(bal);
                 __syncwarp();
                 if (acc.vn > NR_VQCAP - 32) flush_vq<COUNT>(P, sm, acc, m);
             }
+        } else {
+            merge_batch(acc, cost, k, u);
         }
-        merge_batch(acc, cost, k, u);
     }
-}
-
-// The N pass is bound by instruction fetch (ncu: no_instruction is its top stall) and drain() is
-// inlined in five places of a stage: there it is one real function instead.  The kernel parameters
-// stay out of it (taking their address would copy them to local memory): pads by value.
-template <bool COUNT>
-__device__ __noinline__ void drain_n(int padL, int padR, WarpSmemN &sm, Acc &acc, int m,
-                                     const uint32_t *s_probes, const Tables &T4)
-{
-    nr_filter_params P;
-    P.padL = padL; P.padR = padR;
-    drain<COUNT, true>(P, sm, acc, m, s_probes, T4);
-}
-
-template <bool COUNT, bool NMODE>
-__device__ __forceinline__ void drain_any(const nr_filter_params &P, WarpSmemT<NMODE> &sm, Acc &acc, int m,
-                                          const uint32_t *s_probes, const Tables &T4)
-{
-    if constexpr (NMODE) drain_n<COUNT>(P.padL, P.padR, sm, acc, m, s_probes, T4);
-    else drain<COUNT, false>(P, sm, acc, m, s_probes, T4);
 }
 
 // The three "5-mer minus one base" variants of a probe differ in one kept quarter only; in the
@@ -393,20 +348,19 @@ __device__ __forceinline__ uint64_t probe_range(const uint32_t *__restrict__ bit
 template <bool COUNT, bool NMODE>
 __device__ __forceinline__ void enqueue(const nr_filter_params &P, WarpSmemT<NMODE> &sm, Acc &acc, int m,
                                         const uint32_t *s_probes, const Tables &T4, uint64_t mask,
-                                        int strand, int p, int v = 0)
+                                        int strand, int p)
 {
     const uint32_t lane = nr_lane();
     // an item with more hits than the queue holds (dense key bitmaps: whitelists of millions of
     // entries) is queued in four probe ranges of <= 9 x 32 hits
-    // item = variant (N pass, merged variant stage) | probe << 16 | strand << 24 | (slot + 16) << 25
-    const uint32_t where = (uint32_t)v | ((uint32_t)strand << 24) | ((uint32_t)(p + 16) << 25);
+    const uint32_t where = ((uint32_t)strand << 24) | ((uint32_t)(p + 16) << 25);
     const int mine_all = __popcll(mask);
     // common case: no lane holds more than one hit -> positions from one ballot
     if (!__any_sync(0xffffffffu, mine_all > 1)) {
         const uint32_t b = __ballot_sync(0xffffffffu, mine_all != 0);
         if (b == 0u) return;
         const int total = __popc(b);
-        while (acc.qn + total > NR_QCAP) drain_any<COUNT, NMODE>(P, sm, acc, m, s_probes, T4);
+        while (acc.qn + total > NR_QCAP) drain<COUNT, NMODE>(P, sm, acc, m, s_probes, T4);
         if (mine_all)
             sm.queue[acc.qn + __popc(b & ((1u << lane) - 1u))] =
                 where | ((uint32_t)(__ffsll((long long)mask) - 1) << 16);
@@ -428,7 +382,7 @@ __device__ __forceinline__ void enqueue(const nr_filter_params &P, WarpSmemT<NMO
             if ((int)lane >= o) incl += v;
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
-        while (acc.qn + total > NR_QCAP) drain_any<COUNT, NMODE>(P, sm, acc, m, s_probes, T4);
+        while (acc.qn + total > NR_QCAP) drain<COUNT, NMODE>(P, sm, acc, m, s_probes, T4);
         int pos = acc.qn + incl - mine;
         // queue item = (probe, strand, slot position); the key, its rank and its rows are worked
         // out in drain(), one hit per lane
@@ -446,57 +400,27 @@ __device__ __forceinline__ void enqueue(const nr_filter_params &P, WarpSmemT<NMO
 // -1) over all slots of both strands of the read staged in sm.rdp, drained at the end.
 // NMODE: the staged read is substituted variant `v`; slots that cannot reach a substituted N
 // position are skipped (nr_filter_core.h).
-// NMODE, `merged` (reads with ONE N): the pass runs stage `stage` of the three substituted variants
-// together instead.  Lane = (variant 1..3, strand, slot) over the slots whose probes can read the N
-// (0 <= N - p < NR_COV_SPAN); the variant's window is the staged base variant's with the base XORed
-// in (nr_nvar_window), the hits carry the variant for drain(), and probes whose key does not read
-// the N are masked (nr_nvar_probe_needed).  Same probe code as the plain pass: the N pass is
-// bound by instruction fetch, a second copy of the unrolled probes costs more than it saves.
 template <bool COUNT, bool NMODE>
 __device__ __forceinline__ void run_stage(const nr_filter_params &P, WarpSmemT<NMODE> &sm, Acc &acc, int m,
                                           const uint32_t *s_probes, const Tables &s_tab,
                                           const uint32_t *__restrict__ bits_all, int stage, int p0,
                                           int nP, bool edge, int v, int n0, int n1,
-                                          unsigned long long &c_probes_n, const uint64_t *s_cov = nullptr,
-                                          bool merged = false)
+                                          unsigned long long &c_probes_n)
 {
     const uint32_t lane = nr_lane();
     const int nslots = nP > 0 ? 2 * nP : 0;
-    // merged: slots lo0..hi0 of the forward strand, lo1..hi1 of the reverse strand, per variant
-    int lo0 = 0, lo1 = 0, cnt0 = 0, per = 1, nitems = nslots;
-    const int pos0 = n0, pos1 = m - 1 - n0;                  // the (first) N on either strand
-    if (NMODE && merged) {
-        const int p1 = p0 + nP - 1;
-        lo0 = max(p0, pos0 - (NR_COV_SPAN - 1));
-        lo1 = max(p0, pos1 - (NR_COV_SPAN - 1));
-        cnt0 = max(0, min(p1, pos0) - lo0 + 1);
-        per = cnt0 + max(0, min(p1, pos1) - lo1 + 1);
-        nitems = 3 * per;
-        if (per == 0) per = 1;
-    }
-    const int nchunks = (nitems + 31) >> 5;
+    const int nchunks = (nslots + 31) >> 5;
 #pragma unroll 1
     for (int item = 0; item < nchunks; item++) {
         const int slot = item * 32 + (int)lane;
-        bool slot_ok = slot < nitems;
-        int strand, p, lv = 0, rel = 0;
-        if (NMODE && merged) {
-            const int vi = slot_ok ? slot / per : 0;
-            const int rem = slot - vi * per;
-            lv = slot_ok ? vi + 1 : 0;
-            strand = rem >= cnt0 ? 1 : 0;
-            p = strand ? lo1 + rem - cnt0 : lo0 + rem;
-            rel = (strand ? pos1 : pos0) - p;                 // 0 .. NR_COV_SPAN - 1 when slot_ok
-        } else {
-            strand = slot >= nP ? 1 : 0;
-            p = p0 + slot - strand * nP;
-            if (NMODE && v != 0)
-                slot_ok = slot_ok && nr_nvar_slot_needed(v, p, strand ? m - 1 - n0 : n0,
-                                                         n1 < 0 ? -100 : (strand ? m - 1 - n1 : n1));
-        }
+        bool slot_ok = slot < nslots;
+        const int strand = slot >= nP ? 1 : 0;
+        const int p = p0 + slot - strand * nP;
+        if (NMODE && v != 0)
+            slot_ok = slot_ok && nr_nvar_slot_needed(v, p, strand ? m - 1 - n0 : n0,
+                                                     n1 < 0 ? -100 : (strand ? m - 1 - n1 : n1));
         if (NMODE && !__any_sync(0xffffffffu, slot_ok)) continue;
-        uint64_t W = slot_ok ? nr_window64(sm.rdp[strand], p) : 0ull;
-        if (NMODE && merged && slot_ok) W ^= (uint64_t)lv << (2 * rel);
+        const uint64_t W = slot_ok ? nr_window64(sm.rdp[strand], p) : 0ull;
         uint64_t mask;
         if (stage == 0) {
             mask = probe_range<0>(bits_all, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_COST0>{});
@@ -508,17 +432,9 @@ __device__ __forceinline__ void run_stage(const nr_filter_params &P, WarpSmemT<N
             mask = probe_range<NR_PROBES_COST1>(bits_all, W, slot_ok, std::make_integer_sequence<int, NR_PROBES_MAIN - NR_PROBES_COST1>{});
             if (COUNT) c_probes_n += slot_ok ? NR_PROBES_MAIN - NR_PROBES_COST1 : 0;
         }
-        if (NMODE && merged) {
-            mask &= slot_ok ? s_cov[rel] : 0ull;
-        } else if (NMODE && v != 0) {
-            // probes whose key does not read a substituted position only repeat an earlier lookup
-            const int a0 = (strand ? m - 1 - n0 : n0) - p, a1 = n1 < 0 ? -1 : (strand ? m - 1 - n1 : n1) - p;
-            if ((v & 3) != 0) mask &= (a0 >= 0 && a0 < NR_COV_SPAN) ? s_cov[a0] : 0ull;
-            if ((v >> 2) != 0) mask &= (a1 >= 0 && a1 < NR_COV_SPAN) ? s_cov[a1] : 0ull;
-        }
-        enqueue<COUNT, NMODE>(P, sm, acc, m, s_probes, s_tab, mask, strand, p, lv);
+        enqueue<COUNT, NMODE>(P, sm, acc, m, s_probes, s_tab, mask, strand, p);
     }
-    if (stage == 2 && edge && !(NMODE && merged)) {
+    if (stage == 2 && edge) {
         // one-column start overhang + interior insertion (slot -1 only)
         uint64_t mask = 0;
         const int strand = lane >= NR_PROBES_EDGE ? 1 : 0;
@@ -533,7 +449,7 @@ __device__ __forceinline__ void run_stage(const nr_filter_params &P, WarpSmemT<N
         }
         enqueue<COUNT, NMODE>(P, sm, acc, m, s_probes, s_tab, mask, strand, -1);
     }
-    while (acc.qn > 0) drain_any<COUNT, NMODE>(P, sm, acc, m, s_probes, s_tab);
+    while (acc.qn > 0) drain<COUNT, NMODE>(P, sm, acc, m, s_probes, s_tab);
 }
 
 // stage both strands of the packed read w4, padded, in shared memory
@@ -562,15 +478,6 @@ nr_match_filtered_kernel(const nr_filter_params P)
     __shared__ WarpSmemT<NMODE> smem[NR_FWARPS];
     __shared__ uint32_t s_probes[64];
     __shared__ Tables s_tab;
-    // N pass: for every position r relative to a slot, the probes whose key reads base p + r
-    __shared__ uint64_t s_cov[NMODE ? NR_COV_SPAN : 1];
-    if (NMODE && threadIdx.x >= 64 && threadIdx.x < 64 + NR_COV_SPAN) {
-        const int r = (int)threadIdx.x - 64;
-        uint64_t c = 0;
-        for (int T = 0; T < NR_PROBES_ALL; T++)
-            if ((nr_probe_cover(c_probes[T]) >> r) & 1u) c |= 1ull << T;
-        s_cov[r] = c;
-    }
     if (threadIdx.x < 64)
         s_probes[threadIdx.x] = threadIdx.x < NR_PROBES_ALL ? probe_pack(c_probes[threadIdx.x]) : 0u;
     if (threadIdx.x < 4) {
@@ -675,27 +582,18 @@ nr_match_filtered_kernel(const nr_filter_params P)
                     const int n1 = n_n == 2 ? 63 - __clzll((long long)nm) : -1;
                     if (lane == 0) { sm.nm[0] = nm; sm.nm[1] = __brevll(nm) >> (64 - m); }
                     const int nvar = nr_nvar_count(n_n);
-                    // Passes of a round.  One N (nearly every read here): the base variant, staged
-                    // once, runs stage `round`, then the three substituted variants run stage
-                    // `round - 1` together (merged pass of run_stage).  Two N: variant v runs stage
-                    // `round - z(v)` on its own staged copy.
 #pragma unroll 1
                     for (int round = 0; round < 3; round++) {
                         if (acc.best < round) break;
-                        const int npass = n_n == 1 ? (round >= 1 ? 2 : 1) : nvar;
 #pragma unroll 1
-                        for (int ps = 0; ps < npass; ps++) {
-                            const bool merged = n_n == 1 && ps == 1;
-                            const int v = n_n == 1 ? 0 : ps;
-                            const int stage = merged ? round - 1 : round - nr_nvar_nonzero(v);
+                        for (int v = 0; v < nvar; v++) {
+                            const int stage = round - nr_nvar_nonzero(v);
                             if (stage < 0) continue;
-                            if (n_n == 2 || (round == 0 && ps == 0)) {
-                                uint32_t wv[4];
-                                nr_nvar_apply(w4, n0, n1, v, wv);
-                                stage_read(sm, wv, m);
-                            }
+                            uint32_t wv[4];
+                            nr_nvar_apply(w4, n0, n1, v, wv);
+                            stage_read(sm, wv, m);
                             run_stage<COUNT, true>(P, sm, acc, m, s_probes, s_tab, bits_all, stage, p0,
-                                                   nP, edge, v, n0, n1, c_probes_n, s_cov, merged);
+                                                   nP, edge, v, n0, n1, c_probes_n);
                         }
                         // the rows parked by all variants of the round (any variant's bases serve:
                         // variants differ at the N rows only, and those ignore their base)

@@ -95,9 +95,6 @@ void run_stage(const Index &ix, const uint32_t *wl, const uint32_t rdp[2][NR_RDP
                 for (int t = t0; t < t1; t++) {
                     const nr_probe_t &pr = NR_PROBES[t];
                     if (p + nr_probe_first(pr) < 0 || p + nr_probe_end(pr) > m) continue;
-                    if (nmode && v != 0 &&
-                        !nr_nvar_probe_needed(v, p, pr, s ? m - 1 - n0 : n0, n1 < 0 ? -100 : (s ? m - 1 - n1 : n1)))
-                        continue;
                     const uint32_t key = nr_probe_key(W, pr);
                     const int d = pr.drop;
                     const uint32_t bw = ix.bits[d][key >> 5];

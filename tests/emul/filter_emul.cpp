@@ -220,11 +220,6 @@ int nr_emul_filtered_n(const uint32_t *wl, int64_t n, int padL, int padR, const 
         std::map<uint32_t, std::pair<int, int>> found;
         int best = 3;
         const int p0 = nr_slot_first(m, padR), p1 = nr_slot_last(m, padL);
-        uint32_t wb[2][4], rdp0[2][NR_RDP_WORDS];      // the base variant (base 0 at every N)
-        nr_nvar_apply(w0, n0, n1, 0, wb[0]);
-        nr_revcomp4(wb[0], m, wb[1]);
-        pad_read(wb[0], rdp0[0]);
-        pad_read(wb[1], rdp0[1]);
         for (int round = 0; round < 3; round++) {
             if (best < round) break;
             for (int v = 0; v < nr_nvar_count(n_n); v++) {
@@ -249,9 +244,6 @@ int nr_emul_filtered_n(const uint32_t *wl, int64_t n, int padL, int padR, const 
                             for (int t = t0; t < t1; t++) {
                                 const nr_probe_t &pr = NR_PROBES[t];
                                 if (p + nr_probe_first(pr) < 0 || p + nr_probe_end(pr) > m) continue;
-                                if (!nr_nvar_probe_needed(v, p, pr, n0s, n1s)) continue;
-                                // the kernel derives a variant's window from the base variant's
-                                if (nr_nvar_window(nr_window64(rdp0[s], p), p, v, n0s, n1s) != W) return -7;
                                 const uint32_t key = nr_probe_key(W, pr);
                                 counters[0]++;
                                 const uint32_t bw = ix.bits[pr.drop][key >> 5];
