@@ -28,6 +28,7 @@ import pandas as pd
 
 from . import fastx, samio
 from ._lib import NR_FLAG_RC, NR_FLAG_TOO_LONG, NR_MODE_AUTO, NR_UMI_NONE
+from .h5lite import read_10x_h5_barcodes
 from .matcher import Whitelist
 from .whitelists import LINKER_SLIDESEQ
 
@@ -57,12 +58,10 @@ def _read_bc_table(bc_file):
 
 def write_bc_5p10X(sample, outdir, bc_file):
     """utils.py:604-622: `N`*30 + barcode + `N`*40 per whitelist line (text lists; `-1`
-    suffixes stripped).  `.h5` inputs need scanpy, which the reference imports lazily too."""
+    suffixes stripped).  `.h5` inputs (:606-610: `sc.read_10x_h5` + `sc.pp.filter_cells(min_genes=20)`,
+    first 16 characters of the cell names) are read by nanoranger_b200.h5lite -- no scanpy / h5py."""
     if ".h5" in bc_file:
-        import scanpy as sc   # noqa: F401  (absent here: raises ImportError like the reference would)
-        adata = sc.read_10x_h5(bc_file)
-        sc.pp.filter_cells(adata, min_genes=20)
-        bcs = [a[:16] for a in adata.obs.index]
+        bcs = [a[:16] for a in read_10x_h5_barcodes(bc_file, 20)]
     elif ".txt" in bc_file:
         bcs = _read_bc_table(bc_file).bc.apply(lambda x: x.split("-")[0]).to_list()
     else:
@@ -85,11 +84,9 @@ def write_bc_slideseq(sample, outdir, bc_file):
 
 
 def write_bc_3p10XTCR_nuc(sample, outdir, bc_file):
-    """utils.py:1116-1132: cells of a 10x .h5 with >= 4 genes, N*16 + bc + N*28."""
-    import scanpy as sc   # noqa: F401
-    adata = sc.read_10x_h5(bc_file)
-    sc.pp.filter_cells(adata, min_genes=4)
-    bcs = [a[:16] for a in adata.obs.index]
+    """utils.py:1116-1132: cells of a 10x .h5 with >= 4 genes (`sc.read_10x_h5` +
+    `sc.pp.filter_cells(min_genes=4)` there; nanoranger_b200.h5lite here), N*16 + bc + N*28."""
+    bcs = [a[:16] for a in read_10x_h5_barcodes(bc_file, 4)]
     _write_padded(f"{outdir}/{sample}_bcreads.fasta", bcs, bcs, 16, 28)
 
 
