@@ -51,17 +51,22 @@ class Writer:
         arr = np.ascontiguousarray(arr)
         assert arr.ndim == 1
         dt = arr.dtype
-        msgs = [self._msg(1, struct.pack("<BBBx4x", 1, 1, 0) + struct.pack("<Q", len(arr))), self._msg(3, self._dtype_msg(dt))]
+        # chunked datasets are extendible, as PyTables / Cell Ranger write them: maximum dimensions present
+        space = struct.pack("<BBBx4x", 1, 1, 1 if chunks else 0) + struct.pack("<Q", len(arr))
+        if chunks:
+            space += struct.pack("<Q", UNDEF)
+        msgs = [self._msg(1, space), self._msg(3, self._dtype_msg(dt))]
         if chunks is None:
             addr = self.alloc(arr.tobytes()) if len(arr) else UNDEF
             msgs.append(self._msg(8, struct.pack("<BBQQ", 3, 1, addr, arr.nbytes)))
             return self._ohdr(msgs)
         filt = b""
         nf = 0
+        # filter descriptions as libhdf5 writes them: with the filter's name, padded to 8 bytes
         if shuffle:
-            filt += struct.pack("<HHHHI4x", 2, 0, 0, 1, dt.itemsize); nf += 1
+            filt += struct.pack("<HHHH8sI4x", 2, 8, 1, 1, b"shuffle\0", dt.itemsize); nf += 1
         if level:
-            filt += struct.pack("<HHHHI4x", 1, 0, 0, 1, level); nf += 1
+            filt += struct.pack("<HHHH8sI4x", 1, 8, 1, 1, b"deflate\0", level); nf += 1
         if nf:
             msgs.append(self._msg(0x0B, struct.pack("<BB6x", 1, nf) + filt))
         entries = []
