@@ -129,6 +129,26 @@ def exchange_records(rec_t, send_counts, group=None):
     return out
 
 
+def score_histogram(score, nbest, flags, group=None):
+    """AS histogram of the records STAR would write with flag 0 (unique best pair on the forward
+    strand, any score: what `_barcode_scores.csv` counts, reference utils.py:698, 728-730) as 64
+    int64 bins over AS 0..63, summed over the ranks of `group` when torch.distributed is
+    initialised (the barcode match needs no other collective).  score / nbest / flags:
+    this rank's shard as torch tensors (any device)."""
+    import torch
+    from ._lib import NR_FLAG_RC, NR_FLAG_TOO_LONG, NR_SCORE_BELOW
+    flags = flags.to(torch.int32)
+    sc = score.to(torch.int64)
+    # NR_FLAG_BELOW alone does not exclude a record (AUTO resolves it, with its true score);
+    # unresolved scores of NR_MODE_FILTERED carry NR_SCORE_BELOW and are not records
+    keep = (nbest == 1) & ((flags & (NR_FLAG_RC | NR_FLAG_TOO_LONG)) == 0) & (sc != NR_SCORE_BELOW) & (sc >= 0)
+    h = torch.bincount(sc[keep].clamp(max=63), minlength=64)[:64]
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(h, group=group)
+    return h
+
+
 def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
     """contiguous candidate shard of a rank (keeps output order)."""
     per = (n + world - 1) // world

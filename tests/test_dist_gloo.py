@@ -49,6 +49,16 @@ def _worker(rank, world, port, tmp):
     dist.all_reduce(t)
     k_global, _ = O.umi_cluster(bc, gene, um, 1)
     assert int(t.item()) == k_global                      # partitioning by barcode loses nothing
+    # AS histogram of the flag-0 records, summed over the ranks (the match's only collective)
+    from nanoranger_b200._lib import NR_FLAG_RC, NR_SCORE_BELOW
+    score = rng.integers(5, 17, n).astype(np.int8)
+    score[::13] = NR_SCORE_BELOW
+    nbest = rng.integers(1, 3, n).astype(np.uint8)
+    flags = np.where(rng.random(n) < 0.1, NR_FLAG_RC, 0).astype(np.uint8)
+    h = umi.score_histogram(torch.from_numpy(score[lo:hi]), torch.from_numpy(nbest[lo:hi]),
+                            torch.from_numpy(flags[lo:hi])).numpy()
+    keep = (nbest == 1) & (flags == 0) & (score != NR_SCORE_BELOW)
+    assert np.array_equal(h, np.bincount(score[keep].astype(np.int64), minlength=64))
     np.save(os.path.join(tmp, f"ok{rank}.npy"), np.array([hi - lo]))
     dist.destroy_process_group()
 
