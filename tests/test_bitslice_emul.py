@@ -106,3 +106,25 @@ def test_bitslice_32_slideseq_geometry(emul, with_n):
     cands = mixed_candidates(rng, [w.replace("N", "C") for w in wl], 40, 15, 60, with_n=0.2)
     cands += [rs(rng, int(k)) for k in (1, 5, 31, 32, 33, 64)]
     run_all_pairs(emul, O, wl, cands, 15, 24)
+
+
+def test_bitslice_golden_slideseq_fixture(emul):
+    """the reference's own slide-seq list (17 753 x 32 columns, 2 584 entries with N) and reads cut
+    from its sample FASTQ (tests/golden, make_golden.py): every pair's AS equals the oracle's and
+    best / ties / smallest entry / strand equal the committed golden answers"""
+    import gzip
+    from oracle import oracle as O
+    from nanoranger_b200.whitelists import LINKER_SLIDESEQ
+    G = os.path.join(HERE, "golden")
+    bcs = gzip.open(os.path.join(G, "slideseq_whitelist.txt.gz"), "rt").read().split()
+    wl = [b[:8] + LINKER_SLIDESEQ + b[8:] for b in bcs]
+    seqs = [ln.strip() for ln in gzip.open(os.path.join(G, "slideseq.fa.gz"), "rt") if not ln.startswith(">")]
+    gold = np.load(os.path.join(G, "slideseq.oracle.npz"))
+    pick = list(range(0, len(seqs), max(1, len(seqs) // 12)))[:12]
+    run_all_pairs(emul, O, wl, [seqs[i] for i in pick], int(gold["pad_l"]), int(gold["pad_r"]))
+    # run_all_pairs compared with the oracle computed now; the committed answers agree with it
+    wlc, _ = O.encode_many(wl, 32)
+    cc, cl = O.encode_many([seqs[i] for i in pick], 64)
+    ref = O.match(wlc, int(gold["pad_l"]), int(gold["pad_r"]), cc, cl)
+    for k in ("best_idx", "best_score", "n_best", "strand"):
+        assert np.array_equal(ref[k], gold[k][pick]), k
