@@ -121,6 +121,17 @@ class Writer:
         oh = self._ohdr([self._msg(0x11, struct.pack("<QQ", taddr, haddr))])
         return oh, taddr, haddr
 
+    def group2(self, members: dict[str, int]) -> tuple[int, int, int]:
+        """the same group in the HDF5 1.8 style: object header v2 with a link-info message (no
+        fractal heap: compact storage) and one link message per member"""
+        body = b"\x02" + struct.pack("<HB", 18, 0) + struct.pack("<BBQQ", 0, 0, UNDEF, UNDEF)
+        for n in sorted(members):
+            nb = n.encode()
+            link = struct.pack("<BBB", 1, 0, len(nb)) + nb + struct.pack("<Q", members[n])
+            body += b"\x06" + struct.pack("<HB", len(link), 0) + link
+        hdr = b"OHDR" + struct.pack("<BBH", 2, 0x01, len(body)) + body + b"\0\0\0\0"      # checksum not verified by the reader
+        return self.alloc(hdr), UNDEF, UNDEF
+
     def finish(self, root: tuple[int, int, int]) -> bytes:
         oh, taddr, haddr = root
         sb = b"\x89HDF\r\n\x1a\n" + struct.pack("<BBBxBBBxHHI", 0, 0, 0, 0, 8, 8, 4, 16, 0)
@@ -132,7 +143,7 @@ class Writer:
 
 
 def write_10x(path: str, barcodes: list[str], n_genes_per_cell: list[int], n_features: int = 50, version: int = 3,
-              userblock: int = 0, explicit_zeros: int = 0, chunks: int = 7, seed: int = 0):
+              userblock: int = 0, explicit_zeros: int = 0, chunks: int = 7, seed: int = 0, new_groups: bool = False):
     """A Cell Ranger style matrix file: CSC over barcodes under /matrix (version 3) or /GRCh38
     (version 2).  Cell j gets n_genes_per_cell[j] entries > 0 plus `explicit_zeros` stored zeros."""
     rng = np.random.default_rng(seed)
@@ -152,6 +163,13 @@ def write_10x(path: str, barcodes: list[str], n_genes_per_cell: list[int], n_fea
         "indptr": w.dataset(np.array(indptr, np.int64), chunks=chunks, level=0),
         "shape": w.dataset(np.array([n_features, len(barcodes)], np.int32)),
     }
-    grp = w.group(ds)
-    root = w.group({"matrix" if version == 3 else "GRCh38": grp[0]})
+    mk = w.group2 if new_groups else w.group
+    grp = mk(ds)
+    root = mk({"matrix" if version == 3 else "GRCh38": grp[0]})
+    if new_groups:
+        # superblock 2: signature, version, sizes, flags, base, extension, end of file, root header, checksum
+        sb = b"\x89HDF\r\n\x1a\n" + struct.pack("<BBBB", 2, 8, 8, 0) + struct.pack("<QQQQ", userblock, UNDEF, len(w.buf), root[0]) + b"\0" * 4
+        w.buf[:len(sb)] = sb
+        open(path, "wb").write(b"\0" * userblock + bytes(w.buf))
+        return
     open(path, "wb").write(w.finish(root))

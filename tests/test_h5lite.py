@@ -50,6 +50,19 @@ def test_10x_barcodes_filter_cells(tmp_path, version, userblock, zeros):
         assert got == [b for b, g in zip(bcs, genes) if g >= thr]
 
 
+def test_10x_new_style_groups(tmp_path):
+    """superblock 2, object headers v2 with link messages (HDF5 1.8 'latest' groups, compact)"""
+    rng = np.random.default_rng(9)
+    bcs = _barcodes(rng, 21)
+    genes = [int(g) for g in rng.integers(0, 30, len(bcs))]
+    p = str(tmp_path / "n.h5")
+    write_10x(p, bcs, genes, new_groups=True)
+    with H5Lite(p) as f:
+        assert list(f.members()) == ["matrix"]
+        assert sorted(f.members(f.lookup("matrix"))) == ["barcodes", "data", "indices", "indptr", "shape"]
+    assert read_10x_h5_barcodes(p, 4) == [b for b, g in zip(bcs, genes) if g >= 4]
+
+
 def test_write_bc_from_h5(tmp_path):
     """W1's .h5 branch and W3: cells with >= 20 / >= 4 genes, first 16 characters, pads 30/40 and
     16/28 (reference utils.py:606-622, 1116-1132), byte for byte."""
